@@ -1,0 +1,212 @@
+/*
+ * vsiq.h -- C ABI of libvsiq.so: the B200 (sm_100a) fake-quantization hot path.
+ *
+ * The reference (tranngocduvnvp/VSIQuantization) is pure Python/PyTorch and has
+ * no FFI of its own; its boundary for this path is the duck-typed plugin
+ * registry (utils/registry.py:5-27) whose plugins call ATen.  These entry
+ * points are what a binding for that path binds instead of the ATen op chains:
+ * each declaration cites the reference code it replaces.  The Python host side
+ * (vsiquantization_b200/) loads this library with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every tensor pointer is DEVICE memory
+ *     (fp32 unless stated) owned by the caller, except in the *_host entry.
+ *   - every call is asynchronous on the given stream (a cudaStream_t passed as
+ *     void*), allocates nothing (scratch comes in as `workspace`), keeps no
+ *     global mutable state and is re-entrant across streams and devices.
+ *     Workspaces must not be shared by calls running concurrently on
+ *     different streams.  A workspace must be zero-filled once when it is
+ *     allocated; every call leaves it zero-filled where it needs it to be.
+ *   - return value: 0 on success, a positive cudaError_t, or a negative
+ *     VSIQ_ERR_* code.  Nothing throws; there is no CPU fallback.
+ *   - outputs must not alias inputs.
+ *   - layout: a contiguous tensor is described as [outer, channels, inner];
+ *     the channel of flat index i is (i / inner) % channels.
+ *       per tensor             outer = 1, channels = 1,        inner = numel
+ *       per channel, ch_axis 0 outer = 1, channels = shape[0], inner = numel / shape[0]   (OIHW weights)
+ *       per channel, ch_axis 1 outer = N, channels = shape[1], inner = H*W                (NCHW activations)
+ *   - arithmetic: fp32, every operation individually rounded (IEEE division,
+ *     no FMA contraction, round-half-even) so results are bit-identical to the
+ *     reference's ATen-on-CPU composition; sums are accumulated in fp64.
+ */
+#ifndef VSIQ_H_
+#define VSIQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSIQ_VERSION 100 /* major*1000 + minor*100 + patch */
+
+typedef void *vsiq_stream_t; /* cudaStream_t */
+
+enum {
+    VSIQ_OK = 0,
+    VSIQ_ERR_INVALID_ARG = -1, /* null pointer, negative size, bits outside 2..8, qmin >= qmax ... */
+    VSIQ_ERR_WORKSPACE = -2,   /* workspace missing or smaller than *_workspace_bytes() */
+    VSIQ_ERR_UNSUPPORTED = -3, /* combination not implemented (reported, never silently ignored) */
+    VSIQ_ERR_NO_DEVICE = -4    /* no sm_100 device / driver */
+};
+
+enum { VSIQ_F32 = 0, VSIQ_F64 = 1 };
+
+/* mask semantics of the LSQ backward */
+enum {
+    VSIQ_MASK_ROUNDED = 0, /* reference autograd: qmin <= rint(x/s+z) <= qmax, inclusive (uniform.py:54,95) */
+    VSIQ_MASK_FUNLSQ = 1   /* reference dead code FunLSQ: strict bounds on the unrounded x/s (uniform.py:144-150) */
+};
+
+typedef struct vsiq_layout {
+    int64_t outer;
+    int64_t channels;
+    int64_t inner;
+} vsiq_layout;
+
+/* Quantisation parameters: `channels` entries each (1 for per tensor).
+ * scale / zero_point are DEVICE pointers of the stated dtype (the reference's learned scale is a
+ * 0-dim float64 Parameter, quantization_manager.py:99; it is rounded to fp32 before use exactly as
+ * ATen does).  A NULL pointer selects the host scalar instead (the reference's Python float / int
+ * qparams of the non-learning mode, quantization_manager.py:69-71).
+ * zp_learned = 1: zero_point holds the float parameter z_f and the forward uses
+ * clamp(rint(z_f), qmin, qmax) (uniform.py:98-102, lsq_module.py:354-358). */
+typedef struct vsiq_qparams {
+    const void *scale;
+    const void *zero_point;
+    int32_t scale_dtype;
+    int32_t zp_dtype;
+    float scale_host;
+    float zp_host;
+    int32_t zp_learned;
+    int32_t qmin;
+    int32_t qmax;
+} vsiq_qparams;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int vsiq_version(void);
+const char *vsiq_error_string(int code);
+/* SM count and compute capability of the current device (VSIQ_ERR_NO_DEVICE without one). */
+int vsiq_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- (3) fake-quant forward ---------------------------------------------------------------
+ * y = (clamp(rint(x / s + z), qmin, qmax) - z) * s
+ * replaces UniformQuantizer.quantize / discreate_tensor (quantizers/uniform.py:54-55, :95) and
+ * LSQFakeQuantize.fake_quantize_per_{tensor,channel}_affine (quantizers/lsq_module.py:220-274).
+ * codes (optional, may be NULL): the integer codes as int8 (qmin < 0) or uint8 (qmin >= 0) bytes;
+ * the reference only ever holds them as floats (uniform.py:54). */
+int vsiq_fake_quant_fwd(const float *x, float *y, void *codes, const vsiq_layout *layout,
+                        const vsiq_qparams *qp, vsiq_stream_t stream);
+
+/* ---- (3) STE backward ---------------------------------------------------------------------
+ * dx = ((g * s) * m) / s,  m = [qmin <= rint(x/s+z) <= qmax]  -- the autograd graph of the forward
+ * through RoundStraightThrough (quantizers/uniform.py:258-271) and torch.clamp; no qparam grads. */
+int vsiq_fake_quant_bwd_ste(const float *x, const float *g, float *dx, const vsiq_layout *layout,
+                            const vsiq_qparams *qp, vsiq_stream_t stream);
+
+/* ---- (4) LSQ backward ---------------------------------------------------------------------
+ * One pass over (x, g): dx as above plus the per-channel step-size and zero-point gradients
+ *   dscale[c] = gs * sum g * ((q - z) - m * x/s)
+ *   dzp[c]    = gs * [qmin <= rint(z_f) <= qmax] * sum (g*s) * (m - 1)         (dzp may be NULL)
+ * replacing autograd over quantizers/uniform.py:47-55 + ScaleGradient (:242-255) and
+ * quantizers/lsq_module.py:147-173, :317-340.  gs = grad_scale_host * (grad_scale_dev ? *grad_scale_dev : 1)
+ * (the caller computes (qmax * numel / channels) ** -0.5 [* calib_grad_scale, * 5000]).
+ * dscale / dzp: `channels` entries of the stated dtype, OVERWRITTEN (not accumulated).
+ * Deterministic: fixed-order fp64 combination of per-tile partials (no floating-point atomics). */
+size_t vsiq_lsq_bwd_workspace_bytes(const vsiq_layout *layout);
+int vsiq_lsq_bwd(const float *x, const float *g, float *dx, void *dscale, int dscale_dtype, void *dzp,
+                 int dzp_dtype, const vsiq_layout *layout, const vsiq_qparams *qp, double grad_scale_host,
+                 const float *grad_scale_dev, int mask_mode, void *workspace, size_t workspace_bytes,
+                 vsiq_stream_t stream);
+
+/* ---- (1)+(2) observer ---------------------------------------------------------------------
+ * One pass over x producing, per channel, {min, max, sum|x|, sum x, sum x^2} (fp64; min/max are the
+ * exact fp32 extrema, NaN if the channel holds a NaN, like torch.min/max) -- replaces
+ * MinMaxObserver.observe (observers/minmax.py:42-43) and the three extra reductions of
+ * QuantizationManager.collect_qparameter (quantizers/quantization_manager.py:66-68): five passes
+ * and five host syncs become one pass and none.
+ *
+ * stats (optional): [channels][VSIQ_STATS_WIDTH] fp64, this call only.
+ * state (optional): [channels][VSIQ_STATE_WIDTH] fp64 running observer state, updated in the same
+ *   launch: running min/max with the reference's rule (a NaN call extremum never updates,
+ *   minmax.py:44-47; the state starts at 0, :28-29), then scale / zero-point from the running
+ *   extrema exactly as get_scale_zero_point computes them in Python doubles (minmax.py:67-74), and
+ *   the per-call means the LSQ initialisation needs (quantization_manager.py:66,112). */
+#define VSIQ_STATS_WIDTH 5 /* min, max, sum|x|, sum x, sum x^2 */
+#define VSIQ_STATE_WIDTH 8 /* run_min, run_max, scale, zero_point, n_calls, sum mean|x|, sum mean x, sum std */
+size_t vsiq_observe_workspace_bytes(const vsiq_layout *layout);
+int vsiq_observe(const float *x, const vsiq_layout *layout, double *stats, double *state, int bits,
+                 int symmetric, double eps, void *workspace, size_t workspace_bytes, vsiq_stream_t stream);
+
+/* scale / zero-point for n observers at once from their running extrema (after an all-reduce MIN/MAX
+ * of the packed state, see parallel.py): state is [n][VSIQ_STATE_WIDTH]; columns 2,3 are rewritten.
+ * bits / symmetric: one entry per observer (device int32 arrays) -- observers/minmax.py:67-74. */
+int vsiq_qparams_from_minmax(double *state, int64_t n, const int32_t *bits, const int32_t *symmetric,
+                             double eps, vsiq_stream_t stream);
+
+/* LSQ step-size initialisation 2 * mean(mean|x|) / sqrt(2^(bits-1) - 1) from the running state
+ * (quantizers/quantization_manager.py:112), written to scale_out[channels] of the stated dtype. */
+int vsiq_lsq_init_scale(const double *state, int64_t channels, int bits, void *scale_out, int scale_dtype,
+                        vsiq_stream_t stream);
+
+/* ---- (5) Conv/Linear + BN fold (+ weight fake-quant) ---------------------------------------
+ * t = gamma / sqrt(var + eps);  W' = W * t[c];  b' = beta + (b - mean) * t   (b = 0 if bias NULL)
+ * replaces ConvBnReLU.__init__ modules/fused.py:98-108 and LinearBnReLU.__init__ :292-300.
+ * W is [channels, inner].  b_out may be NULL.
+ * Wq_out (optional): the fake-quantised folded weight in the same pass; qp must be non-NULL when Wq_out
+ * is, with qp_channels = 1 (per tensor) or = channels (per channel, ch_axis 0) entries.
+ * stats (optional, needs workspace): per-tensor {min,max,sum|x|,sum x,sum x^2} of W' from the same
+ * pass, to seed the weight observer without re-reading W'. */
+size_t vsiq_bn_fold_workspace_bytes(int64_t channels, int64_t inner);
+int vsiq_bn_fold(const float *W, const float *bias, const float *gamma, const float *beta, const float *mean,
+                 const float *var, float eps, int64_t channels, int64_t inner, float *W_out, float *b_out,
+                 float *Wq_out, const vsiq_qparams *qp, int64_t qp_channels, double *stats, void *workspace,
+                 size_t workspace_bytes, vsiq_stream_t stream);
+
+/* ---- (6) BN statistics re-estimation ------------------------------------------------------
+ * utils/estimate_bn.py:56-99.  The per-batch moments of a conv output [N, C, H*W] come from
+ * vsiq_observe(per channel, ch_axis 1): stats[c] = {.., sum x, sum x^2}.  Optionally all-reduce(SUM)
+ * the stats over ranks (SyncBN-style), then:
+ *   bn_moments_finalize: mean = sum/n, var_b = max(sumsq/n - mean^2, 0), var_u = var_b * n/(n-1)
+ *       batch_mean / batch_var_biased / batch_var_unbiased (each optional) <- this batch
+ *       mean_sum += mean; var_sum += var_u                  (estimate_bn.py:86-87; optional)
+ *   bn_reestimate_finish: running_mean = mean_sum / k; running_var = var_sum / k   (:96-97) */
+int vsiq_bn_moments_finalize(const double *stats, double count, int64_t channels, float *batch_mean,
+                             float *batch_var_biased, float *batch_var_unbiased, float *mean_sum,
+                             float *var_sum, vsiq_stream_t stream);
+int vsiq_bn_reestimate_finish(const float *mean_sum, const float *var_sum, int64_t batch_count,
+                              float *running_mean, float *running_var, int64_t channels,
+                              vsiq_stream_t stream);
+
+/* ---- host-buffer pipeline (end-to-end entry) ----------------------------------------------
+ * Forward + STE backward of one per-tensor quantiser over HOST buffers: x, g -> y, dx.  The range is
+ * cut into chunks that flow H2D -> fused kernel -> D2H on `n_slots` streams so the three stages
+ * overlap.  Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory);
+ * pageable memory works but serialises.  The handle owns its device staging buffers and streams
+ * (the only entry points that allocate).  fwd_bwd returns after everything has landed in y / dx. */
+typedef struct vsiq_host_pipeline vsiq_host_pipeline;
+int vsiq_host_pipeline_create(vsiq_host_pipeline **out, int64_t chunk_elems, int n_slots);
+int vsiq_host_pipeline_destroy(vsiq_host_pipeline *p);
+int vsiq_host_pipeline_fwd_bwd(vsiq_host_pipeline *p, const float *x_host, const float *g_host, float *y_host,
+                               float *dx_host, int64_t n, float scale, float zero_point, int qmin, int qmax);
+/* number of kernels the last fwd_bwd call launched (for launch accounting) */
+int64_t vsiq_host_pipeline_last_launches(const vsiq_host_pipeline *p);
+
+/* fused forward + STE backward on DEVICE buffers (what the pipeline launches per chunk):
+ * one read of x and g, one write of y and dx -- 16 B/element instead of 20. */
+int vsiq_fake_quant_fwd_bwd(const float *x, const float *g, float *y, float *dx, const vsiq_layout *layout,
+                            const vsiq_qparams *qp, vsiq_stream_t stream);
+
+/* ---- self-test ---------------------------------------------------------------------------
+ * The kernels divide by the (tile-uniform) scale through a hoisted correctly-rounded reciprocal and
+ * two exact-residual FMA corrections instead of the per-element IEEE division sequence.  This entry
+ * counts, over ALL 2^32 bit patterns of x, how often that differs from IEEE x / s (expected: 0);
+ * *mismatches_dev (device, zero it first) receives the count. */
+int vsiq_selftest_division(float s, unsigned long long *mismatches_dev, vsiq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSIQ_H_ */

@@ -1,0 +1,372 @@
+"""Parity of the CUDA kernels (through the C ABI) against the CPU oracle and the reference's golden vectors.
+
+Bit-exact: fake-quantised values, integer codes, dx, observer min/max, scales / zero-points, BN fold.
+Tolerance (stated per test): order-dependent sums -- ds, dz, observer means, BN moments.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import bits_equal, first_mismatch, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vsiquantization_b200 import ops as _ops
+    return _ops
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+def sum_mass(x, g, s, z, qmin, qmax):
+    s32 = np.float32(s)
+    with np.errstate(all="ignore"):
+        v = x.astype(np.float32) / s32
+        q = np.clip(np.rint(v + np.float32(z)), qmin, qmax)
+        return float(np.sum(np.abs(g.astype(np.float64) * (q - z))) + np.sum(np.abs(g.astype(np.float64) * v)))
+
+
+# ---------------------------------------------------------------------------------- golden vectors
+def test_golden_uniform_fixed(ops):
+    G = load_golden("uniform_fixed")
+    for tag in G["cases"]:
+        scale, zp, qmin, qmax, bits, sym = G[f"{tag}_qp"]
+        spec = ops.QSpec(int(qmin), int(qmax))
+        x, g = dev(G[f"{tag}_x"]), dev(G[f"{tag}_g"])
+        y, codes = ops.fake_quant_forward(x, float(scale), int(zp), spec, want_codes=True)
+        assert bits_equal(y.cpu().numpy(), G[f"{tag}_y"]), (tag, first_mismatch(y.cpu().numpy(), G[f"{tag}_y"]))
+        ref_codes = G[f"{tag}_codes"]
+        ok = ~np.isnan(ref_codes)
+        assert np.array_equal(codes.cpu().numpy().astype(np.float32)[ok], ref_codes[ok]), tag
+        dx = ops.fake_quant_backward_ste(x, g, float(scale), int(zp), spec)
+        assert bits_equal(dx.cpu().numpy(), G[f"{tag}_dx"]), (tag, first_mismatch(dx.cpu().numpy(), G[f"{tag}_dx"]))
+        y2, dx2 = ops.fake_quant_forward_backward(x, g, float(scale), int(zp), spec)
+        assert bits_equal(y2.cpu().numpy(), G[f"{tag}_y"]) and bits_equal(dx2.cpu().numpy(), G[f"{tag}_dx"]), tag
+
+
+def test_golden_uniform_learned(ops):
+    G = load_golden("uniform_learned")
+    for tag in G["cases"]:
+        scale, zf, qmin, qmax, bits, sym, gs = G[f"{tag}_qp"]
+        sym = bool(sym)
+        x, g = G[f"{tag}_x"], G[f"{tag}_g"]
+        spec = ops.QSpec(int(qmin), int(qmax), zp_learned=not sym)
+        s_t = torch.tensor(scale, dtype=torch.float64, device="cuda")  # 0-dim fp64 like the reference Parameter
+        z_t = torch.tensor(zf, dtype=torch.float32, device="cuda") if not sym else 0
+        y = ops.fake_quant_forward(dev(x), s_t, z_t, spec)
+        assert bits_equal(y.cpu().numpy(), G[f"{tag}_y"]), (tag, first_mismatch(y.cpu().numpy(), G[f"{tag}_y"]))
+        dx, ds, dz = ops.lsq_backward(dev(x), dev(g), s_t, z_t, spec, gs, want_dz=not sym, ds_dtype=torch.float64)
+        assert bits_equal(dx.cpu().numpy(), G[f"{tag}_dx"]), (tag, first_mismatch(dx.cpu().numpy(), G[f"{tag}_dx"]))
+        zeff = float(np.clip(np.rint(np.float32(zf)), qmin, qmax)) if not sym else 0.0
+        mass = gs * sum_mass(x, g, scale, zeff, qmin, qmax)
+        assert ds.dtype == torch.float64
+        assert abs(ds.item() - G[f"{tag}_ds"][0]) <= 1e-5 * mass, (tag, ds.item(), G[f"{tag}_ds"][0], mass)
+        # and against the fp64 oracle ("truth") much tighter
+        _, ds_o, dz_o = oracle.fake_quant_bwd(x, g, scale, zf, int(qmin), int(qmax), zp_learned=not sym, grad_scale=gs,
+                                              want_dz=not sym)
+        assert abs(ds.item() - ds_o[0]) <= 2e-6 * mass, (tag, ds.item(), ds_o[0])
+        if not sym:
+            zmass = gs * float(np.sum(np.abs(g.astype(np.float64) * np.float32(scale))))
+            assert abs(dz.item() - G[f"{tag}_dz"][0]) <= 1e-5 * zmass, (tag, dz.item(), G[f"{tag}_dz"][0])
+            assert abs(dz.item() - dz_o[0]) <= 2e-6 * zmass
+
+
+def test_golden_funlsq(ops):
+    G = load_golden("funlsq")
+    s, z, qmin, qmax, gsc = G["qp"]
+    spec = ops.QSpec(int(qmin), int(qmax), mask_mode=1)
+    x, g = G["x"], G["g"]
+    dx, ds, _ = ops.lsq_backward(dev(x), dev(g), torch.tensor([s], dtype=torch.float32, device="cuda"), 0, spec, gsc)
+    assert bits_equal(dx.cpu().numpy(), G["dx"]), first_mismatch(dx.cpu().numpy(), G["dx"])
+    mass = gsc * float(np.sum(np.abs(g.astype(np.float64))) * 0.5 + 1.0)
+    assert abs(ds.item() - G["ds"][0]) <= 1e-5 * mass
+
+
+def test_golden_lsq_per_channel(ops):
+    G = load_golden("lsq_per_channel")
+    for tag in G["cases"]:
+        qmin, qmax, config_act = (int(v) for v in G[f"{tag}_qp"])
+        x, g = G[f"{tag}_x"], G[f"{tag}_g"]
+        s, zf = G[f"{tag}_scale"], G[f"{tag}_zpf"]
+        C = x.shape[1]
+        spec = ops.QSpec(qmin, qmax, ch_axis=1, zp_learned=True)
+        s_t, z_t = dev(s).view(1, C, 1, 1), dev(zf).view(1, C, 1, 1)
+        y = ops.fake_quant_forward(dev(x), s_t, z_t, spec)
+        assert bits_equal(y.cpu().numpy(), G[f"{tag}_y"]), (tag, first_mismatch(y.cpu().numpy(), G[f"{tag}_y"]))
+        gs = ops.lsq_grad_scale(qmax, x.size, C) * (5000.0 if config_act else 1.0)
+        dx, ds, dz = ops.lsq_backward(dev(x), dev(g), s_t, z_t, spec, gs, want_dz=True)
+        assert bits_equal(dx.cpu().numpy(), G[f"{tag}_dx"]), (tag, first_mismatch(dx.cpu().numpy(), G[f"{tag}_dx"]))
+        ds, dz = ds.cpu().numpy().astype(np.float64), dz.cpu().numpy().astype(np.float64)
+        for c in range(C):
+            zeff = float(np.clip(np.rint(zf[c]), qmin, qmax))
+            mass = gs * sum_mass(x[:, c], g[:, c], s[c], zeff, qmin, qmax)
+            assert abs(ds[c] - G[f"{tag}_ds"][c]) <= 1e-5 * mass, (tag, c, ds[c], G[f"{tag}_ds"][c])
+            zmass = gs * float(np.sum(np.abs(g[:, c].astype(np.float64) * s[c])))
+            assert abs(dz[c] - G[f"{tag}_dz"][c]) <= 1e-5 * zmass, (tag, c, dz[c], G[f"{tag}_dz"][c])
+
+
+def test_golden_observer(ops):
+    G = load_golden("observer")
+    for tag in G["cases"]:
+        name, symtag, btag = tag.rsplit("_", 2)
+        sym, bits = symtag == "sym", int(btag[1:])
+        state = ops.new_observer_state(1, "cuda")
+        trace = G[f"{tag}_trace"]
+        for i in range(int(G[f"{name}_n"])):
+            ops.observe(dev(G[f"{name}_in{i}"]), None, state, bits, sym, 1e-8, want_stats=False)
+            st = state.cpu().numpy()[0]
+            exp = trace[i]
+            for k in range(4):
+                assert st[k] == exp[k] or (np.isnan(st[k]) and np.isnan(exp[k])), (tag, i, k, st[:4], exp)
+
+
+def test_golden_manager_stats(ops):
+    G = load_golden("manager")
+    for tag in G["cases"]:
+        bits = int(tag[1])
+        sym = tag.endswith("_sym")
+        state = ops.new_observer_state(1, "cuda")
+        for i in range(3):
+            x = G[f"{tag}_in{i}"]
+            st = ops.observe(dev(x), None, state, 8, sym).cpu().numpy()[0]
+            assert st[2] / x.size == pytest.approx(G[f"{tag}_mean_abs"][i], rel=2e-6)
+            assert st[3] / x.size == pytest.approx(G[f"{tag}_mean"][i], rel=1e-4, abs=1e-6)
+        s = state.cpu().numpy()[0]
+        assert tuple(s[:4]) == tuple(G[f"{tag}_minmax_scale_zp"])
+        assert s[4] == 3 and s[5] / 3 == pytest.approx(np.mean(G[f"{tag}_mean_abs"]), rel=2e-6)
+        assert s[7] / 3 == pytest.approx(np.mean(G[f"{tag}_std"]), rel=2e-6)
+        out = torch.empty(1, dtype=torch.float64, device="cuda")
+        ops.lsq_init_scale(state, bits, out)
+        # order-dependent fp32 means in the reference: tolerance, not bit-exact
+        assert out.item() == pytest.approx(float(G[f"{tag}_lsq_init"]), rel=2e-6)
+
+
+def test_golden_bn_fold(ops):
+    G = load_golden("bn_fold")
+    for tag in G["cases"]:
+        W, b, bn, eps = G[f"{tag}_W"], G[f"{tag}_b"], G[f"{tag}_bn"], float(G[f"{tag}_eps"])
+        Wf, bf, _, _ = ops.bn_fold(dev(W), dev(b) if b.size else None, dev(bn[0]), dev(bn[1]), dev(bn[2]), dev(bn[3]), eps)
+        assert bits_equal(Wf.cpu().numpy(), G[f"{tag}_Wf"]), (tag, first_mismatch(Wf.cpu().numpy(), G[f"{tag}_Wf"]))
+        assert bits_equal(bf.cpu().numpy(), G[f"{tag}_bf"]), (tag, first_mismatch(bf.cpu().numpy(), G[f"{tag}_bf"]))
+        # fused fold + fake-quant + stats == fold, then oracle fake-quant / stats of the folded weight
+        spec = ops.QSpec(-8, 7)
+        Wf2, bf2, Wq, st = ops.bn_fold(dev(W), dev(b) if b.size else None, dev(bn[0]), dev(bn[1]), dev(bn[2]), dev(bn[3]),
+                                       eps, scale=0.11, zero_point=0, spec=spec, want_stats=True)
+        assert bits_equal(Wf2.cpu().numpy(), G[f"{tag}_Wf"]) and bits_equal(bf2.cpu().numpy(), G[f"{tag}_bf"])
+        assert bits_equal(Wq.cpu().numpy(), oracle.fake_quant_fwd(G[f"{tag}_Wf"], 0.11, 0, -8, 7))
+        so = oracle.minmax_stats(G[f"{tag}_Wf"])[0]
+        sg = st.cpu().numpy()[0]
+        assert sg[0] == so[0] and sg[1] == so[1]
+        np.testing.assert_allclose(sg[2:], so[2:], rtol=1e-6, atol=1e-9)
+        # per-channel (ch_axis 0) weight fake-quant in the fold
+        C = W.shape[0]
+        sc = np.linspace(0.05, 0.2, C).astype(np.float32)
+        _, _, Wq2, _ = ops.bn_fold(dev(W), None, dev(bn[0]), dev(bn[1]), dev(bn[2]), dev(bn[3]), eps, scale=dev(sc),
+                                   zero_point=0, spec=ops.QSpec(-8, 7, ch_axis=0))
+        assert bits_equal(Wq2.cpu().numpy(), oracle.fake_quant_fwd(G[f"{tag}_Wf"], sc, 0, -8, 7, ch_axis=0))
+
+
+def test_golden_bn_reestimate(ops):
+    G = load_golden("bn_reestimate")
+    k = int(G["num_batches"])
+    C = G["conv_out"].shape[2]
+    mean_sum = torch.zeros(C, device="cuda")
+    var_sum = torch.zeros(C, device="cuda")
+    for i in range(k):
+        ops.bn_batch_moments(dev(G["conv_out"][i]), mean_sum, var_sum)
+    rm, rv = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_reestimate_finish(mean_sum, var_sum, k, rm, rv)
+    np.testing.assert_allclose(rm.cpu().numpy(), G["running_mean"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(rv.cpu().numpy(), G["running_var"], rtol=1e-5, atol=1e-7)
+    rm_o, rv_o = oracle.bn_reestimate(list(G["conv_out"][:k]))
+    np.testing.assert_allclose(rm.cpu().numpy(), rm_o, rtol=2e-6, atol=1e-8)
+    np.testing.assert_allclose(rv.cpu().numpy(), rv_o, rtol=2e-6, atol=1e-8)
+
+
+# ------------------------------------------------------------------------ seeded inputs vs the oracle
+PER_TENSOR_SIZES = [1, 7, 8, 9, 31, 255, 1023, 1024, 1025, 2047, 2048, 2049, 8191, 8192, 8193, 100003, (1 << 20) + 5]
+
+
+@pytest.mark.parametrize("n", PER_TENSOR_SIZES)
+def test_per_tensor_ragged_sizes(ops, n):
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 2).astype(np.float32)
+    g = rng.standard_normal(n).astype(np.float32)
+    for (qmin, qmax, s, z) in ((-128, 127, 3.0 / 127, 0), (0, 15, 0.4, 8), (-2, 1, 0.9, 0)):
+        spec = ops.QSpec(qmin, qmax)
+        y = ops.fake_quant_forward(dev(x), s, z, spec)
+        assert bits_equal(y.cpu().numpy(), oracle.fake_quant_fwd(x, s, z, qmin, qmax)), (n, qmin)
+        gs = ops.lsq_grad_scale(qmax, n)
+        dx_o, ds_o, _ = oracle.fake_quant_bwd(x, g, s, z, qmin, qmax, grad_scale=gs)
+        dx = ops.fake_quant_backward_ste(dev(x), dev(g), s, z, spec)
+        assert bits_equal(dx.cpu().numpy(), dx_o), (n, qmin)
+        s_t = torch.tensor(s, dtype=torch.float64, device="cuda")
+        dx2, ds, _ = ops.lsq_backward(dev(x), dev(g), s_t, z, spec, gs, ds_dtype=torch.float64)
+        assert bits_equal(dx2.cpu().numpy(), dx_o)
+        mass = gs * sum_mass(x, g, s, z, qmin, qmax)
+        assert abs(ds.item() - ds_o[0]) <= 2e-6 * mass + 1e-30, (n, ds.item(), ds_o[0])
+        st = ops.observe(dev(x)).cpu().numpy()[0]
+        so = oracle.minmax_stats(x)[0]
+        assert st[0] == so[0] and st[1] == so[1]
+        np.testing.assert_allclose(st[2:], so[2:], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape,ch_axis", [
+    ((16, 3, 3, 3), 0), ((64, 32, 3, 3), 0), ((7, 4609), 0), ((5, 2048), 0), ((3, 10007), 0),
+    ((2, 16, 10, 10), 1), ((3, 8, 20, 20), 1), ((2, 5, 47, 47), 1), ((2, 3, 160, 160), 1), ((1, 4, 3, 2731), 1),
+    ((4, 6), 1), ((9, 1), 0),
+])
+def test_per_channel_layouts(ops, shape, ch_axis):
+    rng = np.random.default_rng(sum(shape))
+    C = shape[ch_axis]
+    x = (rng.standard_normal(shape) * 2 + 0.3).astype(np.float32)
+    g = rng.standard_normal(shape).astype(np.float32)
+    s = (0.02 * rng.uniform(0.5, 2.0, C)).astype(np.float32)
+    zf = rng.uniform(100, 150, C).astype(np.float32)
+    qshape = [1] * len(shape)
+    qshape[ch_axis] = C
+    spec = ops.QSpec(0, 255, ch_axis=ch_axis, zp_learned=True)
+    s_t, z_t = dev(s).view(qshape), dev(zf).view(qshape)
+    y = ops.fake_quant_forward(dev(x), s_t, z_t, spec)
+    y_o = oracle.fake_quant_fwd(x, s, zf, 0, 255, ch_axis=ch_axis, zp_learned=True)
+    assert bits_equal(y.cpu().numpy(), y_o), first_mismatch(y.cpu().numpy(), y_o)
+    gs = ops.lsq_grad_scale(255, x.size, C)
+    dx_o, ds_o, dz_o = oracle.fake_quant_bwd(x, g, s, zf, 0, 255, ch_axis=ch_axis, zp_learned=True, grad_scale=gs, want_dz=True)
+    dx, ds, dz = ops.lsq_backward(dev(x), dev(g), s_t, z_t, spec, gs, want_dz=True)
+    assert bits_equal(dx.cpu().numpy(), dx_o), first_mismatch(dx.cpu().numpy(), dx_o)
+    xm = np.moveaxis(x, ch_axis, 0).reshape(C, -1)
+    gm = np.moveaxis(g, ch_axis, 0).reshape(C, -1)
+    ds, dz = ds.cpu().numpy().astype(np.float64), dz.cpu().numpy().astype(np.float64)
+    for c in range(C):
+        zeff = float(np.clip(np.rint(zf[c]), 0, 255))
+        mass = gs * sum_mass(xm[c], gm[c], s[c], zeff, 0, 255)
+        assert abs(ds[c] - ds_o[c]) <= 2e-6 * mass + 1e-30, (c, ds[c], ds_o[c])
+        zmass = gs * float(np.sum(np.abs(gm[c].astype(np.float64) * s[c])))
+        assert abs(dz[c] - dz_o[c]) <= 2e-6 * zmass + 1e-30, (c, dz[c], dz_o[c])
+    st = ops.observe(dev(x), ch_axis=ch_axis).cpu().numpy()
+    so = oracle.minmax_stats(x, ch_axis=ch_axis)
+    assert np.array_equal(st[:, :2], so[:, :2])
+    np.testing.assert_allclose(st[:, 2:], so[:, 2:], rtol=1e-6, atol=1e-6)
+    # STE backward and the fused sweep agree with the LSQ backward's dx
+    dx2 = ops.fake_quant_backward_ste(dev(x), dev(g), s_t, z_t, spec)
+    assert bits_equal(dx2.cpu().numpy(), dx_o)
+
+
+def test_unaligned_views(ops):
+    """Tensors whose storage offset breaks 32-byte alignment take the scalar instantiation."""
+    rng = np.random.default_rng(5)
+    base = torch.as_tensor(rng.standard_normal(40000).astype(np.float32)).cuda()
+    gbase = torch.as_tensor(rng.standard_normal(40000).astype(np.float32)).cuda()
+    for off in (1, 3, 5):
+        x = base[off:off + 30001]
+        g = gbase[off:off + 30001]
+        assert x.data_ptr() % 32 != 0
+        xn, gn = x.cpu().numpy(), g.cpu().numpy()
+        spec = ops.QSpec(-8, 7)
+        y = ops.fake_quant_forward(x, 0.3, 0, spec)
+        assert bits_equal(y.cpu().numpy(), oracle.fake_quant_fwd(xn, 0.3, 0, -8, 7))
+        dx = ops.fake_quant_backward_ste(x, g, 0.3, 0, spec)
+        assert bits_equal(dx.cpu().numpy(), oracle.fake_quant_bwd(xn, gn, 0.3, 0, -8, 7, want_ds=False)[0])
+        st = ops.observe(x).cpu().numpy()[0]
+        so = oracle.minmax_stats(xn)[0]
+        assert st[0] == so[0] and st[1] == so[1]
+
+
+def test_special_values_and_odd_scales(ops):
+    """denormals / inf / NaN / huge inputs and scales outside the fast-division window stay bit-exact."""
+    sp = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-40, 1.17549435e-38, np.inf, -np.inf, np.nan, 3.4e38, -3.4e38, 1e-30,
+                   6e-39, 2.0 ** -61, 2.0 ** -60, 2.0 ** 60, 2.0 ** 61, 1.5, -2.5, 0.5, -0.5], dtype=np.float32)
+    x = np.tile(sp, 50)
+    g = np.random.default_rng(0).standard_normal(x.size).astype(np.float32)
+    for s in (0.0236, 2.0 ** -41, 2.0 ** 41, 1e-38, 3e38, -0.05, 1.0):
+        for (qmin, qmax, z) in ((-128, 127, 0), (0, 255, 128)):
+            spec = ops.QSpec(qmin, qmax)
+            y = ops.fake_quant_forward(dev(x), s, z, spec)
+            y_o = oracle.fake_quant_fwd(x, s, z, qmin, qmax)
+            assert bits_equal(y.cpu().numpy(), y_o), (s, qmin, first_mismatch(y.cpu().numpy(), y_o))
+            dx = ops.fake_quant_backward_ste(dev(x), dev(g), s, z, spec)
+            dx_o = oracle.fake_quant_bwd(x, g, s, z, qmin, qmax, want_ds=False)[0]
+            assert bits_equal(dx.cpu().numpy(), dx_o), (s, qmin, first_mismatch(dx.cpu().numpy(), dx_o))
+
+
+@pytest.mark.parametrize("scale", [3.0 / 127, 3.0 / 7, 0.0173, 1.0, 2.0 ** -5, 1.9999999, 1.0000001, 0.3333333, 7.7e-4,
+                                   123.456, 2.0 ** -40, 2.0 ** 40, 1.1754944e-38, -0.021])
+def test_division_exhaustive(ops, scale):
+    """The hoisted-reciprocal division equals IEEE x/s for ALL 2^32 values of x."""
+    assert ops.selftest_division(scale) == 0
+
+
+def test_division_random_scales(ops):
+    rng = np.random.default_rng(123)
+    for s in np.exp(rng.uniform(np.log(1e-6), np.log(1e3), 24)).astype(np.float32):
+        assert ops.selftest_division(float(s)) == 0, s
+
+
+def test_empty_and_errors(ops):
+    e = torch.empty(0, device="cuda")
+    assert ops.fake_quant_forward(e, 0.1, 0, ops.QSpec(-8, 7)).numel() == 0
+    assert ops.fake_quant_backward_ste(e, e, 0.1, 0, ops.QSpec(-8, 7)).numel() == 0
+    with pytest.raises(RuntimeError):
+        ops.fake_quant_forward(torch.zeros(4), 0.1, 0, ops.QSpec(-8, 7))  # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        ops.fake_quant_forward(torch.zeros(4, device="cuda", dtype=torch.float16), 0.1, 0, ops.QSpec(-8, 7))
+    from vsiquantization_b200._lib import VsiqError
+    with pytest.raises(VsiqError):
+        ops.fake_quant_forward(torch.zeros(4, device="cuda"), 0.1, 0, ops.QSpec(7, 7))  # qmin >= qmax
+
+
+# --------------------------------------------------------------- full-size, size-independent properties
+@pytest.mark.parametrize("log2n", [26, 28])
+def test_full_size_properties(ops, log2n):
+    n = 1 << log2n
+    torch.manual_seed(0)
+    x = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda")
+    s, qmin, qmax = 3.0 / 127, -128, 127
+    spec = ops.QSpec(qmin, qmax)
+    y, codes = ops.fake_quant_forward(x, s, 0, spec, want_codes=True)
+    y1 = ops.fake_quant_forward(x, s, 0, spec)
+    assert torch.equal(y, y1)
+    # idempotence: fq(fq(x)) == fq(x)
+    assert torch.equal(ops.fake_quant_forward(y1, s, 0, spec), y1)
+    # codes in range, y == codes * s bitwise
+    assert int(codes.min()) >= qmin and int(codes.max()) <= qmax
+    assert torch.equal(codes.float() * torch.tensor(s, device="cuda", dtype=torch.float32), y1)
+    # monotone: sorting commutes with quantisation on a sample
+    xs = torch.sort(x[: 1 << 20]).values
+    ys = ops.fake_quant_forward(xs, s, 0, spec)
+    assert bool((ys[1:] >= ys[:-1]).all())
+    # mask <=> in range; dx == g inside, 0 outside (to 1 ulp: dx = (g*s)/s)
+    dx = ops.fake_quant_backward_ste(x, g, s, 0, spec)
+    inside = (torch.round(x / torch.tensor(s, device="cuda")) >= qmin) & (torch.round(x / torch.tensor(s, device="cuda")) <= qmax)
+    assert bool((dx[~inside] == 0).all())
+    assert torch.allclose(dx[inside], g[inside], rtol=2e-7, atol=0)
+    # the first 2^20 elements against the oracle, bit for bit
+    k = 1 << 20
+    xo, go = x[:k].cpu().numpy(), g[:k].cpu().numpy()
+    assert bits_equal(y1[:k].cpu().numpy(), oracle.fake_quant_fwd(xo, s, 0, qmin, qmax))
+    assert bits_equal(dx[:k].cpu().numpy(), oracle.fake_quant_bwd(xo, go, s, 0, qmin, qmax, want_ds=False)[0])
+    # LSQ ds: linear in g (ds(2g) == 2 ds(g)) and equal to the chunked oracle sum
+    s_t = torch.tensor(s, dtype=torch.float64, device="cuda")
+    gs = ops.lsq_grad_scale(qmax, n)
+    _, ds1, _ = ops.lsq_backward(x, g, s_t, 0, spec, gs, ds_dtype=torch.float64)
+    _, ds2, _ = ops.lsq_backward(x, g * 2, s_t, 0, spec, gs, ds_dtype=torch.float64)
+    assert ds2.item() == pytest.approx(2 * ds1.item(), rel=1e-12)
+    acc = 0.0
+    mass = 0.0
+    step = 1 << 24
+    for i in range(0, n, step):
+        xo, go = x[i:i + step].cpu().numpy(), g[i:i + step].cpu().numpy()
+        acc += oracle.fake_quant_bwd(xo, go, s, 0, qmin, qmax, grad_scale=gs)[1][0]
+        mass += gs * sum_mass(xo, go, s, 0, qmin, qmax)
+    assert abs(ds1.item() - acc) <= 2e-6 * mass
+    # observer: exact extrema, sums to fp64 accuracy
+    st = ops.observe(x).cpu().numpy()[0]
+    assert st[0] == float(x.min()) and st[1] == float(x.max())
+    assert st[3] == pytest.approx(float(x.double().sum()), rel=1e-6, abs=1e-2)
+    assert st[4] == pytest.approx(float((x.double() ** 2).sum()), rel=1e-6)

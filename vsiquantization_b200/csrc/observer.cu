@@ -1,0 +1,348 @@
+// observer.cu -- kernels (1), (2) and (6): one-pass min/max + moment reduction with the observer
+// state update and scale/zero-point computation folded into its last CTA; batched qparams; LSQ
+// step-size initialisation; BN re-estimation finalisers.
+//
+// Reference semantics:
+//   observe           observers/minmax.py:42-47 (x.min()/x.max(): NaN in -> NaN out; NaN never updates the
+//                     running state; state starts at 0)
+//   extra statistics  quantizers/quantization_manager.py:66-68 (mean|x|, mean x, unbiased std)
+//   scale/zero-point  observers/minmax.py:67-74 (Python doubles; banker's round; zp not clamped)
+//   LSQ init          quantizers/quantization_manager.py:112
+//   BN re-estimation  utils/estimate_bn.py:56-99 (batch mean / UNBIASED batch var, summed, / count)
+//
+// Roofline: HBM, 4 algorithmic bytes per element (one read of x; the reference makes five passes).
+#include "common.cuh"
+
+namespace vsiq {
+
+constexpr int kPartialWidth = 6;  // min, max, sum|x|, sum x, sum x^2, nan flag
+
+struct StatsOp : OpBase {
+    float mn, mx;
+    bool bad;            // saw a NaN
+    float fa, f1, f2;    // fp32 partials of the current vector (<= 8 elements)
+    double sa, s1, s2;   // fp64 running sums of this thread
+    __device__ __forceinline__ void reset() {
+        mn = INFINITY;
+        mx = -INFINITY;
+        bad = false;
+        fa = f1 = f2 = 0.0f;
+        sa = s1 = s2 = 0.0;
+    }
+    __device__ __forceinline__ void apply(const float (&a)[1], float (&)[1]) {
+        const float x = a[0];
+        bad = bad || (x != x);
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
+        fa += fabsf(x);
+        f1 += x;
+        f2 = fmaf(x, x, f2);
+    }
+    __device__ __forceinline__ void vec_done() {
+        sa += (double)fa;
+        s1 += (double)f1;
+        s2 += (double)f2;
+        fa = f1 = f2 = 0.0f;
+    }
+};
+
+// Reduce a group's StatsOp into one partial record (valid in thread 0 of the group / lane 0).
+template <int GROUP>
+__device__ __forceinline__ void stats_group_reduce(StatsOp& op, double (&out)[kPartialWidth],
+                                                   double (*s_red)[kPartialWidth]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float mn = warp_min(op.bad ? NAN : op.mn);
+    float mx = warp_max(op.bad ? NAN : op.mx);
+    double sa = warp_sum(op.sa), s1 = warp_sum(op.s1), s2 = warp_sum(op.s2);
+    if (GROUP == 32) {
+        out[0] = (double)mn;
+        out[1] = (double)mx;
+        out[2] = sa;
+        out[3] = s1;
+        out[4] = s2;
+        out[5] = 0.0;
+        return;
+    }
+    __syncthreads();
+    if (lane == 0) {
+        s_red[warp][0] = (double)mn;
+        s_red[warp][1] = (double)mx;
+        s_red[warp][2] = sa;
+        s_red[warp][3] = s1;
+        s_red[warp][4] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = (float)s_red[0][0], b = (float)s_red[0][1];
+        double x2 = s_red[0][2], x3 = s_red[0][3], x4 = s_red[0][4];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) {
+            a = nanmin(a, (float)s_red[w][0]);
+            b = nanmax(b, (float)s_red[w][1]);
+            x2 += s_red[w][2];
+            x3 += s_red[w][3];
+            x4 += s_red[w][4];
+        }
+        out[0] = (double)a;
+        out[1] = (double)b;
+        out[2] = x2;
+        out[3] = x3;
+        out[4] = x4;
+        out[5] = 0.0;
+    }
+}
+
+// observers/minmax.py:67-74 in IEEE doubles
+__device__ __forceinline__ void qparams_from_minmax(double mn, double mx, int bits, int symmetric, double eps,
+                                                    double* scale, double* zp) {
+    if (symmetric) {
+        const double a = fabs(mn), b = fabs(mx);
+        const double max_abs = (b > a) ? b : a;  // Python max(a, b)
+        *scale = max_abs / ((double)((1 << (bits - 1)) - 1) + eps);
+        *zp = 0.0;
+    } else {
+        const double s = (mx - mn) / ((double)((1 << bits) - 1) + eps);
+        *scale = s;
+        *zp = rint(-mn / (s + eps));
+    }
+}
+
+template <int GROUP, int V>
+__global__ void __launch_bounds__(kThreads)
+    observe_kernel(const float* __restrict__ x, Tiles tiles, int64_t outer, void* ws, double* __restrict__ stats,
+                   double* __restrict__ state, int bits, int symmetric, double eps) {
+    __shared__ double s_red[kWarps][kPartialWidth];
+    const float* const in[1] = {x};
+    float* const out[1] = {nullptr};
+    double* partials = ws_partials(ws);
+    const bool single_row = tiles.rows == 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    StatsOp op;
+    op.reset();
+    for (uint32_t t = group_index<GROUP>(); t < tiles.n_tiles; t += group_count<GROUP>()) {
+        const TileCursor<GROUP> c = tile_at<GROUP>(tiles, t);
+        span_apply<GROUP, V, 1, 0>(in, out, c.offset, c.len, op);
+        if (!single_row) {
+            double rec[kPartialWidth];
+            stats_group_reduce<GROUP>(op, rec, s_red);
+            if ((GROUP == 32 && lane == 0) || (GROUP != 32 && threadIdx.x == 0)) {
+#pragma unroll
+                for (int k = 0; k < kPartialWidth; ++k) partials[(size_t)t * kPartialWidth + k] = rec[k];
+            }
+            op.reset();
+        }
+    }
+    if (single_row) {
+        double rec[kPartialWidth];
+        stats_group_reduce<GROUP>(op, rec, s_red);
+        const size_t slot = group_index<GROUP>();
+        if (((GROUP == 32 && lane == 0) || (GROUP != 32 && threadIdx.x == 0)) && slot < tiles.n_tiles) {
+#pragma unroll
+            for (int k = 0; k < kPartialWidth; ++k) partials[slot * kPartialWidth + k] = rec[k];
+        }
+    }
+
+    if (!last_cta_ticket((unsigned int*)ws)) return;
+
+    const int64_t C = tiles.channels;
+    const double count = (double)outer * (double)tiles.inner;
+    for (int64_t c = warp; c < C; c += kWarps) {
+        float mn = INFINITY, mx = -INFINITY;
+        double sa = 0.0, s1 = 0.0, s2 = 0.0;
+        if (single_row) {
+            const uint32_t n_slots = group_count<GROUP>() < tiles.n_tiles ? group_count<GROUP>() : tiles.n_tiles;
+            for (uint32_t i = lane; i < n_slots; i += 32) {
+                const double* p = partials + (size_t)i * kPartialWidth;
+                mn = nanmin(mn, (float)__ldcg(p));
+                mx = nanmax(mx, (float)__ldcg(p + 1));
+                sa += __ldcg(p + 2);
+                s1 += __ldcg(p + 3);
+                s2 += __ldcg(p + 4);
+            }
+        } else {
+            const int64_t items = outer * (int64_t)tiles.chunks;
+            for (int64_t i = lane; i < items; i += 32) {
+                const int64_t o = i / tiles.chunks, k = i - o * tiles.chunks;
+                const double* p = partials + (size_t)((o * C + c) * tiles.chunks + k) * kPartialWidth;
+                mn = nanmin(mn, (float)__ldcg(p));
+                mx = nanmax(mx, (float)__ldcg(p + 1));
+                sa += __ldcg(p + 2);
+                s1 += __ldcg(p + 3);
+                s2 += __ldcg(p + 4);
+            }
+        }
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        sa = warp_sum(sa);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            if (stats) {
+                double* o = stats + c * VSIQ_STATS_WIDTH;
+                o[0] = (double)mn;
+                o[1] = (double)mx;
+                o[2] = sa;
+                o[3] = s1;
+                o[4] = s2;
+            }
+            if (state) {
+                double* st = state + c * VSIQ_STATE_WIDTH;
+                double run_min = st[0], run_max = st[1];
+                if ((double)mn < run_min) run_min = (double)mn;  // NaN compares false: never updates
+                if ((double)mx > run_max) run_max = (double)mx;
+                double sc, zp;
+                qparams_from_minmax(run_min, run_max, bits, symmetric, eps, &sc, &zp);
+                const double mean = s1 / count;
+                const double var = (s2 - count * mean * mean) / (count - 1.0);  // torch.std: unbiased
+                st[0] = run_min;
+                st[1] = run_max;
+                st[2] = sc;
+                st[3] = zp;
+                st[4] += 1.0;
+                st[5] += sa / count;
+                st[6] += mean;
+                st[7] += sqrt(var > 0.0 ? var : 0.0);
+            }
+        }
+    }
+}
+
+__global__ void qparams_kernel(double* state, int64_t n, const int32_t* __restrict__ bits,
+                               const int32_t* __restrict__ symmetric, double eps) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* st = state + i * VSIQ_STATE_WIDTH;
+    double sc, zp;
+    qparams_from_minmax(st[0], st[1], bits[i], symmetric[i], eps, &sc, &zp);
+    st[2] = sc;
+    st[3] = zp;
+}
+
+__global__ void lsq_init_kernel(const double* __restrict__ state, int64_t C, int bits, void* out, int out_f64) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double* st = state + c * VSIQ_STATE_WIDTH;
+    // quantization_manager.py:112: 2 * np.mean(mean_abs_x) / np.sqrt(2 ** (bits - 1) - 1)
+    const double s0 = 2.0 * (st[5] / st[4]) / sqrt((double)((1 << (bits - 1)) - 1));
+    if (out_f64)
+        ((double*)out)[c] = s0;
+    else
+        ((float*)out)[c] = (float)s0;
+}
+
+__global__ void bn_moments_finalize_kernel(const double* __restrict__ stats, double count, int64_t C,
+                                           float* batch_mean, float* batch_var_biased, float* batch_var_unbiased,
+                                           float* mean_sum, float* var_sum) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double s1 = stats[c * VSIQ_STATS_WIDTH + 3], s2 = stats[c * VSIQ_STATS_WIDTH + 4];
+    const double mean = s1 / count;
+    double var_b = s2 / count - mean * mean;
+    var_b = var_b > 0.0 ? var_b : 0.0;
+    const double var_u = var_b * (count / (count - 1.0));
+    const float m32 = (float)mean, vu32 = (float)var_u;
+    if (batch_mean) batch_mean[c] = m32;
+    if (batch_var_biased) batch_var_biased[c] = (float)var_b;
+    if (batch_var_unbiased) batch_var_unbiased[c] = vu32;
+    if (mean_sum) mean_sum[c] = __fadd_rn(mean_sum[c], m32);   // estimate_bn.py:86
+    if (var_sum) var_sum[c] = __fadd_rn(var_sum[c], vu32);      // estimate_bn.py:87
+}
+
+__global__ void bn_reestimate_finish_kernel(const float* __restrict__ mean_sum, const float* __restrict__ var_sum,
+                                            float k, float* running_mean, float* running_var, int64_t C) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    running_mean[c] = __fdiv_rn(mean_sum[c], k);  // estimate_bn.py:96
+    running_var[c] = __fdiv_rn(var_sum[c], k);    // estimate_bn.py:97
+}
+
+template <class K>
+static int occupancy_grid(K kernel, uint32_t n_ctas_wanted) {
+    DeviceProps dp;
+    if (int e = get_device_props(&dp)) return -e;
+    int per_sm = 0;
+    cudaError_t ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (ce != cudaSuccess || per_sm < 1) per_sm = 1;
+    return grid_for(n_ctas_wanted, per_sm);
+}
+
+}  // namespace vsiq
+
+using namespace vsiq;
+
+extern "C" size_t vsiq_observe_workspace_bytes(const vsiq_layout* layout) {
+    if (check_layout(layout)) return 0;
+    Tiles tc, tw;
+    size_t slots = 1;
+    if (make_tiles<kThreads>(layout->outer, layout->channels, layout->inner, &tc)) slots = tc.n_tiles;
+    if (layout->inner < kWarpGroupMaxInner && make_tiles<32>(layout->outer, layout->channels, layout->inner, &tw))
+        slots = tw.n_tiles > slots ? tw.n_tiles : slots;
+    return kWsHeader + slots * kPartialWidth * sizeof(double);
+}
+
+extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* stats, double* state, int bits,
+                            int symmetric, double eps, void* workspace, size_t workspace_bytes,
+                            vsiq_stream_t stream) {
+    if (!x || (!stats && !state)) return VSIQ_ERR_INVALID_ARG;
+    if (int e = check_layout(layout)) return e;
+    if (state && (bits < 2 || bits > 8)) return VSIQ_ERR_INVALID_ARG;
+    if (layout->outer * layout->channels * layout->inner == 0) return VSIQ_ERR_INVALID_ARG;  // min() of nothing
+    if (!workspace || workspace_bytes < vsiq_observe_workspace_bytes(layout)) return VSIQ_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool warp_group = layout->inner < kWarpGroupMaxInner;
+    const bool vec8 = aligned32(x);
+    Tiles tiles;
+#define CALL(G, V)                                                                                            \
+    {                                                                                                         \
+        if (!make_tiles<G>(layout->outer, layout->channels, layout->inner, &tiles)) return VSIQ_ERR_INVALID_ARG; \
+        uint32_t want = G == kThreads ? tiles.n_tiles : (tiles.n_tiles + kWarps - 1) / kWarps;                \
+        int grid = occupancy_grid(observe_kernel<G, V>, want);                                                \
+        if (grid < 0) return -grid;                                                                           \
+        observe_kernel<G, V><<<grid, kThreads, 0, st>>>(x, tiles, layout->outer, workspace, stats, state, bits, \
+                                                        symmetric, eps);                                      \
+    }
+    if (warp_group) {
+        if (vec8) CALL(32, 8) else CALL(32, 1)
+    } else {
+        if (vec8) CALL(kThreads, 8) else CALL(kThreads, 1)
+    }
+#undef CALL
+    return (int)cudaGetLastError();
+}
+
+extern "C" int vsiq_qparams_from_minmax(double* state, int64_t n, const int32_t* bits, const int32_t* symmetric,
+                                        double eps, vsiq_stream_t stream) {
+    if (!state || !bits || !symmetric || n < 0) return VSIQ_ERR_INVALID_ARG;
+    if (n == 0) return VSIQ_OK;
+    qparams_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(state, n, bits, symmetric, eps);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int vsiq_lsq_init_scale(const double* state, int64_t channels, int bits, void* scale_out, int scale_dtype,
+                                   vsiq_stream_t stream) {
+    if (!state || !scale_out || channels <= 0 || bits < 2 || bits > 8) return VSIQ_ERR_INVALID_ARG;
+    if (scale_dtype != VSIQ_F32 && scale_dtype != VSIQ_F64) return VSIQ_ERR_INVALID_ARG;
+    lsq_init_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, (cudaStream_t)stream>>>(state, channels, bits,
+                                                                                          scale_out, scale_dtype);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int vsiq_bn_moments_finalize(const double* stats, double count, int64_t channels, float* batch_mean,
+                                        float* batch_var_biased, float* batch_var_unbiased, float* mean_sum,
+                                        float* var_sum, vsiq_stream_t stream) {
+    if (!stats || channels <= 0 || !(count > 1.0)) return VSIQ_ERR_INVALID_ARG;
+    bn_moments_finalize_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        stats, count, channels, batch_mean, batch_var_biased, batch_var_unbiased, mean_sum, var_sum);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int vsiq_bn_reestimate_finish(const float* mean_sum, const float* var_sum, int64_t batch_count,
+                                         float* running_mean, float* running_var, int64_t channels,
+                                         vsiq_stream_t stream) {
+    if (!mean_sum || !var_sum || !running_mean || !running_var || channels <= 0 || batch_count <= 0)
+        return VSIQ_ERR_INVALID_ARG;
+    bn_reestimate_finish_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        mean_sum, var_sum, (float)batch_count, running_mean, running_var, channels);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,453 @@
+"""Tensor-level wrappers over the C ABI and the torch.autograd.Functions built on them.
+
+Everything here takes/returns CUDA fp32 tensors and launches on torch's current stream.  PyTorch is
+used for device memory, streams and autograd bookkeeping only; all arithmetic happens in libvsiq.so.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple, Union
+
+import torch
+
+from . import _lib
+from ._lib import F32, F64, Layout, QParams, check, lib
+
+Number = Union[int, float]
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} lives on {t.device}; vsiquantization_b200 runs on CUDA only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def layout_of(shape, ch_axis: Optional[int]) -> Tuple[int, int, int]:
+    """(outer, channels, inner) of a contiguous tensor quantised along ch_axis (None = per tensor)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if ch_axis is None:
+        return 1, 1, n
+    if ch_axis < 0:
+        ch_axis += len(shape)
+    outer = 1
+    for d in shape[:ch_axis]:
+        outer *= int(d)
+    C = int(shape[ch_axis])
+    inner = n // (outer * C) if outer * C else 0
+    return outer, C, inner
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Zero-initialised scratch, one per (device, stream); kernels leave it zeroed."""
+    key = (device.index, _stream_ptr())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise TypeError(f"quantisation parameters must be float32 or float64 tensors, got {t.dtype}")
+
+
+@dataclass
+class QSpec:
+    """How one quantiser maps onto the ABI: integer range, channel axis and the qparam sources."""
+    qmin: int
+    qmax: int
+    ch_axis: Optional[int] = None
+    zp_learned: bool = False
+    mask_mode: int = _lib.MASK_ROUNDED
+
+
+def _make_qparams(spec: QSpec, scale, zero_point, channels: int, device: torch.device, keep: list) -> QParams:
+    qp = QParams()
+    qp.qmin, qp.qmax = int(spec.qmin), int(spec.qmax)
+    qp.zp_learned = 1 if spec.zp_learned else 0
+    qp.scale_dtype = qp.zp_dtype = F32
+    if isinstance(scale, torch.Tensor):
+        s = scale.detach()
+        if s.device != device:
+            s = s.to(device)
+        if s.numel() != channels:
+            raise ValueError(f"scale has {s.numel()} entries, the layout has {channels} channels")
+        s = s.contiguous()
+        keep.append(s)
+        qp.scale = s.data_ptr()
+        qp.scale_dtype = _dtype_code(s)
+    else:
+        if channels != 1:
+            raise ValueError("a scalar scale needs a per-tensor layout")
+        qp.scale = None
+        qp.scale_host = float(scale)  # ctypes rounds the double to fp32 (RN), like ATen's scalar cast
+    if isinstance(zero_point, torch.Tensor):
+        z = zero_point.detach()
+        if z.device != device:
+            z = z.to(device)
+        if not z.is_floating_point():
+            z = z.to(torch.float32)
+        if z.numel() != channels:
+            raise ValueError(f"zero_point has {z.numel()} entries, the layout has {channels} channels")
+        z = z.contiguous()
+        keep.append(z)
+        qp.zero_point = z.data_ptr()
+        qp.zp_dtype = _dtype_code(z)
+    else:
+        qp.zero_point = None
+        qp.zp_host = float(zero_point)
+        if channels != 1 and isinstance(scale, torch.Tensor):
+            # scalar zero-point with per-channel scales: broadcast it
+            z = torch.full((channels,), float(zero_point), dtype=torch.float32, device=device)
+            keep.append(z)
+            qp.zero_point = z.data_ptr()
+    return qp
+
+
+def _count_launch(n: int = 1) -> None:
+    _lib.launch_count += n
+
+
+# ----------------------------------------------------------------------------------------------
+# raw ops
+# ----------------------------------------------------------------------------------------------
+def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_codes: bool = False):
+    """y = (clamp(rint(x/s + z), qmin, qmax) - z) * s  [reference: quantizers/uniform.py:54-55,95]."""
+    x = _require_cuda_f32(x, "x")
+    outer, C, inner = layout_of(x.shape, spec.ch_axis)
+    lay = Layout(outer, C, inner)
+    keep: list = []
+    with torch.cuda.device(x.device):
+        qp = _make_qparams(spec, scale, zero_point, C, x.device, keep)
+        y = torch.empty_like(x)
+        codes = None
+        if want_codes:
+            codes = torch.empty(x.shape, dtype=torch.int8 if spec.qmin < 0 else torch.uint8, device=x.device)
+        check(lib.vsiq_fake_quant_fwd(x.data_ptr(), y.data_ptr(), codes.data_ptr() if want_codes else None,
+                                      ctypes.byref(lay), ctypes.byref(qp), _stream_ptr()), "vsiq_fake_quant_fwd")
+        _count_launch()
+    return (y, codes) if want_codes else y
+
+
+def fake_quant_backward_ste(x: torch.Tensor, g: torch.Tensor, scale, zero_point, spec: QSpec) -> torch.Tensor:
+    """dx of the forward through the straight-through estimator [uniform.py:258-271 + clamp backward]."""
+    x = _require_cuda_f32(x, "x")
+    g = _require_cuda_f32(g, "grad_output")
+    outer, C, inner = layout_of(x.shape, spec.ch_axis)
+    lay = Layout(outer, C, inner)
+    keep: list = []
+    with torch.cuda.device(x.device):
+        qp = _make_qparams(spec, scale, zero_point, C, x.device, keep)
+        dx = torch.empty_like(x)
+        check(lib.vsiq_fake_quant_bwd_ste(x.data_ptr(), g.data_ptr(), dx.data_ptr(), ctypes.byref(lay),
+                                          ctypes.byref(qp), _stream_ptr()), "vsiq_fake_quant_bwd_ste")
+        _count_launch()
+    return dx
+
+
+def fake_quant_forward_backward(x, g, scale, zero_point, spec: QSpec):
+    """Fused forward + STE backward sweep (16 B/element) -- used by the host pipeline and the bench."""
+    x = _require_cuda_f32(x, "x")
+    g = _require_cuda_f32(g, "grad_output")
+    outer, C, inner = layout_of(x.shape, spec.ch_axis)
+    lay = Layout(outer, C, inner)
+    keep: list = []
+    with torch.cuda.device(x.device):
+        qp = _make_qparams(spec, scale, zero_point, C, x.device, keep)
+        y, dx = torch.empty_like(x), torch.empty_like(x)
+        check(lib.vsiq_fake_quant_fwd_bwd(x.data_ptr(), g.data_ptr(), y.data_ptr(), dx.data_ptr(), ctypes.byref(lay),
+                                          ctypes.byref(qp), _stream_ptr()), "vsiq_fake_quant_fwd_bwd")
+        _count_launch()
+    return y, dx
+
+
+def lsq_backward(x, g, scale, zero_point, spec: QSpec, grad_scale: float, grad_scale_dev: Optional[torch.Tensor] = None,
+                 ds_out: Optional[torch.Tensor] = None, dz_out: Optional[torch.Tensor] = None, want_dz: bool = False,
+                 ds_dtype: torch.dtype = torch.float32, dz_dtype: torch.dtype = torch.float32):
+    """dx + per-channel dscale (+ dzero_point) in one pass [uniform.py:47-55,242-255; lsq_module.py:147-173,317-340].
+
+    ds_out / dz_out let the caller point the kernel at slices of a flat gradient buffer (parallel.py)."""
+    x = _require_cuda_f32(x, "x")
+    g = _require_cuda_f32(g, "grad_output")
+    outer, C, inner = layout_of(x.shape, spec.ch_axis)
+    lay = Layout(outer, C, inner)
+    keep: list = []
+    with torch.cuda.device(x.device):
+        qp = _make_qparams(spec, scale, zero_point, C, x.device, keep)
+        dx = torch.empty_like(x)
+        ds = ds_out if ds_out is not None else torch.empty(C, dtype=ds_dtype, device=x.device)
+        dz = dz_out if dz_out is not None else (torch.empty(C, dtype=dz_dtype, device=x.device) if want_dz else None)
+        if ds.numel() != C or (dz is not None and dz.numel() != C):
+            raise ValueError("gradient outputs must have one entry per channel")
+        nbytes = lib.vsiq_lsq_bwd_workspace_bytes(ctypes.byref(lay))
+        ws = _workspace(nbytes, x.device)
+        gsd = None
+        if grad_scale_dev is not None:
+            gsd = grad_scale_dev.detach().to(device=x.device, dtype=torch.float32).contiguous()
+            keep.append(gsd)
+        check(lib.vsiq_lsq_bwd(x.data_ptr(), g.data_ptr(), dx.data_ptr(), ds.data_ptr(), _dtype_code(ds),
+                               dz.data_ptr() if dz is not None else None, _dtype_code(dz) if dz is not None else F32,
+                               ctypes.byref(lay), ctypes.byref(qp), float(grad_scale),
+                               gsd.data_ptr() if gsd is not None else None, int(spec.mask_mode), ws.data_ptr(),
+                               ws.numel(), _stream_ptr()), "vsiq_lsq_bwd")
+        _count_launch()
+    return dx, ds, dz
+
+
+def new_observer_state(channels: int = 1, device=None) -> torch.Tensor:
+    """[channels, 8] fp64: run_min, run_max, scale, zero_point, n_calls, sum mean|x|, sum mean x, sum std.
+    Running extrema start at 0 like the reference's observer (observers/minmax.py:28-29); scale starts at the
+    manager's default 1 (quantization_manager.py:45)."""
+    st = torch.zeros(channels, _lib.STATE_WIDTH, dtype=torch.float64, device=device)
+    st[:, 2] = 1.0
+    return st
+
+
+def observe(x: torch.Tensor, ch_axis: Optional[int] = None, state: Optional[torch.Tensor] = None, bits: int = 8,
+            symmetric: bool = True, eps: float = 1e-8, want_stats: bool = True) -> Optional[torch.Tensor]:
+    """One pass: per-channel {min, max, sum|x|, sum x, sum x^2} (+ running observer state, scale, zero-point).
+
+    Replaces observers/minmax.py:42-47,67-74 and quantization_manager.py:66-68.  No host sync."""
+    x = _require_cuda_f32(x, "x")
+    outer, C, inner = layout_of(x.shape, ch_axis)
+    lay = Layout(outer, C, inner)
+    with torch.cuda.device(x.device):
+        stats = torch.empty(C, _lib.STATS_WIDTH, dtype=torch.float64, device=x.device) if want_stats else None
+        if state is not None:
+            if state.dtype != torch.float64 or not state.is_cuda or state.numel() != C * _lib.STATE_WIDTH \
+                    or not state.is_contiguous():
+                raise ValueError("observer state must be a contiguous CUDA float64 tensor [channels, 8]")
+        ws = _workspace(lib.vsiq_observe_workspace_bytes(ctypes.byref(lay)), x.device)
+        check(lib.vsiq_observe(x.data_ptr(), ctypes.byref(lay), stats.data_ptr() if want_stats else None,
+                               state.data_ptr() if state is not None else None, int(bits), int(bool(symmetric)),
+                               float(eps), ws.data_ptr(), ws.numel(), _stream_ptr()), "vsiq_observe")
+        _count_launch()
+    return stats
+
+
+def qparams_from_minmax(states: torch.Tensor, bits: torch.Tensor, symmetric: torch.Tensor, eps: float = 1e-8) -> None:
+    """Recompute scale / zero-point of n observers in place from their running extrema [minmax.py:67-74]."""
+    n = states.numel() // _lib.STATE_WIDTH
+    if states.dtype != torch.float64 or not states.is_cuda or not states.is_contiguous():
+        raise ValueError("states must be a contiguous CUDA float64 tensor [n, 8]")
+    bits = bits.to(device=states.device, dtype=torch.int32).contiguous()
+    symmetric = symmetric.to(device=states.device, dtype=torch.int32).contiguous()
+    if bits.numel() != n or symmetric.numel() != n:
+        raise ValueError("bits / symmetric need one entry per observer")
+    with torch.cuda.device(states.device):
+        check(lib.vsiq_qparams_from_minmax(states.data_ptr(), n, bits.data_ptr(), symmetric.data_ptr(), float(eps),
+                                           _stream_ptr()), "vsiq_qparams_from_minmax")
+        _count_launch()
+
+
+def lsq_init_scale(state: torch.Tensor, bits: int, out: torch.Tensor) -> torch.Tensor:
+    """2 * mean(mean|x|) / sqrt(2^(bits-1) - 1) per channel, written into `out` [quantization_manager.py:112]."""
+    C = state.numel() // _lib.STATE_WIDTH
+    if out.numel() != C or not out.is_cuda:
+        raise ValueError("out must be a CUDA tensor with one entry per channel")
+    with torch.cuda.device(state.device):
+        check(lib.vsiq_lsq_init_scale(state.data_ptr(), C, int(bits), out.data_ptr(), _dtype_code(out), _stream_ptr()),
+              "vsiq_lsq_init_scale")
+        _count_launch()
+    return out
+
+
+def bn_fold(W, bias, gamma, beta, mean, var, eps: float, scale=None, zero_point=0, spec: Optional[QSpec] = None,
+            want_stats: bool = False):
+    """W' = W * gamma/sqrt(var+eps), b' = beta + (b - mean) * gamma/sqrt(var+eps)  [modules/fused.py:98-108,292-300].
+
+    With `spec` also returns the fake-quantised W' from the same pass; with want_stats the per-tensor
+    {min,max,sum|x|,sum x,sum x^2} of W'.  Returns (W', b', Wq or None, stats or None)."""
+    W = _require_cuda_f32(W, "weight")
+    C = W.shape[0]
+    inner = W.numel() // C
+    dev = W.device
+    vecs = [_require_cuda_f32(t.detach(), n) for t, n in ((gamma, "gamma"), (beta, "beta"), (mean, "mean"), (var, "var"))]
+    for v in vecs:
+        if v.numel() != C:
+            raise ValueError("BN vectors must have one entry per output channel")
+    b = _require_cuda_f32(bias.detach(), "bias") if bias is not None else None
+    keep: list = []
+    with torch.cuda.device(dev):
+        Wf = torch.empty_like(W)
+        bf = torch.empty(C, dtype=torch.float32, device=dev)
+        Wq = None
+        qp = None
+        qpc = 1
+        if spec is not None:
+            if spec.ch_axis not in (None, 0):
+                raise ValueError("weight fake-quant in the fold supports per-tensor or ch_axis 0")
+            qpc = C if spec.ch_axis == 0 else 1
+            qp = _make_qparams(spec, scale, zero_point, qpc, dev, keep)
+            Wq = torch.empty_like(W)
+        stats = torch.empty(1, _lib.STATS_WIDTH, dtype=torch.float64, device=dev) if want_stats else None
+        ws = _workspace(lib.vsiq_bn_fold_workspace_bytes(C, inner), dev) if want_stats else None
+        check(lib.vsiq_bn_fold(W.data_ptr(), b.data_ptr() if b is not None else None, vecs[0].data_ptr(),
+                               vecs[1].data_ptr(), vecs[2].data_ptr(), vecs[3].data_ptr(), float(eps), C, inner,
+                               Wf.data_ptr(), bf.data_ptr(), Wq.data_ptr() if Wq is not None else None,
+                               ctypes.byref(qp) if qp is not None else None, qpc,
+                               stats.data_ptr() if want_stats else None, ws.data_ptr() if ws is not None else None,
+                               ws.numel() if ws is not None else 0, _stream_ptr()), "vsiq_bn_fold")
+        _count_launch()
+    return Wf, bf, Wq, stats
+
+
+def bn_batch_moments(x: torch.Tensor, mean_sum: Optional[torch.Tensor] = None, var_sum: Optional[torch.Tensor] = None):
+    """Per-channel batch mean, biased and unbiased variance of an [N,C,...] tensor in one pass, optionally
+    accumulating mean / unbiased var into running sums (utils/estimate_bn.py:82,86-87).
+
+    For SyncBN-style multi-GPU re-estimation call observe(x, ch_axis=1), all-reduce(SUM) the stats and pass the
+    global per-channel count to bn_moments_finalize() instead."""
+    x = _require_cuda_f32(x, "x")
+    C = x.shape[1]
+    stats = observe(x, ch_axis=1)
+    return bn_moments_finalize(stats, float(x.numel() // C), mean_sum, var_sum)
+
+
+def bn_moments_finalize(stats: torch.Tensor, count: float, mean_sum=None, var_sum=None):
+    C = stats.shape[0]
+    dev = stats.device
+    with torch.cuda.device(dev):
+        m = torch.empty(C, dtype=torch.float32, device=dev)
+        vb = torch.empty(C, dtype=torch.float32, device=dev)
+        vu = torch.empty(C, dtype=torch.float32, device=dev)
+        check(lib.vsiq_bn_moments_finalize(stats.data_ptr(), float(count), C, m.data_ptr(), vb.data_ptr(), vu.data_ptr(),
+                                           mean_sum.data_ptr() if mean_sum is not None else None,
+                                           var_sum.data_ptr() if var_sum is not None else None, _stream_ptr()),
+              "vsiq_bn_moments_finalize")
+        _count_launch()
+    return m, vb, vu
+
+
+def bn_reestimate_finish(mean_sum, var_sum, batch_count: int, running_mean, running_var) -> None:
+    """running = sum / batch_count  [utils/estimate_bn.py:96-97]."""
+    C = mean_sum.numel()
+    with torch.cuda.device(mean_sum.device):
+        check(lib.vsiq_bn_reestimate_finish(mean_sum.data_ptr(), var_sum.data_ptr(), int(batch_count),
+                                            running_mean.data_ptr(), running_var.data_ptr(), C, _stream_ptr()),
+              "vsiq_bn_reestimate_finish")
+        _count_launch()
+
+
+def selftest_division(scale: float, device=None) -> int:
+    """Mismatches between the kernels' reciprocal-based division and IEEE x/s over all 2^32 x (expect 0)."""
+    dev = torch.device(device or "cuda")
+    with torch.cuda.device(dev):
+        out = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(lib.vsiq_selftest_division(float(scale), out.data_ptr(), _stream_ptr()), "vsiq_selftest_division")
+        _count_launch()
+        return int(out.item())
+
+
+class HostPipeline:
+    """Forward + STE backward over HOST (ideally pinned) buffers, chunked and overlapped on several streams."""
+
+    def __init__(self, chunk_elems: int = 1 << 22, n_slots: int = 4, device=None):
+        self._h = ctypes.c_void_p()
+        self.device = torch.device(device or "cuda")
+        with torch.cuda.device(self.device):
+            check(lib.vsiq_host_pipeline_create(ctypes.byref(self._h), int(chunk_elems), int(n_slots)),
+                  "vsiq_host_pipeline_create")
+
+    def fwd_bwd(self, x: torch.Tensor, g: torch.Tensor, scale: float, zero_point: float, qmin: int, qmax: int,
+                y: Optional[torch.Tensor] = None, dx: Optional[torch.Tensor] = None):
+        for t, n in ((x, "x"), (g, "g")):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{n} must be a contiguous float32 HOST tensor")
+        y = torch.empty_like(x, pin_memory=True) if y is None else y
+        dx = torch.empty_like(x, pin_memory=True) if dx is None else dx
+        with torch.cuda.device(self.device):
+            check(lib.vsiq_host_pipeline_fwd_bwd(self._h, x.data_ptr(), g.data_ptr(), y.data_ptr(), dx.data_ptr(),
+                                                 x.numel(), float(scale), float(zero_point), int(qmin), int(qmax)),
+                  "vsiq_host_pipeline_fwd_bwd")
+        _count_launch(int(lib.vsiq_host_pipeline_last_launches(self._h)))
+        return y, dx
+
+    def close(self):
+        if self._h:
+            lib.vsiq_host_pipeline_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd
+# ----------------------------------------------------------------------------------------------
+class FakeQuantFixed(torch.autograd.Function):
+    """Fake-quant with constant qparams; STE backward.  (uniform.py:54-55 with is_learning_scale=False)"""
+
+    @staticmethod
+    def forward(ctx, x, scale, zero_point, spec: QSpec):
+        ctx.spec, ctx.scale, ctx.zero_point = spec, scale, zero_point
+        ctx.save_for_backward(x)
+        return fake_quant_forward(x, scale, zero_point, spec)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        dx = fake_quant_backward_ste(x, g, ctx.scale, ctx.zero_point, ctx.spec) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None
+
+
+class FakeQuantLearned(torch.autograd.Function):
+    """Fake-quant with learnable step size (and optionally zero-point); LSQ backward in one pass.
+
+    scale: tensor with `channels` entries of any shape (0-dim fp64 Parameter in the reference's per-tensor
+    path, [1,C,1,1] fp32 in lsq_module.py); zero_point: same-shaped float tensor, or a Python number."""
+
+    @staticmethod
+    def forward(ctx, x, scale, zero_point, spec: QSpec, grad_scale: float, grad_scale_dev):
+        ctx.spec, ctx.grad_scale, ctx.grad_scale_dev = spec, grad_scale, grad_scale_dev
+        ctx.zp_is_tensor = isinstance(zero_point, torch.Tensor)
+        ctx.zp_const = None if ctx.zp_is_tensor else zero_point
+        if ctx.zp_is_tensor:
+            ctx.save_for_backward(x, scale, zero_point)
+        else:
+            ctx.save_for_backward(x, scale)
+        return fake_quant_forward(x, scale, zero_point, spec)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.zp_is_tensor:
+            x, scale, zp = ctx.saved_tensors
+        else:
+            x, scale = ctx.saved_tensors
+            zp = ctx.zp_const
+        want_dz = ctx.zp_is_tensor and ctx.needs_input_grad[2]
+        dx, ds, dz = lsq_backward(x, g, scale, zp, ctx.spec, ctx.grad_scale, ctx.grad_scale_dev, want_dz=want_dz,
+                                  ds_dtype=scale.dtype, dz_dtype=zp.dtype if ctx.zp_is_tensor else torch.float32)
+        ds = ds.view(scale.shape).to(scale.device) if ctx.needs_input_grad[1] else None
+        dz = dz.view(zp.shape).to(zp.device) if want_dz else None
+        return (dx if ctx.needs_input_grad[0] else None), ds, dz, None, None, None
+
+
+def lsq_grad_scale(qmax: int, numel: int, channels: int = 1) -> float:
+    """(qmax * numel / channels) ** -0.5  [uniform.py:69-71; lsq_module.py:327-340]."""
+    return float((qmax * (numel / channels)) ** -0.5) if channels > 1 else float((qmax * numel) ** -0.5)
