@@ -201,10 +201,11 @@ int vsiq_fake_quant_fwd_bwd(const float *x, const float *g, float *y, float *dx,
 
 /* ---- self-test ---------------------------------------------------------------------------
  * The kernels divide by the (tile-uniform) scale through a hoisted correctly-rounded reciprocal and
- * two exact-residual FMA corrections instead of the per-element IEEE division sequence.  This entry
- * counts, over ALL 2^32 bit patterns of x, how often that differs from IEEE x / s (expected: 0);
+ * exact-residual FMA corrections instead of the per-element IEEE division sequence.  This entry
+ * counts, over ALL 2^32 bit patterns of the input, how often the fast arithmetic differs from the IEEE
+ * sequence (expected: 0).  mode 0: x / s.  mode 1: RN(RN(g*s) / s) (the dx path).
  * *mismatches_dev (device, zero it first) receives the count. */
-int vsiq_selftest_division(float s, unsigned long long *mismatches_dev, vsiq_stream_t stream);
+int vsiq_selftest_division(float s, int mode, unsigned long long *mismatches_dev, vsiq_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvsiq.so")
+LIB_PATH = os.environ.get("VSIQ_LIB") or os.path.join(_HERE, "libvsiq.so")  # VSIQ_LIB: A/B-testing builds
 
 F32, F64 = 0, 1
 MASK_ROUNDED, MASK_FUNLSQ = 0, 1
@@ -69,7 +69,7 @@ _SIGNATURES = {
     "vsiq_host_pipeline_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                            c_int, c_int]),
     "vsiq_host_pipeline_last_launches": (c_int64, [c_void_p]),
-    "vsiq_selftest_division": (c_int, [c_float, c_void_p, c_void_p]),
+    "vsiq_selftest_division": (c_int, [c_float, c_int, c_void_p, c_void_p]),
 }
 
 EXPORTED = tuple(_SIGNATURES)

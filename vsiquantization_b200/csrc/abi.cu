@@ -1,4 +1,5 @@
 // abi.cu -- library-level entry points and the host-side helpers shared by the launchers.
+#include <math.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -29,26 +30,33 @@ int get_device_props(DeviceProps* out) {
     return 0;
 }
 
-// Grid policy.  Default: a persistent grid of (SM count x resident CTAs per SM) CTAs walking the tiles
-// with a grid stride.  VSIQ_GRID_WAVES=k (k >= 1) allows k x that many CTAs; VSIQ_GRID_WAVES=0 launches
-// one CTA per tile (tuning knobs, read once).
+// Grid policy.  Default: one CTA per tile group, scheduled by the hardware -- the first A/B on B200 showed
+// 1.02-1.05x the measured copy bandwidth against 0.85x for a static persistent grid (profiles/README.md).
+// VSIQ_GRID_WAVES=k (k >= 1) caps the grid at k x (SM count x 4) CTAs that walk the tiles with a grid
+// stride instead (tuning knob for experiments, read once).
 static int grid_waves() {
     static int waves = -1;
     if (waves < 0) {
         const char* s = getenv("VSIQ_GRID_WAVES");
-        waves = s ? atoi(s) : 1;
-        if (waves < 0) waves = 1;
+        waves = s ? atoi(s) : 0;
+        if (waves < 0) waves = 0;
     }
     return waves;
 }
 
-int grid_for(uint32_t n_ctas_wanted, int ctas_per_sm) {
+int single_wave_ctas() {
+    DeviceProps dp;
+    if (get_device_props(&dp)) return 1;
+    return dp.sm_count * 4;
+}
+
+int launch_grid(uint32_t n_ctas_wanted) {
     DeviceProps dp;
     if (int e = get_device_props(&dp)) return -e;
     if (n_ctas_wanted < 1) n_ctas_wanted = 1;
     const int waves = grid_waves();
     if (waves == 0) return (int)(n_ctas_wanted > 0x7fffffffu ? 0x7fffffffu : n_ctas_wanted);
-    const uint64_t cap = (uint64_t)dp.sm_count * (uint64_t)ctas_per_sm * (uint64_t)waves;
+    const uint64_t cap = (uint64_t)dp.sm_count * 4u * (uint64_t)waves;
     return (int)(n_ctas_wanted < cap ? n_ctas_wanted : cap);
 }
 
@@ -78,8 +86,15 @@ int fill_qp(const vsiq_qparams* in, QPDev* out) {
     out->scale_host = in->scale_host;
     out->zp_host = in->zp_host;
     out->zp_learned = in->zp_learned ? 1 : 0;
+    if (in->qmin < -(1 << 22) || in->qmax > (1 << 22)) return VSIQ_ERR_UNSUPPORTED;  // keeps q +- 0.5 exact in fp32
     out->lo = (float)in->qmin;
     out->hi = (float)in->qmax;
+    // rint(t) >= qmin  <=>  t >= qmin - 0.5 when qmin is even (the tie rounds up to qmin), else t > qmin - 0.5
+    out->tlo = out->lo - 0.5f;
+    if (in->qmin & 1) out->tlo = nextafterf(out->tlo, INFINITY);
+    // rint(t) <= qmax  <=>  t <= qmax + 0.5 when qmax is even, else t < qmax + 0.5
+    out->thi = out->hi + 0.5f;
+    if (in->qmax & 1) out->thi = nextafterf(out->thi, -INFINITY);
     return VSIQ_OK;
 }
 

@@ -29,10 +29,13 @@ struct FoldOp : OpBase {
         fa = f1 = f2 = 0.0f;
         sa = s1 = s2 = 0.0;
     }
+    // Folded weights are quantised with the IEEE sequence: W is a few MB at most (launch-bound), and it
+    // keeps the statistics free of the redo protocol.
+    __device__ __forceinline__ void apply_slow(const float (&a)[1], float (&o)[WANT_Q ? 2 : 1]) { apply(a, o); }
     __device__ __forceinline__ void apply(const float (&a)[1], float (&o)[WANT_Q ? 2 : 1]) {
         const float w = __fmul_rn(a[0], t);
         o[0] = w;
-        if (WANT_Q) o[WANT_Q ? 1 : 0] = fq_dequant(clamp_torch(fq_round(w, p), p.lo, p.hi), p);
+        if (WANT_Q) o[WANT_Q ? 1 : 0] = dequant(elem_slow(w, p).q, p);
         if (WANT_STATS) {
             bad = bad || (w != w);
             mn = fminf(mn, w);
@@ -131,16 +134,6 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
-template <class K>
-static int occupancy_grid(K kernel, uint32_t n_ctas_wanted) {
-    DeviceProps dp;
-    if (int e = get_device_props(&dp)) return -e;
-    int per_sm = 0;
-    cudaError_t ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
-    if (ce != cudaSuccess || per_sm < 1) per_sm = 1;
-    return grid_for(n_ctas_wanted, per_sm);
-}
-
 // upper bound of groups any launch of this kernel can have (partials are per group)
 static size_t fold_max_groups(int64_t channels, int64_t inner) {
     Tiles tc, tw;
@@ -183,7 +176,7 @@ extern "C" int vsiq_bn_fold(const float* W, const float* bias, const float* gamm
     {                                                                                                           \
         if (!make_tiles<G>(1, channels, inner, &tiles)) return VSIQ_ERR_INVALID_ARG;                            \
         uint32_t want = G == kThreads ? tiles.n_tiles : (tiles.n_tiles + kWarps - 1) / kWarps;                  \
-        int grid = occupancy_grid(bn_fold_kernel<G, V, Q, S>, want);                                            \
+        int grid = launch_grid(want);                                            \
         if (grid < 0) return -grid;                                                                             \
         bn_fold_kernel<G, V, Q, S><<<grid, kThreads, 0, st>>>(W, bias, gamma, beta, mean, var, eps, tiles, W_out, \
                                                               b_out, Wq_out, qpd, qp_per_channel, stats, workspace); \

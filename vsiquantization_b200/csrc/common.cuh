@@ -10,7 +10,8 @@
 //   * inside a tile every thread issues UNROLL 256-bit loads per input (LDG.E.256, sm_100+) before any
 //     arithmetic, computes, then issues 256-bit stores; ragged heads/tails and unaligned rows fall to
 //     a scalar peel, fully unaligned tensors to the V=1 instantiation;
-//   * grids are capped at (SM count x resident CTAs) and walk tiles with a grid stride.
+//   * grids launch one CTA per tile (or per 8 warp-tiles) and let the hardware scheduler balance the SMs:
+//     measured on B200 this reaches the copy roofline where a static persistent grid stalls at ~85 %.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -23,8 +24,14 @@ namespace vsiq {
 constexpr int kThreads = 256;  // threads per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kVec = 8;        // fp32 lanes per 256-bit access
-constexpr int kUnroll = 2;     // vectors in flight per thread per input array
-constexpr int kBatchesPerTile = 2;
+#ifndef VSIQ_UNROLL
+#define VSIQ_UNROLL 2
+#endif
+#ifndef VSIQ_BATCHES
+#define VSIQ_BATCHES 2
+#endif
+constexpr int kUnroll = VSIQ_UNROLL;            // vectors in flight per thread per input array
+constexpr int kBatchesPerTile = VSIQ_BATCHES;   // batches per tile
 
 template <int GROUP>
 struct TileGeom {
@@ -45,7 +52,11 @@ struct Vec {
 
 __device__ __forceinline__ Vec<8> ld_stream(const float* p, Vec<8>*) {
     Vec<8> r;
+#ifdef VSIQ_LOAD_EVICT_FIRST
+    asm("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
         : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
           "=f"(r.v[7])
         : "l"(p));
@@ -62,14 +73,20 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
     return r;
 }
 __device__ __forceinline__ void st_stream(float* p, const Vec<8>& r) {
+#ifdef VSIQ_STORE_CS
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
+#elif defined(VSIQ_STORE_NA)
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
+#else
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
+#endif
                  "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
                  : "memory");
 }
 __device__ __forceinline__ void st_stream(float* p, const Vec<1>& r) { *p = r.v[0]; }
 
 // ---------------------------------------------------------------------------------------------
-// Quantisation parameters
+// Quantisation parameters and the element arithmetic
 // ---------------------------------------------------------------------------------------------
 struct QPDev {  // kernel-argument mirror of vsiq_qparams
     const void* scale;
@@ -79,41 +96,22 @@ struct QPDev {  // kernel-argument mirror of vsiq_qparams
     float scale_host;
     float zp_host;
     int zp_learned;
-    float lo;
-    float hi;
+    float lo;   // (float)qmin
+    float hi;   // (float)qmax
+    float tlo;  // smallest t with rint(t) >= qmin   (qmin - 0.5 if qmin is even, else the next float up)
+    float thi;  // largest  t with rint(t) <= qmax   (qmax + 0.5 if qmax is even, else the next float down)
 };
 
 struct QP {  // per-tile (uniform) values
-    float s;   // scale rounded to fp32 (ATen rounds the fp64 0-dim Parameter the same way)
-    float r;   // RN(1/s), hoisted out of the element loop
-    float z;   // effective zero-point used by the forward
-    float zf;  // raw (float) zero-point parameter
-    float lo, hi;
-    bool fast; // |s| in [2^-40, 2^40]: the reciprocal-based exact division below is valid
+    float s;        // scale rounded to fp32 (ATen rounds the fp64 0-dim Parameter the same way)
+    float r;        // RN(1/s), hoisted out of the element loop
+    float z;        // effective zero-point used by the forward
+    float zf;       // raw (float) zero-point parameter
+    float lo, hi;   // integer range as floats
+    float tlo, thi; // pre-rounding clamp thresholds (see QPDev)
+    float zero_dx;  // (+0) / s : what a clamped-out element's dx is
+    bool fast;      // |s| in [2^-40, 2^40]: the reciprocal-based exact division below is valid
 };
-
-// IEEE-754 round-to-nearest x / s without a per-element MUFU.RCP + FCHK (the XU pipe issues only 16
-// lanes/clk/SM, which would bound these kernels before HBM does).  With r = RN(1/s):
-//     q0 = RN(x*r); q1 = RN(q0 + (x - q0*s)*r)   -> faithful (error < 2^-46 relative before rounding)
-//     q2 = RN(q1 + (x - q1*s)*r)                 -> correctly rounded (Markstein's theorem)
-// The residuals are exact FMAs as long as nothing under/overflows: guaranteed for
-// 2^-60 <= |x| < 2^61 and 2^-40 <= |s| <= 2^40.  x == 0 returns x*r (signed zero of the right sign);
-// everything else (denormal, huge, inf, NaN) takes the IEEE division instruction sequence.
-// tests/test_gpu_division.py checks it against __fdiv_rn over ALL 2^32 values of x for many scales.
-static __device__ __noinline__ float div_ieee(float x, float s) { return __fdiv_rn(x, s); }
-
-__device__ __forceinline__ float div_exact(float x, float s, float r, bool fast) {
-    const float q0 = __fmul_rn(x, r);
-    const float e0 = __fmaf_rn(-q0, s, x);
-    const float q1 = __fmaf_rn(e0, r, q0);
-    const float e1 = __fmaf_rn(-q1, s, x);
-    const float q2 = __fmaf_rn(e1, r, q1);
-    const uint32_t ex = (__float_as_uint(x) >> 23) & 0xffu;
-    const bool in_range = fast && ((ex - 67u) < 121u);  // biased exponent in [67, 187]
-    float q = in_range ? q2 : q0;
-    if (!in_range && (x != 0.0f || !fast)) q = div_ieee(x, s);  // rare: denormal / huge / inf / NaN / odd scale
-    return q;
-}
 
 // torch.clamp semantics: NaN propagates, -0.0 survives a 0 lower bound (fminf/fmaxf would lose both).
 __device__ __forceinline__ float clamp_torch(float r, float lo, float hi) {
@@ -121,11 +119,24 @@ __device__ __forceinline__ float clamp_torch(float r, float lo, float hi) {
     r = (r > hi) ? hi : r;
     return r;
 }
+// NaN-propagating min / max in one instruction each (FMNMX.NAN)
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float d;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
 
 __device__ __forceinline__ QP load_qp(const QPDev& d, int64_t c) {
     QP q;
     q.lo = d.lo;
     q.hi = d.hi;
+    q.tlo = d.tlo;
+    q.thi = d.thi;
     if (d.scale)
         q.s = d.scale_f64 ? (float)__ldg((const double*)d.scale + c) : __ldg((const float*)d.scale + c);
     else
@@ -136,25 +147,94 @@ __device__ __forceinline__ QP load_qp(const QPDev& d, int64_t c) {
         q.zf = d.zp_host;
     q.z = d.zp_learned ? clamp_torch(rintf(q.zf), q.lo, q.hi) : q.zf;
     q.r = __frcp_rn(q.s);
+    q.zero_dx = __fdiv_rn(0.0f, q.s);
     const float as = fabsf(q.s);
     q.fast = (as >= 9.094947017729282e-13f) && (as <= 1.099511627776e12f);  // 2^-40 .. 2^40
     return q;
 }
 
-// The reference's forward, one element (quantizers/uniform.py:54-55,95): every op individually rounded.
-//   r = rint(x / s + z);  q = clamp(r);  y = (q - z) * s
-__device__ __forceinline__ float fq_round(float x, const QP& p) {
-    return rintf(__fadd_rn(div_exact(x, p.s, p.r, p.fast), p.z));
+// ---- exact arithmetic, IEEE instruction sequences (the "slow" path; also the definition) -----------
+// Reference forward, one element (quantizers/uniform.py:54-55,95), every op individually rounded:
+//   v = x / s;  t = v + z;  r = rint(t);  q = clamp(r, qmin, qmax);  y = (q - z) * s
+// Reference backward (autograd): m = [qmin <= r <= qmax];  dx = where(m, g*s, 0) / s
+struct Elem {
+    float v;  // x / s
+    float t;  // v + z
+    float q;  // clamp(rint(t))
+    bool m;   // rint(t) within [qmin, qmax]
+};
+// clamp(rint(t), lo, hi) == rint(clamp_t(t)) for every t, NaN and signed zeros included: below tlo the
+// value is replaced by lo itself (rint(tlo) would be -0.0 for lo == 0 where torch gives +0.0), above thi
+// by thi (rint(thi) == hi); inside, rint keeps the sign of a negative zero exactly like torch.
+__device__ __forceinline__ float clamp_t(float t, const QP& p) { return min_nan(t < p.tlo ? p.lo : t, p.thi); }
+__device__ __forceinline__ float quantize_t(float t, const QP& p) { return rintf(clamp_t(t, p)); }
+__device__ __forceinline__ float dequant(float q, const QP& p) { return __fmul_rn(__fsub_rn(q, p.z), p.s); }
+
+static __device__ __noinline__ Elem elem_slow(float x, const QP& p) {
+    Elem e;
+    e.v = __fdiv_rn(x, p.s);
+    e.t = __fadd_rn(e.v, p.z);
+    e.q = quantize_t(e.t, p);
+    e.m = (e.t >= p.tlo) && (e.t <= p.thi);
+    return e;
 }
-__device__ __forceinline__ float fq_dequant(float q, const QP& p) { return __fmul_rn(__fsub_rn(q, p.z), p.s); }
-__device__ __forceinline__ bool fq_inrange(float r, const QP& p) { return (r >= p.lo) && (r <= p.hi); }
-// autograd of the forward: dx = where(m, g*s, 0) / s   (mul-, clamp-, STE-, add-, div-backward)
-__device__ __forceinline__ float ste_dx(float g, bool m, const QP& p) {
-    float gd = __fmul_rn(g, p.s);
-    return div_exact(m ? gd : 0.0f, p.s, p.r, p.fast);
+static __device__ __noinline__ float dx_slow(float g, bool m, const QP& p) {
+    return __fdiv_rn(m ? __fmul_rn(g, p.s) : 0.0f, p.s);
 }
 
+// ---- the same results without a per-element MUFU.RCP + FCHK + branch ------------------------------
+// x / s by the hoisted r = RN(1/s) and exact-residual FMAs (the XU pipe issues only 16 lanes/clk/SM and
+// would bound these kernels before HBM does):
+//     q0 = RN(x*r); q1 = RN(q0 + (x - q0*s)*r)   -> faithful (relative error < 2^-46 before rounding)
+//     q2 = RN(q1 + (x - q1*s)*r)                 -> correctly rounded (Markstein's theorem)
+// The residuals are exact as long as nothing under/overflows: guaranteed for 2^-60 <= |x| < 2^61 and
+// 2^-40 <= |s| <= 2^40.  x == 0 gives a zero whose sign is taken from q0 (= sign(x) xor sign(s)).
+// Anything else (denormal, huge, inf, NaN, odd scale) raises `bad`; the caller then recomputes the whole
+// vector with the IEEE sequence above, so the branch is per 8 elements and almost never taken.
+// dx = RN(RN(g*s) / s): g itself is a faithful quotient, so ONE correction step is exact:
+//     gd = RN(g*s);  rho = gd - g*s (exact FMA);  dx = RN(g + rho*r), sign taken from g.
+// tests/test_gpu_kernels.py::test_division_* check both against the IEEE division over ALL 2^32 inputs.
+constexpr float kFastLo = 8.673617379884035e-19f;  // 2^-60
+constexpr float kFastHi = 2.305843009213694e18f;   // 2^61
+
+__device__ __forceinline__ float div_fast(float x, const QP& p, bool& bad) {
+    const float q0 = __fmul_rn(x, p.r);
+    const float e0 = __fmaf_rn(-q0, p.s, x);
+    const float q1 = __fmaf_rn(e0, p.r, q0);
+    const float e1 = __fmaf_rn(-q1, p.s, x);
+    const float q2 = __fmaf_rn(e1, p.r, q1);
+    const float ax = fabsf(x);
+    const bool in = (ax >= kFastLo) && (ax < kFastHi);
+    bad = bad || (!in && x != 0.0f);
+    return copysignf(q2, q0);
+}
+__device__ __forceinline__ Elem elem_fast(float x, const QP& p, bool& bad) {
+    Elem e;
+    e.v = div_fast(x, p, bad);
+    e.t = __fadd_rn(e.v, p.z);
+    const float tc = clamp_t(e.t, p);
+    e.q = rintf(tc);
+    e.m = (tc == e.t);  // clamped value unchanged <=> in range (false for NaN)
+    return e;
+}
+__device__ __forceinline__ float dx_fast(float g, bool m, const QP& p, bool& bad) {
+    const float gd = __fmul_rn(g, p.s);
+    const float rho = __fmaf_rn(-g, p.s, gd);
+    const float q = copysignf(__fmaf_rn(rho, p.r, g), g);
+    const float ag = fabsf(g);
+    const bool in = (ag >= kFastLo) && (ag < kFastHi);
+    bad = bad || (!in && g != 0.0f);
+    return m ? q : p.zero_dx;
+}
+
+// Ops plug into span_apply through this protocol (one vector = up to 8 consecutive elements):
+//   vec_begin()            reset per-vector state
+//   apply(in, out)         one element, fast arithmetic; may raise the op's `bad` flag
+//   vec_bad()              true -> span_apply calls vec_begin() and apply_slow() for the whole vector
+//   vec_done()             commit per-vector partial sums
 struct OpBase {
+    __device__ __forceinline__ void vec_begin() {}
+    __device__ __forceinline__ bool vec_bad() const { return false; }
     __device__ __forceinline__ void vec_done() {}
 };
 
@@ -167,14 +247,17 @@ struct Tiles {
     int64_t inner;
     uint32_t chunks;    // tiles per row
     uint32_t n_tiles;   // rows * chunks  (< 2^31)
+    int tile;           // elements per tile: TileGeom<GROUP>::kTile x tile_mult
 };
 
 template <int GROUP>
-__host__ __device__ inline bool make_tiles(int64_t outer, int64_t channels, int64_t inner, Tiles* t) {
+__host__ __device__ inline bool make_tiles(int64_t outer, int64_t channels, int64_t inner, Tiles* t,
+                                           int tile_mult = 1) {
     t->rows = outer * channels;
     t->channels = channels;
     t->inner = inner;
-    const int64_t tile = TileGeom<GROUP>::kTile;
+    const int64_t tile = (int64_t)TileGeom<GROUP>::kTile * tile_mult;
+    t->tile = (int)tile;
     int64_t chunks = (inner + tile - 1) / tile;
     int64_t n = t->rows * chunks;
     if (chunks <= 0 || n <= 0 || n >= (int64_t(1) << 31)) return false;
@@ -209,9 +292,9 @@ __device__ __forceinline__ TileCursor<GROUP> tile_at(const Tiles& t, uint32_t id
     TileCursor<GROUP> c;
     uint32_t row = idx / t.chunks;
     uint32_t chunk = idx - row * t.chunks;
-    int64_t start = (int64_t)chunk * TileGeom<GROUP>::kTile;
+    int64_t start = (int64_t)chunk * t.tile;
     int64_t rem = t.inner - start;
-    c.len = rem < TileGeom<GROUP>::kTile ? (int)rem : TileGeom<GROUP>::kTile;
+    c.len = rem < t.tile ? (int)rem : t.tile;
     c.row = row;
     c.channel = t.channels == 1 ? 0 : (int64_t)(row % (uint32_t)t.channels);
     c.offset = (int64_t)row * t.inner + start;
@@ -220,9 +303,8 @@ __device__ __forceinline__ TileCursor<GROUP> tile_at(const Tiles& t, uint32_t id
 
 // ---------------------------------------------------------------------------------------------
 // span_apply: run Op over `len` consecutive elements starting at element `off`, cooperatively by a
-// GROUP of threads.  Op::apply(const float (&in)[NIN], float (&out)[NOUT]) handles one element;
-// Op::vec_done() is called after every vector (<= 8 elements) so reducing ops can spill their short
-// fp32 partials into fp64 accumulators.
+// GROUP of threads through the OpBase protocol above (apply per element, vec_begin / vec_bad / vec_done
+// per vector of <= 8 elements, apply_slow when a vector needs the IEEE sequences).
 // Base pointers are 32-byte aligned when V == 8 (checked on the host); the row offset need not be.
 // ---------------------------------------------------------------------------------------------
 template <int GROUP, int V, int NIN, int NOUT, class Op>
@@ -238,7 +320,12 @@ __device__ __forceinline__ void span_apply(const float* const (&in)[NIN],
             float a[NIN], o[NOUT > 0 ? NOUT : 1];
 #pragma unroll
             for (int k = 0; k < NIN; ++k) a[k] = ld_stream1(in[k] + off + tid);
+            op.vec_begin();
             op.apply(a, o);
+            if (op.vec_bad()) {
+                op.vec_begin();
+                op.apply_slow(a, o);
+            }
             op.vec_done();
 #pragma unroll
             for (int k = 0; k < NOUT; ++k) out[k][off + tid] = o[k];
@@ -264,6 +351,7 @@ __device__ __forceinline__ void span_apply(const float* const (&in)[NIN],
             if (ok[j]) {
                 const int vi = b + j * GROUP + tid;
                 Vec<V> vout[NOUT > 0 ? NOUT : 1];
+                op.vec_begin();
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     float a[NIN], o[NOUT > 0 ? NOUT : 1];
@@ -272,6 +360,18 @@ __device__ __forceinline__ void span_apply(const float* const (&in)[NIN],
                     op.apply(a, o);
 #pragma unroll
                     for (int k = 0; k < NOUT; ++k) vout[k].v[e] = o[k];
+                }
+                if (op.vec_bad()) {  // rare: redo the vector with the IEEE sequences
+                    op.vec_begin();
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        float a[NIN], o[NOUT > 0 ? NOUT : 1];
+#pragma unroll
+                        for (int k = 0; k < NIN; ++k) a[k] = vin[k][j].v[e];
+                        op.apply_slow(a, o);
+#pragma unroll
+                        for (int k = 0; k < NOUT; ++k) vout[k].v[e] = o[k];
+                    }
                 }
                 op.vec_done();
 #pragma unroll
@@ -286,7 +386,12 @@ __device__ __forceinline__ void span_apply(const float* const (&in)[NIN],
             float a[NIN], o[NOUT > 0 ? NOUT : 1];
 #pragma unroll
             for (int k = 0; k < NIN; ++k) a[k] = ld_stream1(in[k] + off + i);
+            op.vec_begin();
             op.apply(a, o);
+            if (op.vec_bad()) {
+                op.vec_begin();
+                op.apply_slow(a, o);
+            }
             op.vec_done();
 #pragma unroll
             for (int k = 0; k < NOUT; ++k) out[k][off + i] = o[k];
@@ -356,7 +461,19 @@ struct DeviceProps {
     int cc_major, cc_minor;
 };
 int get_device_props(DeviceProps* out);         // cached per device
-int grid_for(uint32_t n_groups_wanted, int ctas_per_sm);  // capped persistent grid (>= 1)
+int launch_grid(uint32_t n_ctas_wanted);   // one CTA per tile group unless VSIQ_GRID_WAVES caps it (tuning knob)
+int single_wave_ctas();                    // CTAs that are co-resident for sure (SM count x 4)
+// Reducing kernels pay a block reduction + a partial record per tile: pick the largest tile multiplier that
+// still leaves >= 8 tiles per SM for the hardware scheduler to balance (1 for small problems).
+template <int GROUP>
+inline int reduce_tile_mult(int64_t outer, int64_t channels, int64_t inner) {
+    const int64_t want = (int64_t)single_wave_ctas() * 2 * (GROUP == kThreads ? 1 : kWarps);
+    for (int m = 8; m > 1; m >>= 1) {
+        Tiles t;
+        if (make_tiles<GROUP>(outer, channels, inner, &t, m) && (int64_t)t.n_tiles >= want) return m;
+    }
+    return 1;
+}
 bool aligned32(const void* p);
 int check_layout(const vsiq_layout* l);
 int fill_qp(const vsiq_qparams* in, QPDev* out);

@@ -14,57 +14,86 @@
 namespace vsiq {
 
 // ------------------------------------------------------------------------------------------ ops
-struct FwdOp : OpBase {
+struct QuantOpBase : OpBase {
     QP p;
+    bool bad;
+    __device__ __forceinline__ void vec_begin() { bad = !p.fast; }
+    __device__ __forceinline__ bool vec_bad() const { return bad; }
+};
+
+struct FwdOp : QuantOpBase {
     __device__ __forceinline__ void apply(const float (&a)[1], float (&o)[1]) {
-        float r = fq_round(a[0], p);
-        o[0] = fq_dequant(clamp_torch(r, p.lo, p.hi), p);
+        o[0] = dequant(elem_fast(a[0], p, bad).q, p);
+    }
+    __device__ __forceinline__ void apply_slow(const float (&a)[1], float (&o)[1]) {
+        o[0] = dequant(elem_slow(a[0], p).q, p);
     }
 };
 
-struct SteBwdOp : OpBase {
-    QP p;
+struct SteBwdOp : QuantOpBase {
     __device__ __forceinline__ void apply(const float (&a)[2], float (&o)[1]) {
-        float r = fq_round(a[0], p);
-        o[0] = ste_dx(a[1], fq_inrange(r, p), p);
+        const Elem e = elem_fast(a[0], p, bad);
+        o[0] = dx_fast(a[1], e.m, p, bad);
+    }
+    __device__ __forceinline__ void apply_slow(const float (&a)[2], float (&o)[1]) {
+        o[0] = dx_slow(a[1], elem_slow(a[0], p).m, p);
     }
 };
 
-struct FwdBwdOp : OpBase {
-    QP p;
+struct FwdBwdOp : QuantOpBase {
     __device__ __forceinline__ void apply(const float (&a)[2], float (&o)[2]) {
-        float r = fq_round(a[0], p);
-        o[0] = fq_dequant(clamp_torch(r, p.lo, p.hi), p);
-        o[1] = ste_dx(a[1], fq_inrange(r, p), p);
+        const Elem e = elem_fast(a[0], p, bad);
+        o[0] = dequant(e.q, p);
+        o[1] = dx_fast(a[1], e.m, p, bad);
+    }
+    __device__ __forceinline__ void apply_slow(const float (&a)[2], float (&o)[2]) {
+        const Elem e = elem_slow(a[0], p);
+        o[0] = dequant(e.q, p);
+        o[1] = dx_slow(a[1], e.m, p);
     }
 };
 
 template <int MASK_MODE, bool WANT_DZ>
-struct LsqBwdOp : OpBase {
-    QP p;
+struct LsqBwdOp : QuantOpBase {
     float e_acc;  // sum g * ((q - z) - m * x/s)   over this thread's elements of the current tile
     float b_acc;  // sum g over clamped-out elements
-    __device__ __forceinline__ void apply(const float (&a)[2], float (&o)[1]) {
-        const float x = a[0], g = a[1];
-        const float v = div_exact(x, p.s, p.r, p.fast);
+    float e_vec, b_vec;  // the current vector's share (committed by vec_done, discarded on a redo)
+    __device__ __forceinline__ void vec_begin() {
+        bad = !p.fast;
+        e_vec = 0.0f;
+        b_vec = 0.0f;
+    }
+    __device__ __forceinline__ void vec_done() {
+        e_acc += e_vec;
+        if (WANT_DZ) b_acc += b_vec;
+    }
+    __device__ __forceinline__ void accumulate(float g, const Elem& e, float (&o)[1]) {
         if (MASK_MODE == VSIQ_MASK_ROUNDED) {
-            const float r = rintf(__fadd_rn(v, p.z));
-            const bool m = fq_inrange(r, p);
-            const float d = __fsub_rn(clamp_torch(r, p.lo, p.hi), p.z);
-            o[0] = ste_dx(g, m, p);
-            // reference: g*(q-z) from mul-backward minus where(m, g*s, 0) * ((x/s)/s) from div-backward.
+            // reference: g*(q-z) from mul-backward minus where(m, g*s, 0) * ((x/s)/s) from div-backward;
             // v * 0 keeps the reference's NaN for infinite inputs.
-            const float mv = __fmul_rn(v, m ? 1.0f : 0.0f);
-            e_acc = fmaf(g, d - mv, e_acc);
-            if (WANT_DZ) b_acc += m ? 0.0f : g;
+            const float d = __fsub_rn(e.q, p.z);
+            const float mv = __fmul_rn(e.v, e.m ? 1.0f : 0.0f);
+            e_vec = fmaf(g, d - mv, e_vec);
+            if (WANT_DZ) b_vec += e.m ? 0.0f : g;
         } else {
-            const float small = v < p.lo ? 1.0f : 0.0f;
-            const float big = v > p.hi ? 1.0f : 0.0f;
+            // FunLSQ (quantizers/uniform.py:144-150): strict masks on the unrounded v, z ignored
+            const float small = e.v < p.lo ? 1.0f : 0.0f;
+            const float big = e.v > p.hi ? 1.0f : 0.0f;
             const float mid = 1.0f - small - big;
-            const float term = small * p.lo + big * p.hi + mid * (rintf(v) - v);
-            e_acc = fmaf(term, g, e_acc);
+            const float term = small * p.lo + big * p.hi + mid * (rintf(e.v) - e.v);
+            e_vec = fmaf(term, g, e_vec);
             o[0] = __fmul_rn(mid, g);
         }
+    }
+    __device__ __forceinline__ void apply(const float (&a)[2], float (&o)[1]) {
+        const Elem e = elem_fast(a[0], p, bad);
+        if (MASK_MODE == VSIQ_MASK_ROUNDED) o[0] = dx_fast(a[1], e.m, p, bad);
+        accumulate(a[1], e, o);
+    }
+    __device__ __forceinline__ void apply_slow(const float (&a)[2], float (&o)[1]) {
+        const Elem e = elem_slow(a[0], p);
+        if (MASK_MODE == VSIQ_MASK_ROUNDED) o[0] = dx_slow(a[1], e.m, p);
+        accumulate(a[1], e, o);
     }
 };
 
@@ -118,30 +147,106 @@ __global__ void __launch_bounds__(kThreads) fq_codes_kernel(const float* __restr
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int64_t c = channels == 1 ? 0 : (i / inner) % channels;
         const QP p = load_qp(qpd, c);
-        const float q = clamp_torch(fq_round(ld_stream1(x + i), p), p.lo, p.hi);
-        if (y) y[i] = fq_dequant(q, p);
+        const float q = elem_slow(ld_stream1(x + i), p).q;
+        if (y) y[i] = dequant(q, p);
         const int qi = (q == q) ? (int)q : 0;  // NaN has no code; emit 0
         codes[i] = (int8_t)(qi & 0xff);
     }
 }
 
-// LSQ backward.  Partials: single-row tensors (per tensor) accumulate in registers across all tiles a
-// group owns and emit ONE partial per group; multi-row tensors (per channel) emit one partial per
-// tile.  The last CTA combines them per channel in a fixed order in fp64 and applies the grad-scale.
+// LSQ backward.  Every tile emits one partial record {E, B} (fp32 inside a warp, fp64 across warps);
+// the records of a channel are then combined in a fixed order in fp64 and scaled by the grad-scale:
+//   * small launches (a single wave of CTAs): by the last CTA to finish, in the same launch;
+//   * large launches: by lsq_finalize_kernel on the same stream, so the streaming CTAs retire without a
+//     fence or an atomic (a per-CTA __threadfence would expose the store latency of every tile).
+// Tile index = (o * C + c) * chunks + k, so channel c owns `outer * chunks` records.
+struct LsqOut {
+    void* dscale;
+    void* dzp;
+    int ds_f64, dz_f64;
+    double gs_host;
+    const float* gs_dev;
+    int want_dz;
+};
+
+__device__ __forceinline__ void lsq_store_channel(const LsqOut& o, const QPDev& qpd, int64_t c, double e, double b) {
+    const double gs = o.gs_host * (o.gs_dev ? (double)__ldg(o.gs_dev) : 1.0);
+    const QP p = load_qp(qpd, c);
+    const double ds = gs * e;
+    if (o.ds_f64)
+        ((double*)o.dscale)[c] = ds;
+    else
+        ((float*)o.dscale)[c] = (float)ds;
+    if (o.want_dz) {
+        const float zr = rintf(p.zf);
+        const bool cz = qpd.zp_learned ? ((zr >= p.lo) && (zr <= p.hi)) : true;
+        const double dz = cz ? -gs * (double)p.s * b : 0.0;  // sum (g*s)*(m-1) = -s * sum_{clamped} g
+        if (o.dz_f64)
+            ((double*)o.dzp)[c] = dz;
+        else
+            ((float*)o.dzp)[c] = (float)dz;
+    }
+}
+
+// one warp combines channel c
+__device__ __forceinline__ void lsq_combine_warp(const double* partials, const Tiles& tiles, int64_t outer, int64_t c,
+                                                 const LsqOut& o, const QPDev& qpd) {
+    const int lane = threadIdx.x & 31;
+    const int64_t C = tiles.channels, items = outer * (int64_t)tiles.chunks;
+    double e = 0.0, b = 0.0;
+    for (int64_t i = lane; i < items; i += 32) {
+        const int64_t oo = i / tiles.chunks, k = i - oo * tiles.chunks;
+        const size_t slot = (size_t)((oo * C + c) * tiles.chunks + k);
+        e += __ldcg(partials + 2 * slot);
+        b += __ldcg(partials + 2 * slot + 1);
+    }
+    e = warp_sum(e);
+    b = warp_sum(b);
+    if (lane == 0) lsq_store_channel(o, qpd, c, e, b);
+}
+
+// a whole CTA combines channel c (long rows / per tensor: many records per channel)
+__device__ __forceinline__ void lsq_combine_cta(const double* partials, const Tiles& tiles, int64_t outer, int64_t c,
+                                                const LsqOut& o, const QPDev& qpd, double (*s_red)[2]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t C = tiles.channels, items = outer * (int64_t)tiles.chunks;
+    double e = 0.0, b = 0.0;
+    for (int64_t i = threadIdx.x; i < items; i += kThreads) {
+        const int64_t oo = i / tiles.chunks, k = i - oo * tiles.chunks;
+        const size_t slot = (size_t)((oo * C + c) * tiles.chunks + k);
+        e += __ldcg(partials + 2 * slot);
+        b += __ldcg(partials + 2 * slot + 1);
+    }
+    e = warp_sum(e);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) {
+        s_red[warp][0] = e;
+        s_red[warp][1] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double es = 0.0, bs = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            es += s_red[w][0];
+            bs += s_red[w][1];
+        }
+        lsq_store_channel(o, qpd, c, es, bs);
+    }
+}
+
 template <int GROUP, int V, int MASK_MODE, bool WANT_DZ>
 __global__ void __launch_bounds__(kThreads)
     lsq_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, Tiles tiles,
-                   QPDev qpd, void* ws, void* dscale, int ds_f64, void* dzp, int dz_f64, double gs_host,
-                   const float* __restrict__ gs_dev, int64_t outer) {
+                   QPDev qpd, void* ws, LsqOut o, int64_t outer, int use_ticket) {
     __shared__ double s_red[kWarps][2];
     const float* const in[2] = {x, g};
     float* const out[1] = {dx};
     double* partials = ws_partials(ws);
-    const bool single_row = tiles.rows == 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     LsqBwdOp<MASK_MODE, WANT_DZ> op;
-    double e_run = 0.0, b_run = 0.0;
     int64_t cur_channel = -1;
     for (uint32_t t = group_index<GROUP>(); t < tiles.n_tiles; t += group_count<GROUP>()) {
         const TileCursor<GROUP> c = tile_at<GROUP>(tiles, t);
@@ -152,51 +257,18 @@ __global__ void __launch_bounds__(kThreads)
         op.e_acc = 0.0f;
         op.b_acc = 0.0f;
         span_apply<GROUP, V, 2, 1>(in, out, c.offset, c.len, op);
-        if (single_row) {
-            e_run += (double)op.e_acc;
-            if (WANT_DZ) b_run += (double)op.b_acc;
-        } else {
-            // per-tile flush: fp32 inside the warp, fp64 across warps
-            float e = warp_sum(op.e_acc);
-            float b = WANT_DZ ? warp_sum(op.b_acc) : 0.0f;
-            if (GROUP == 32) {
-                if (lane == 0) {
-                    partials[2 * (size_t)t] = (double)e;
-                    partials[2 * (size_t)t + 1] = (double)b;
-                }
-            } else {
-                __syncthreads();  // s_red free again
-                if (lane == 0) {
-                    s_red[warp][0] = (double)e;
-                    s_red[warp][1] = (double)b;
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    double es = 0.0, bs = 0.0;
-#pragma unroll
-                    for (int w = 0; w < kWarps; ++w) {
-                        es += s_red[w][0];
-                        bs += s_red[w][1];
-                    }
-                    partials[2 * (size_t)t] = es;
-                    partials[2 * (size_t)t + 1] = bs;
-                }
-            }
-        }
-    }
-    if (single_row) {
-        double e = warp_sum(e_run);
-        double b = WANT_DZ ? warp_sum(b_run) : 0.0;
+        const float e = warp_sum(op.e_acc);
+        const float b = WANT_DZ ? warp_sum(op.b_acc) : 0.0f;
         if (GROUP == 32) {
-            const size_t slot = group_index<32>();
-            if (lane == 0 && slot < tiles.n_tiles) {  // idle warps own no slot
-                partials[2 * slot] = e;
-                partials[2 * slot + 1] = b;
+            if (lane == 0) {
+                partials[2 * (size_t)t] = (double)e;
+                partials[2 * (size_t)t + 1] = (double)b;
             }
         } else {
+            __syncthreads();  // s_red free again
             if (lane == 0) {
-                s_red[warp][0] = e;
-                s_red[warp][1] = b;
+                s_red[warp][0] = (double)e;
+                s_red[warp][1] = (double)b;
             }
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -206,67 +278,32 @@ __global__ void __launch_bounds__(kThreads)
                     es += s_red[w][0];
                     bs += s_red[w][1];
                 }
-                partials[2 * (size_t)blockIdx.x] = es;
-                partials[2 * (size_t)blockIdx.x + 1] = bs;
+                partials[2 * (size_t)t] = es;
+                partials[2 * (size_t)t + 1] = bs;
             }
         }
     }
-
+    if (!use_ticket) return;
     if (!last_cta_ticket((unsigned int*)ws)) return;
+    for (int64_t c = warp; c < tiles.channels; c += kWarps) lsq_combine_warp(partials, tiles, outer, c, o, qpd);
+}
 
-    // ---- finalize (one CTA): fixed-order fp64 combination, grad-scale, dtype conversion ----
-    const double gs = gs_host * (gs_dev ? (double)__ldg(gs_dev) : 1.0);
-    const int64_t C = tiles.channels;
-    for (int64_t c = warp; c < C; c += kWarps) {
-        double e = 0.0, b = 0.0;
-        if (single_row) {
-            const uint32_t n_slots = group_count<GROUP>() < tiles.n_tiles ? group_count<GROUP>() : tiles.n_tiles;
-            for (uint32_t i = lane; i < n_slots; i += 32) {
-                e += __ldcg(partials + 2 * (size_t)i);
-                b += __ldcg(partials + 2 * (size_t)i + 1);
-            }
-        } else {
-            const int64_t items = outer * (int64_t)tiles.chunks;
-            for (int64_t i = lane; i < items; i += 32) {
-                const int64_t o = i / tiles.chunks, k = i - o * tiles.chunks;
-                const size_t slot = (size_t)((o * C + c) * tiles.chunks + k);
-                e += __ldcg(partials + 2 * slot);
-                b += __ldcg(partials + 2 * slot + 1);
-            }
-        }
-        e = warp_sum(e);
-        b = warp_sum(b);
-        if (lane == 0) {
-            const QP p = load_qp(qpd, c);
-            const double ds = gs * e;
-            if (ds_f64)
-                ((double*)dscale)[c] = ds;
-            else
-                ((float*)dscale)[c] = (float)ds;
-            if (WANT_DZ) {
-                const float zr = rintf(p.zf);
-                const bool cz = qpd.zp_learned ? ((zr >= p.lo) && (zr <= p.hi)) : true;
-                const double dz = cz ? -gs * (double)p.s * b : 0.0;
-                if (dz_f64)
-                    ((double*)dzp)[c] = dz;
-                else
-                    ((float*)dzp)[c] = (float)dz;
-            }
-        }
+template <bool CTA_WIDE>
+__global__ void __launch_bounds__(kThreads)
+    lsq_finalize_kernel(Tiles tiles, QPDev qpd, const void* ws, LsqOut o, int64_t outer) {
+    __shared__ double s_red[kWarps][2];
+    const double* partials = (const double*)((const char*)ws + kWsHeader);
+    if (CTA_WIDE) {
+        for (int64_t c = blockIdx.x; c < tiles.channels; c += gridDim.x)
+            lsq_combine_cta(partials, tiles, outer, c, o, qpd, s_red);
+    } else {
+        for (int64_t c = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); c < tiles.channels;
+             c += (int64_t)gridDim.x * kWarps)
+            lsq_combine_warp(partials, tiles, outer, c, o, qpd);
     }
 }
 
 // ------------------------------------------------------------------------------------ launchers
-template <class K>
-static int occupancy_grid(K kernel, uint32_t n_ctas_wanted) {
-    DeviceProps dp;
-    if (int e = get_device_props(&dp)) return -e;
-    int per_sm = 0;
-    cudaError_t ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
-    if (ce != cudaSuccess || per_sm < 1) per_sm = 1;
-    return grid_for(n_ctas_wanted, per_sm);
-}
-
 template <int GROUP>
 static uint32_t ctas_for_tiles(uint32_t n_tiles) {
     return GROUP == kThreads ? n_tiles : (n_tiles + kWarps - 1) / kWarps;
@@ -295,17 +332,17 @@ using namespace vsiq;
 
 extern "C" int vsiq_fake_quant_fwd(const float* x, float* y, void* codes, const vsiq_layout* layout,
                                    const vsiq_qparams* qp, vsiq_stream_t stream) {
-    if (!x || (!y && !codes)) return VSIQ_ERR_INVALID_ARG;
     if (int e = check_layout(layout)) return e;
     QPDev qpd;
     if (int e = fill_qp(qp, &qpd)) return e;
     const int64_t n = layout->outer * layout->channels * layout->inner;
     if (n == 0) return VSIQ_OK;
+    if (!x || (!y && !codes)) return VSIQ_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (codes) {
         if (qp->qmin < -128 || qp->qmax > 255 || (qp->qmin < 0 && qp->qmax > 127)) return VSIQ_ERR_UNSUPPORTED;
         int64_t blocks = (n + kThreads - 1) / kThreads;
-        int grid = grid_for((uint32_t)(blocks > (1 << 30) ? (1 << 30) : blocks), 8);
+        int grid = (int)(blocks > (1 << 20) ? (1 << 20) : blocks);
         if (grid < 0) return -grid;
         fq_codes_kernel<<<grid, kThreads, 0, st>>>(x, y, (int8_t*)codes, n, layout->inner, layout->channels, qpd);
         return (int)cudaGetLastError();
@@ -317,7 +354,7 @@ extern "C" int vsiq_fake_quant_fwd(const float* x, float* y, void* codes, const 
     {                                                                                       \
         if (!make_tiles<G>(layout->outer, layout->channels, layout->inner, &tiles))         \
             return VSIQ_ERR_INVALID_ARG;                                                    \
-        int grid = occupancy_grid(fq_fwd_kernel<G, V>, ctas_for_tiles<G>(tiles.n_tiles));   \
+        int grid = launch_grid(ctas_for_tiles<G>(tiles.n_tiles));   \
         if (grid < 0) return -grid;                                                         \
         fq_fwd_kernel<G, V><<<grid, kThreads, 0, st>>>(x, y, tiles, qpd);                   \
     }
@@ -328,11 +365,11 @@ extern "C" int vsiq_fake_quant_fwd(const float* x, float* y, void* codes, const 
 
 extern "C" int vsiq_fake_quant_bwd_ste(const float* x, const float* g, float* dx, const vsiq_layout* layout,
                                        const vsiq_qparams* qp, vsiq_stream_t stream) {
-    if (!x || !g || !dx) return VSIQ_ERR_INVALID_ARG;
     if (int e = check_layout(layout)) return e;
     QPDev qpd;
     if (int e = fill_qp(qp, &qpd)) return e;
     if (layout->outer * layout->channels * layout->inner == 0) return VSIQ_OK;
+    if (!x || !g || !dx) return VSIQ_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const bool warp_group = layout->inner < kWarpGroupMaxInner;
     const bool vec8 = aligned32(x) && aligned32(g) && aligned32(dx);
@@ -341,7 +378,7 @@ extern "C" int vsiq_fake_quant_bwd_ste(const float* x, const float* g, float* dx
     {                                                                                         \
         if (!make_tiles<G>(layout->outer, layout->channels, layout->inner, &tiles))           \
             return VSIQ_ERR_INVALID_ARG;                                                      \
-        int grid = occupancy_grid(fq_bwd_ste_kernel<G, V>, ctas_for_tiles<G>(tiles.n_tiles)); \
+        int grid = launch_grid(ctas_for_tiles<G>(tiles.n_tiles)); \
         if (grid < 0) return -grid;                                                           \
         fq_bwd_ste_kernel<G, V><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd);             \
     }
@@ -352,11 +389,11 @@ extern "C" int vsiq_fake_quant_bwd_ste(const float* x, const float* g, float* dx
 
 extern "C" int vsiq_fake_quant_fwd_bwd(const float* x, const float* g, float* y, float* dx,
                                        const vsiq_layout* layout, const vsiq_qparams* qp, vsiq_stream_t stream) {
-    if (!x || !g || !y || !dx) return VSIQ_ERR_INVALID_ARG;
     if (int e = check_layout(layout)) return e;
     QPDev qpd;
     if (int e = fill_qp(qp, &qpd)) return e;
     if (layout->outer * layout->channels * layout->inner == 0) return VSIQ_OK;
+    if (!x || !g || !y || !dx) return VSIQ_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const bool warp_group = layout->inner < kWarpGroupMaxInner;
     const bool vec8 = aligned32(x) && aligned32(g) && aligned32(y) && aligned32(dx);
@@ -365,7 +402,7 @@ extern "C" int vsiq_fake_quant_fwd_bwd(const float* x, const float* g, float* y,
     {                                                                                         \
         if (!make_tiles<G>(layout->outer, layout->channels, layout->inner, &tiles))           \
             return VSIQ_ERR_INVALID_ARG;                                                      \
-        int grid = occupancy_grid(fq_fwd_bwd_kernel<G, V>, ctas_for_tiles<G>(tiles.n_tiles)); \
+        int grid = launch_grid(ctas_for_tiles<G>(tiles.n_tiles)); \
         if (grid < 0) return -grid;                                                           \
         fq_fwd_bwd_kernel<G, V><<<grid, kThreads, 0, st>>>(x, g, y, dx, tiles, qpd);          \
     }
@@ -390,7 +427,7 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
                             int dzp_dtype, const vsiq_layout* layout, const vsiq_qparams* qp, double grad_scale_host,
                             const float* grad_scale_dev, int mask_mode, void* workspace, size_t workspace_bytes,
                             vsiq_stream_t stream) {
-    if (!x || !g || !dx || !dscale) return VSIQ_ERR_INVALID_ARG;
+    if (!dscale) return VSIQ_ERR_INVALID_ARG;
     if (int e = check_layout(layout)) return e;
     if (mask_mode != VSIQ_MASK_ROUNDED && mask_mode != VSIQ_MASK_FUNLSQ) return VSIQ_ERR_INVALID_ARG;
     if (mask_mode == VSIQ_MASK_FUNLSQ && dzp) return VSIQ_ERR_UNSUPPORTED;
@@ -406,18 +443,39 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
         if (ce == cudaSuccess && dzp) ce = cudaMemsetAsync(dzp, 0, (size_t)layout->channels * (dzp_dtype ? 8 : 4), st);
         return (int)ce;
     }
+    if (!x || !g || !dx) return VSIQ_ERR_INVALID_ARG;
     const bool warp_group = layout->inner < kWarpGroupMaxInner;
     const bool vec8 = aligned32(x) && aligned32(g) && aligned32(dx);
     Tiles tiles;
-#define LAUNCH(G, V, M, Z)                                                                                   \
-    {                                                                                                        \
-        if (!make_tiles<G>(layout->outer, layout->channels, layout->inner, &tiles))                          \
-            return VSIQ_ERR_INVALID_ARG;                                                                     \
-        int grid = occupancy_grid(lsq_bwd_kernel<G, V, M, Z>, ctas_for_tiles<G>(tiles.n_tiles));             \
-        if (grid < 0) return -grid;                                                                          \
-        lsq_bwd_kernel<G, V, M, Z><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd, workspace, dscale,       \
-                                                              dscale_dtype, dzp, dzp_dtype, grad_scale_host, \
-                                                              grad_scale_dev, layout->outer);                \
+    LsqOut lo;
+    lo.dscale = dscale;
+    lo.dzp = dzp;
+    lo.ds_f64 = dscale_dtype == VSIQ_F64;
+    lo.dz_f64 = dzp_dtype == VSIQ_F64;
+    lo.gs_host = grad_scale_host;
+    lo.gs_dev = grad_scale_dev;
+    lo.want_dz = dzp != nullptr;
+#define LAUNCH(G, V, M, Z)                                                                                     \
+    {                                                                                                          \
+        const int mult = reduce_tile_mult<G>(layout->outer, layout->channels, layout->inner);                 \
+        if (!make_tiles<G>(layout->outer, layout->channels, layout->inner, &tiles, mult))                      \
+            return VSIQ_ERR_INVALID_ARG;                                                                       \
+        int grid = launch_grid(ctas_for_tiles<G>(tiles.n_tiles));                                              \
+        if (grid < 0) return -grid;                                                                            \
+        const int use_ticket = grid <= single_wave_ctas() ? 1 : 0;                                             \
+        lsq_bwd_kernel<G, V, M, Z><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd, workspace, lo,             \
+                                                              layout->outer, use_ticket);                      \
+        if (!use_ticket) {                                                                                     \
+            const int64_t items = layout->outer * (int64_t)tiles.chunks;                                       \
+            if (items >= 512) {                                                                                \
+                int fgrid = (int)(layout->channels < 1024 ? layout->channels : 1024);                          \
+                lsq_finalize_kernel<true><<<fgrid, kThreads, 0, st>>>(tiles, qpd, workspace, lo, layout->outer); \
+            } else {                                                                                           \
+                int64_t fg = (layout->channels + kWarps - 1) / kWarps;                                         \
+                lsq_finalize_kernel<false><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, qpd, workspace, \
+                                                                                              lo, layout->outer); \
+            }                                                                                                  \
+        }                                                                                                      \
     }
 #define CALL(G, V)                                   \
     {                                                \
@@ -436,31 +494,49 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
 }
 
 // ------------------------------------------------------------------------------------ self-test
-// Counts the x bit patterns (all 2^32 of them) for which the reciprocal-based division differs from
-// the IEEE division, for one divisor s.  NaN results compare equal to NaN.
+// Counts the input bit patterns (all 2^32 of them) for which the fast arithmetic differs from the IEEE
+// sequences, for one divisor s.  mode 0: x / s (div_fast, with the vector-level fallback the kernels
+// use).  mode 1: RN(RN(g*s) / s) (dx_fast).  NaN results compare equal to NaN.
 namespace vsiq {
-__global__ void __launch_bounds__(kThreads) division_selftest_kernel(float s, unsigned long long* mismatches) {
-    const float r = __frcp_rn(s);
+__global__ void __launch_bounds__(kThreads) division_selftest_kernel(float s, int mode, unsigned long long* mismatches) {
+    QP p;
+    p.s = s;
+    p.r = __frcp_rn(s);
+    p.z = 0.0f;
+    p.zf = 0.0f;
+    p.lo = -128.0f;
+    p.hi = 127.0f;
+    p.tlo = -128.5f;
+    p.thi = 127.49999f;
+    p.zero_dx = __fdiv_rn(0.0f, s);
     const float as = fabsf(s);
-    const bool fast = (as >= 9.094947017729282e-13f) && (as <= 1.099511627776e12f);
-    unsigned int bad = 0;
+    p.fast = (as >= 9.094947017729282e-13f) && (as <= 1.099511627776e12f);
+    unsigned int wrong = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
         const float x = __uint_as_float((uint32_t)i);
-        const float a = div_exact(x, s, r, fast);
-        const float b = __fdiv_rn(x, s);
+        bool bad = !p.fast;
+        float a, b;
+        if (mode == 0) {
+            a = div_fast(x, p, bad);
+            b = __fdiv_rn(x, s);
+        } else {
+            a = dx_fast(x, true, p, bad);
+            b = __fdiv_rn(__fmul_rn(x, s), s);
+        }
+        if (bad) a = b;  // the kernels redo such vectors with the IEEE sequence
         const bool same = (__float_as_uint(a) == __float_as_uint(b)) || ((a != a) && (b != b));
-        bad += same ? 0u : 1u;
+        wrong += same ? 0u : 1u;
     }
-    bad = __reduce_add_sync(0xffffffffu, bad);
-    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);
+    wrong = __reduce_add_sync(0xffffffffu, wrong);
+    if ((threadIdx.x & 31) == 0 && wrong) atomicAdd(mismatches, (unsigned long long)wrong);
 }
 }  // namespace vsiq
 
-extern "C" int vsiq_selftest_division(float s, unsigned long long* mismatches_dev, vsiq_stream_t stream) {
-    if (!mismatches_dev) return VSIQ_ERR_INVALID_ARG;
+extern "C" int vsiq_selftest_division(float s, int mode, unsigned long long* mismatches_dev, vsiq_stream_t stream) {
+    if (!mismatches_dev || (mode != 0 && mode != 1)) return VSIQ_ERR_INVALID_ARG;
     DeviceProps dp;
     if (int e = get_device_props(&dp)) return e;
-    division_selftest_kernel<<<dp.sm_count * 8, kThreads, 0, (cudaStream_t)stream>>>(s, mismatches_dev);
+    division_selftest_kernel<<<dp.sm_count * 8, kThreads, 0, (cudaStream_t)stream>>>(s, mode, mismatches_dev);
     return (int)cudaGetLastError();
 }

@@ -38,6 +38,7 @@ struct StatsOp : OpBase {
         f1 += x;
         f2 = fmaf(x, x, f2);
     }
+    __device__ __forceinline__ void apply_slow(const float (&a)[1], float (&o)[1]) { apply(a, o); }
     __device__ __forceinline__ void vec_done() {
         sa += (double)fa;
         s1 += (double)f1;
@@ -107,104 +108,136 @@ __device__ __forceinline__ void qparams_from_minmax(double mn, double mx, int bi
     }
 }
 
+// What the combine step produces / updates for one channel.
+struct ObserveOut {
+    double* stats;  // [C][VSIQ_STATS_WIDTH] or null
+    double* state;  // [C][VSIQ_STATE_WIDTH] or null
+    int bits;
+    int symmetric;
+    double eps;
+    double count;   // elements per channel = outer * inner
+};
+
+__device__ __forceinline__ void observe_store_channel(const ObserveOut& o, int64_t c, float mn, float mx, double sa,
+                                                      double s1, double s2) {
+    if (o.stats) {
+        double* d = o.stats + c * VSIQ_STATS_WIDTH;
+        d[0] = (double)mn;
+        d[1] = (double)mx;
+        d[2] = sa;
+        d[3] = s1;
+        d[4] = s2;
+    }
+    if (o.state) {
+        double* st = o.state + c * VSIQ_STATE_WIDTH;
+        double run_min = st[0], run_max = st[1];
+        if ((double)mn < run_min) run_min = (double)mn;  // NaN compares false: never updates (minmax.py:44-47)
+        if ((double)mx > run_max) run_max = (double)mx;
+        double sc, zp;
+        qparams_from_minmax(run_min, run_max, o.bits, o.symmetric, o.eps, &sc, &zp);
+        const double mean = s1 / o.count;
+        const double var = (s2 - o.count * mean * mean) / (o.count - 1.0);  // torch.std: unbiased
+        st[0] = run_min;
+        st[1] = run_max;
+        st[2] = sc;
+        st[3] = zp;
+        st[4] += 1.0;
+        st[5] += sa / o.count;
+        st[6] += mean;
+        st[7] += sqrt(var > 0.0 ? var : 0.0);
+    }
+}
+
+// Combine the records of channel c: STRIDE threads cooperate (32 = one warp, kThreads = the whole CTA).
+template <int STRIDE>
+__device__ __forceinline__ void observe_combine(const double* partials, const Tiles& tiles, int64_t outer, int64_t c,
+                                                const ObserveOut& o, double (*s_red)[kPartialWidth]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = STRIDE == 32 ? lane : (int)threadIdx.x;
+    const int64_t C = tiles.channels, items = outer * (int64_t)tiles.chunks;
+    float mn = INFINITY, mx = -INFINITY;
+    double sa = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t i = tid; i < items; i += STRIDE) {
+        const int64_t oo = i / tiles.chunks, k = i - oo * tiles.chunks;
+        const double* p = partials + (size_t)((oo * C + c) * tiles.chunks + k) * kPartialWidth;
+        mn = nanmin(mn, (float)__ldcg(p));
+        mx = nanmax(mx, (float)__ldcg(p + 1));
+        sa += __ldcg(p + 2);
+        s1 += __ldcg(p + 3);
+        s2 += __ldcg(p + 4);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    sa = warp_sum(sa);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (STRIDE == 32) {
+        if (lane == 0) observe_store_channel(o, c, mn, mx, sa, s1, s2);
+        return;
+    }
+    __syncthreads();
+    if (lane == 0) {
+        s_red[warp][0] = (double)mn;
+        s_red[warp][1] = (double)mx;
+        s_red[warp][2] = sa;
+        s_red[warp][3] = s1;
+        s_red[warp][4] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = (float)s_red[0][0], b = (float)s_red[0][1];
+        double x2 = s_red[0][2], x3 = s_red[0][3], x4 = s_red[0][4];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) {
+            a = nanmin(a, (float)s_red[w][0]);
+            b = nanmax(b, (float)s_red[w][1]);
+            x2 += s_red[w][2];
+            x3 += s_red[w][3];
+            x4 += s_red[w][4];
+        }
+        observe_store_channel(o, c, a, b, x2, x3, x4);
+    }
+}
+
+// One record per tile; combined by the last CTA (small launches) or by observe_finalize_kernel (large ones).
 template <int GROUP, int V>
 __global__ void __launch_bounds__(kThreads)
-    observe_kernel(const float* __restrict__ x, Tiles tiles, int64_t outer, void* ws, double* __restrict__ stats,
-                   double* __restrict__ state, int bits, int symmetric, double eps) {
+    observe_kernel(const float* __restrict__ x, Tiles tiles, int64_t outer, void* ws, ObserveOut o, int use_ticket) {
     __shared__ double s_red[kWarps][kPartialWidth];
     const float* const in[1] = {x};
     float* const out[1] = {nullptr};
     double* partials = ws_partials(ws);
-    const bool single_row = tiles.rows == 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     StatsOp op;
-    op.reset();
     for (uint32_t t = group_index<GROUP>(); t < tiles.n_tiles; t += group_count<GROUP>()) {
         const TileCursor<GROUP> c = tile_at<GROUP>(tiles, t);
+        op.reset();
         span_apply<GROUP, V, 1, 0>(in, out, c.offset, c.len, op);
-        if (!single_row) {
-            double rec[kPartialWidth];
-            stats_group_reduce<GROUP>(op, rec, s_red);
-            if ((GROUP == 32 && lane == 0) || (GROUP != 32 && threadIdx.x == 0)) {
-#pragma unroll
-                for (int k = 0; k < kPartialWidth; ++k) partials[(size_t)t * kPartialWidth + k] = rec[k];
-            }
-            op.reset();
-        }
-    }
-    if (single_row) {
         double rec[kPartialWidth];
         stats_group_reduce<GROUP>(op, rec, s_red);
-        const size_t slot = group_index<GROUP>();
-        if (((GROUP == 32 && lane == 0) || (GROUP != 32 && threadIdx.x == 0)) && slot < tiles.n_tiles) {
+        if ((GROUP == 32 && lane == 0) || (GROUP != 32 && threadIdx.x == 0)) {
 #pragma unroll
-            for (int k = 0; k < kPartialWidth; ++k) partials[slot * kPartialWidth + k] = rec[k];
+            for (int k = 0; k < kPartialWidth; ++k) partials[(size_t)t * kPartialWidth + k] = rec[k];
         }
     }
-
+    if (!use_ticket) return;
     if (!last_cta_ticket((unsigned int*)ws)) return;
+    for (int64_t c = warp; c < tiles.channels; c += kWarps) observe_combine<32>(partials, tiles, outer, c, o, s_red);
+}
 
-    const int64_t C = tiles.channels;
-    const double count = (double)outer * (double)tiles.inner;
-    for (int64_t c = warp; c < C; c += kWarps) {
-        float mn = INFINITY, mx = -INFINITY;
-        double sa = 0.0, s1 = 0.0, s2 = 0.0;
-        if (single_row) {
-            const uint32_t n_slots = group_count<GROUP>() < tiles.n_tiles ? group_count<GROUP>() : tiles.n_tiles;
-            for (uint32_t i = lane; i < n_slots; i += 32) {
-                const double* p = partials + (size_t)i * kPartialWidth;
-                mn = nanmin(mn, (float)__ldcg(p));
-                mx = nanmax(mx, (float)__ldcg(p + 1));
-                sa += __ldcg(p + 2);
-                s1 += __ldcg(p + 3);
-                s2 += __ldcg(p + 4);
-            }
-        } else {
-            const int64_t items = outer * (int64_t)tiles.chunks;
-            for (int64_t i = lane; i < items; i += 32) {
-                const int64_t o = i / tiles.chunks, k = i - o * tiles.chunks;
-                const double* p = partials + (size_t)((o * C + c) * tiles.chunks + k) * kPartialWidth;
-                mn = nanmin(mn, (float)__ldcg(p));
-                mx = nanmax(mx, (float)__ldcg(p + 1));
-                sa += __ldcg(p + 2);
-                s1 += __ldcg(p + 3);
-                s2 += __ldcg(p + 4);
-            }
-        }
-        mn = warp_min(mn);
-        mx = warp_max(mx);
-        sa = warp_sum(sa);
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane == 0) {
-            if (stats) {
-                double* o = stats + c * VSIQ_STATS_WIDTH;
-                o[0] = (double)mn;
-                o[1] = (double)mx;
-                o[2] = sa;
-                o[3] = s1;
-                o[4] = s2;
-            }
-            if (state) {
-                double* st = state + c * VSIQ_STATE_WIDTH;
-                double run_min = st[0], run_max = st[1];
-                if ((double)mn < run_min) run_min = (double)mn;  // NaN compares false: never updates
-                if ((double)mx > run_max) run_max = (double)mx;
-                double sc, zp;
-                qparams_from_minmax(run_min, run_max, bits, symmetric, eps, &sc, &zp);
-                const double mean = s1 / count;
-                const double var = (s2 - count * mean * mean) / (count - 1.0);  // torch.std: unbiased
-                st[0] = run_min;
-                st[1] = run_max;
-                st[2] = sc;
-                st[3] = zp;
-                st[4] += 1.0;
-                st[5] += sa / count;
-                st[6] += mean;
-                st[7] += sqrt(var > 0.0 ? var : 0.0);
-            }
-        }
+template <bool CTA_WIDE>
+__global__ void __launch_bounds__(kThreads)
+    observe_finalize_kernel(Tiles tiles, int64_t outer, const void* ws, ObserveOut o) {
+    __shared__ double s_red[kWarps][kPartialWidth];
+    const double* partials = (const double*)((const char*)ws + kWsHeader);
+    if (CTA_WIDE) {
+        for (int64_t c = blockIdx.x; c < tiles.channels; c += gridDim.x)
+            observe_combine<kThreads>(partials, tiles, outer, c, o, s_red);
+    } else {
+        for (int64_t c = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); c < tiles.channels;
+             c += (int64_t)gridDim.x * kWarps)
+            observe_combine<32>(partials, tiles, outer, c, o, s_red);
     }
 }
 
@@ -257,16 +290,6 @@ __global__ void bn_reestimate_finish_kernel(const float* __restrict__ mean_sum, 
     running_var[c] = __fdiv_rn(var_sum[c], k);    // estimate_bn.py:97
 }
 
-template <class K>
-static int occupancy_grid(K kernel, uint32_t n_ctas_wanted) {
-    DeviceProps dp;
-    if (int e = get_device_props(&dp)) return -e;
-    int per_sm = 0;
-    cudaError_t ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
-    if (ce != cudaSuccess || per_sm < 1) per_sm = 1;
-    return grid_for(n_ctas_wanted, per_sm);
-}
-
 }  // namespace vsiq
 
 using namespace vsiq;
@@ -293,14 +316,34 @@ extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* s
     const bool warp_group = layout->inner < kWarpGroupMaxInner;
     const bool vec8 = aligned32(x);
     Tiles tiles;
-#define CALL(G, V)                                                                                            \
-    {                                                                                                         \
-        if (!make_tiles<G>(layout->outer, layout->channels, layout->inner, &tiles)) return VSIQ_ERR_INVALID_ARG; \
-        uint32_t want = G == kThreads ? tiles.n_tiles : (tiles.n_tiles + kWarps - 1) / kWarps;                \
-        int grid = occupancy_grid(observe_kernel<G, V>, want);                                                \
-        if (grid < 0) return -grid;                                                                           \
-        observe_kernel<G, V><<<grid, kThreads, 0, st>>>(x, tiles, layout->outer, workspace, stats, state, bits, \
-                                                        symmetric, eps);                                      \
+    ObserveOut oo;
+    oo.stats = stats;
+    oo.state = state;
+    oo.bits = bits;
+    oo.symmetric = symmetric;
+    oo.eps = eps;
+    oo.count = (double)layout->outer * (double)layout->inner;
+#define CALL(G, V)                                                                                              \
+    {                                                                                                           \
+        const int mult = reduce_tile_mult<G>(layout->outer, layout->channels, layout->inner);                  \
+        if (!make_tiles<G>(layout->outer, layout->channels, layout->inner, &tiles, mult))                       \
+            return VSIQ_ERR_INVALID_ARG;                                                                        \
+        uint32_t want = G == kThreads ? tiles.n_tiles : (tiles.n_tiles + kWarps - 1) / kWarps;                  \
+        int grid = launch_grid(want);                                                                           \
+        if (grid < 0) return -grid;                                                                             \
+        const int use_ticket = grid <= single_wave_ctas() ? 1 : 0;                                              \
+        observe_kernel<G, V><<<grid, kThreads, 0, st>>>(x, tiles, layout->outer, workspace, oo, use_ticket);    \
+        if (!use_ticket) {                                                                                      \
+            const int64_t items = layout->outer * (int64_t)tiles.chunks;                                        \
+            if (items >= 512) {                                                                                 \
+                int fgrid = (int)(layout->channels < 1024 ? layout->channels : 1024);                           \
+                observe_finalize_kernel<true><<<fgrid, kThreads, 0, st>>>(tiles, layout->outer, workspace, oo); \
+            } else {                                                                                            \
+                int64_t fg = (layout->channels + kWarps - 1) / kWarps;                                          \
+                observe_finalize_kernel<false><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(              \
+                    tiles, layout->outer, workspace, oo);                                                       \
+            }                                                                                                   \
+        }                                                                                                       \
     }
     if (warp_group) {
         if (vec8) CALL(32, 8) else CALL(32, 1)

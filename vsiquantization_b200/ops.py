@@ -140,7 +140,7 @@ def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_cod
     lay = Layout(outer, C, inner)
     keep: list = []
     with torch.cuda.device(x.device):
-        qp = _make_qparams(spec, scale, zero_point, C, x.device, keep)
+        qp = _make_qparams(spec, scale, zero_point, max(C, 1), x.device, keep)
         y = torch.empty_like(x)
         codes = None
         if want_codes:
@@ -351,12 +351,14 @@ def bn_reestimate_finish(mean_sum, var_sum, batch_count: int, running_mean, runn
         _count_launch()
 
 
-def selftest_division(scale: float, device=None) -> int:
-    """Mismatches between the kernels' reciprocal-based division and IEEE x/s over all 2^32 x (expect 0)."""
+def selftest_division(scale: float, mode: int = 0, device=None) -> int:
+    """Mismatches between the kernels' fast arithmetic and the IEEE sequences over all 2^32 inputs (expect 0).
+    mode 0: x / s;  mode 1: RN(RN(g*s) / s)."""
     dev = torch.device(device or "cuda")
     with torch.cuda.device(dev):
         out = torch.zeros(1, dtype=torch.int64, device=dev)
-        check(lib.vsiq_selftest_division(float(scale), out.data_ptr(), _stream_ptr()), "vsiq_selftest_division")
+        check(lib.vsiq_selftest_division(float(scale), int(mode), out.data_ptr(), _stream_ptr()),
+              "vsiq_selftest_division")
         _count_launch()
         return int(out.item())
 
