@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark of the fake-quantization hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--log2n L]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): one per-tensor W8 symmetric
+UniformQuantizer over a 2^28-element fp32 tensor; one step = the forward kernel + the STE backward kernel
+(20 algorithmic bytes per element: read x / write y, then read g, read x / write dx).  x is 1 GiB, larger than the
+126 MB L2, so nothing survives between launches.
+
+Prints ONE JSON line (rank 0).  `value` is whole-job GB/s with inputs resident in HBM; `e2e` is the same metric
+through the host-buffer entry of the C ABI (pinned host x, g -> y, dx; both PCIe directions inside the timed region);
+`roofline` is the dominant kernel (STE backward, 12 B/element) against the measured HBM copy bandwidth; `cpu_baseline`
+is the reference's op sequence (torch-eager port, oracle/torch_port.py) on the host cores over a bounded sample.
+
+`--impl reference`: the reference arm -- the same CPU port, all host threads, rank 0 only.
+Under torchrun (N > 1) every rank runs the same per-GPU workload (weak scaling, no data-path collective); the time is
+the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fake-quant fwd+bwd GB/s (20 algorithmic bytes/element)"
+QMIN, QMAX, SCALE, ZP = -128, 127, 3.0 / 127, 0  # W8 symmetric, ~0.3 % of randn clipped
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--log2n", type=int, default=28, help="log2 of the tensor size (elements) per GPU")
+    ap.add_argument("--cpu-log2n", type=int, default=25, help="log2 of the bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel: str, log2n: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if one matches."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(f"{kernel}@2^{log2n}")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(log2n: int, iters: int = 5, warm: int = 2):
+    """The reference's op sequence on the host cores (torch eager, all threads) over 2^log2n elements."""
+    import torch
+    from oracle import torch_port
+    n = 1 << log2n
+    torch.manual_seed(0)
+    x, g = torch.randn(n), torch.randn(n)
+    ts = []
+    for i in range(warm + iters):
+        t0 = time.perf_counter()
+        torch_port.fwd_bwd(x, g, SCALE, ZP, QMIN, QMAX)
+        if i >= warm:
+            ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    out = {"value": 20.0 * n / med / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+           "sample": f"2^{log2n} elements per iteration, median of {iters} after {warm} warm-ups; torch-eager port of "
+                     f"quantizers/uniform.py:54-55,95 + autograd (oracle/torch_port.py)",
+           "ms_per_step": med * 1e3, "host_cpus": os.cpu_count()}
+    # the single-sweep C port (OpenMP) as a second, stronger yardstick
+    try:
+        import numpy as np
+        import oracle
+        xn, gn = x.numpy(), g.numpy()
+        yo, dxo = np.empty_like(xn), np.empty_like(xn)
+        tc = []
+        for i in range(warm + iters):
+            t0 = time.perf_counter()
+            oracle.fake_quant_fwd_bwd(xn, gn, SCALE, ZP, QMIN, QMAX, yo, dxo)
+            if i >= warm:
+                tc.append(time.perf_counter() - t0)
+        tc.sort()
+        out["c_port_fused_gbs"] = 20.0 * n / tc[len(tc) // 2] / 1e9
+        out["c_port_threads"] = oracle.max_threads()
+    except Exception as e:  # the C port is optional
+        out["c_port_fused_gbs"] = None
+        out["c_port_note"] = str(e)[:80]
+    return out
+
+
+# ---------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0  # the reference arm runs on rank 0 alone
+    import torch
+    from oracle import torch_port
+    n = 1 << args.cpu_log2n
+    torch.manual_seed(0)
+    x, g = torch.randn(n), torch.randn(n)
+    for _ in range(args.warmup):
+        torch_port.fwd_bwd(x, g, SCALE, ZP, QMIN, QMAX)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        torch_port.fwd_bwd(x, g, SCALE, ZP, QMIN, QMAX)
+    dt = time.perf_counter() - t0
+    value = 20.0 * n * args.steps / dt / 1e9
+    sample = (f"each step = fwd+bwd over a bounded sample of 2^{args.cpu_log2n} elements of the 2^{args.log2n}-element "
+              f"workload; torch-eager port of the reference's op sequence (oracle/torch_port.py), all host threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"per-tensor W8 symmetric UniformQuantizer fwd+STE bwd, CPU sample 2^{args.cpu_log2n} fp32 "
+                                   f"elements per step (workload 2^{args.log2n})"},
+            "cpu_baseline": {"value": value, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample, "host_cpus": os.cpu_count()},
+            "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# -------------------------------------------------------------------------------------- native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- vsiquantization_b200 has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from vsiquantization_b200 import _lib, ops
+
+    n = 1 << args.log2n
+    torch.manual_seed(rank)
+    x = torch.randn(n, device=dev)
+    g = torch.randn(n, device=dev)
+    spec = ops.QSpec(QMIN, QMAX)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        y = ops.fake_quant_forward(x, SCALE, ZP, spec)
+        dx = ops.fake_quant_backward_ste(x, g, SCALE, ZP, spec)
+        return y, dx
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = _lib.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        y = ops.fake_quant_forward(x, SCALE, ZP, spec)
+        ev[3 * i + 1].record()
+        dx = ops.fake_quant_backward_ste(x, g, SCALE, ZP, spec)
+        ev[3 * i + 2].record()
+        ev[3 * i + 3].record()
+    barrier()
+    launches = _lib.launch_count - launches0
+    total_ms = ev[0].elapsed_time(ev[3 * args.steps])
+    fwd_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)) / args.steps
+    bwd_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = 20.0 * n * args.steps * world / (total_ms * 1e-3) / 1e9
+
+    # correctness spot check inside the bench (first 2^16 elements against the oracle), rank 0
+    check = None
+    if rank == 0:
+        try:
+            import oracle
+            k = 1 << 16
+            yo = oracle.fake_quant_fwd(x[:k].cpu().numpy(), SCALE, ZP, QMIN, QMAX)
+            dxo = oracle.fake_quant_bwd(x[:k].cpu().numpy(), g[:k].cpu().numpy(), SCALE, ZP, QMIN, QMAX, want_ds=False)[0]
+            check = bool((y[:k].cpu().numpy().view("uint32") == yo.view("uint32")).all() and
+                         (dx[:k].cpu().numpy().view("uint32") == dxo.view("uint32")).all())
+        except Exception as e:
+            check = f"oracle unavailable: {str(e)[:60]}"
+    del y, dx
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e2e_n = n
+        xh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
+        gh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
+        yh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
+        dh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
+        xh.copy_(x)
+        gh.copy_(g)
+        pipe = ops.HostPipeline(chunk_elems=1 << 22, n_slots=4, device=dev)
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            pipe.fwd_bwd(xh, gh, SCALE, ZP, QMIN, QMAX, yh, dh)
+        barrier()
+        l0 = _lib.launch_count
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pipe.fwd_bwd(xh, gh, SCALE, ZP, QMIN, QMAX, yh, dh)  # returns when y, dx have landed on the host
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e_launches = _lib.launch_count - l0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": 20.0 * e2e_n * e2e_steps * world / dt / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": 8 * e2e_n, "d2h_bytes_per_step": 8 * e2e_n, "steps": e2e_steps,
+               "ms_per_step": dt / e2e_steps * 1e3, "gpu_launches": e2e_launches,
+               "pcie_gbs_each_way": 8.0 * e2e_n * e2e_steps / dt / 1e9,
+               "api": "vsiq_host_pipeline_fwd_bwd (ops.HostPipeline): 4 Mi-element chunks on 4 streams, fused fwd+bwd kernel"}
+        pipe.close()
+        del xh, gh, yh, dh
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    achieved = 12.0 * n / (bwd_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"fake-quant microbench (BASELINE configs[1]): per-tensor W8 symmetric UniformQuantizer, "
+                               f"2^{args.log2n} fp32 elements per GPU, step = forward kernel + STE backward kernel",
+                   "elements_per_gpu": n, "qmin": QMIN, "qmax": QMAX, "scale": SCALE,
+                   "l2_policy": "inputs larger than L2 (x = %d MiB > 126 MB); no flush needed" % (4 * n >> 20),
+                   "parallelism": f"dp{world} (independent per-GPU tensors, no data-path collective)"},
+        "roofline": {"bound": "hbm", "kernel": "fq_bwd_ste_kernel<256,8> (read g, read x, write dx: 12 B/element)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": ncu_traffic("fq_bwd_ste_kernel", args.log2n),
+                     "algorithmic_bytes_per_launch": 12 * n, "avg_launch_ms": bwd_ms,
+                     "fwd_kernel": {"achieved": 8.0 * n / (fwd_ms * 1e-3) / 1e9, "avg_launch_ms": fwd_ms,
+                                    "frac": 8.0 * n / (fwd_ms * 1e-3) / 1e9 / peak}},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "oracle_spot_check_bit_exact": check,
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_log2n)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

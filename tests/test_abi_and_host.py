@@ -1,0 +1,143 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/vsiq.h declares (no compute calls without a
+GPU), the ctypes binding covers them, and the host-side logic (config manager, pattern matching, registry, layouts)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "vsiq.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vsiq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vsiquantization_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 20
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in include/vsiq.h but not exported by libvsiq.so"
+    assert sorted(_lib.EXPORTED) == syms, "ctypes binding and header disagree"
+    assert _lib.lib.vsiq_version() == 100
+    assert b"invalid" in _lib.lib.vsiq_error_string(-1)
+
+
+def test_no_cpu_fallback():
+    from vsiquantization_b200 import ops
+    from vsiquantization_b200.quantizers.uniform import UniformQuantizer
+    with pytest.raises(RuntimeError):
+        ops.fake_quant_forward(torch.zeros(8), 0.1, 0, ops.QSpec(-8, 7))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            UniformQuantizer(8, True).quantize(torch.zeros(8), 0.1, 0, False)
+        from vsiquantization_b200._lib import lib
+        assert lib.vsiq_device_info(None, None, None) == -4  # VSIQ_ERR_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "vsiquantization_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".sh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "vsiq_oracle" not in src, f
+
+
+def test_layout_of():
+    from vsiquantization_b200.ops import layout_of
+    assert layout_of((4, 3, 5, 5), None) == (1, 1, 300)
+    assert layout_of((16, 3, 3, 3), 0) == (1, 16, 27)
+    assert layout_of((2, 8, 20, 20), 1) == (2, 8, 400)
+    assert layout_of((7,), None) == (1, 1, 7) and layout_of((4, 6), -1) == (4, 6, 1)
+
+
+def test_registry_and_quantizer_ranges():
+    from vsiquantization_b200.utils.registry import CLASS_REGISTRY, register_class
+    import vsiquantization_b200.quantizers.quantization_manager  # noqa: F401
+    assert {"UniformQuantizer", "LSQQuantizer", "MinMaxObserver", "LSQObserver"} <= set(CLASS_REGISTRY)
+    for bits in range(2, 9):
+        q = CLASS_REGISTRY["UniformQuantizer"](bits, True)
+        assert (q.qmin, q.qmax) == (-(2 ** (bits - 1)), 2 ** (bits - 1) - 1)
+        q = CLASS_REGISTRY["UniformQuantizer"](bits, False)
+        assert (q.qmin, q.qmax) == (0, 2 ** bits - 1)
+
+    @register_class
+    class Probe:
+        pass
+    assert CLASS_REGISTRY["Probe"] is Probe
+    del CLASS_REGISTRY["Probe"]
+    with pytest.raises(KeyError):
+        CLASS_REGISTRY["LSQQuantiser"]
+
+
+def test_fuse_config_manager(tmp_path):
+    from vsiquantization_b200.modules.fuse_config import (FuseConfig, FuseConfigManager, create_fuse_config_manager,
+                                                            load_fuse_config_from_yaml)
+    d = FuseConfig()
+    assert (d.observer_w_name, d.quantizer_w_name, d.w_symmetric, d.a_symmetric, d.is_fuse_bn, d.bits_w, d.bits_a) == \
+        ("MinMaxObserver", "UniformQuantizer", True, True, True, 8, 8)
+    with pytest.raises(TypeError):
+        FuseConfig(no_such_field=1)
+    m = FuseConfigManager()
+    m.add_layer_config("backbone.*conv", FuseConfig(bits_w=4))
+    m.add_layer_config(".*conv.*", FuseConfig(bits_w=2))
+    m.add_layer_config("head[", FuseConfig(bits_w=6))  # invalid regex -> substring match
+    assert m.get_config_for_layer("backbone.3.conv").bits_w == 4      # first match wins, insertion order
+    assert m.get_config_for_layer("neck.conv1").bits_w == 2
+    assert m.get_config_for_layer("xhead[0").bits_w == 6
+    assert m.get_config_for_layer("fc").bits_w == 8
+    assert m.get_all_patterns() == ["backbone.*conv", ".*conv.*", "head["]
+    m.clear_layer_configs()
+    assert m.get_config_for_layer("backbone.3.conv").bits_w == 8
+    with pytest.raises(ValueError):
+        create_fuse_config_manager(layer_configs={"a": 3})
+    assert create_fuse_config_manager(layer_configs={"a": {"bits_a": 4}}).get_config_for_layer("a").bits_a == 4
+    with pytest.raises(FileNotFoundError):
+        load_fuse_config_from_yaml(str(tmp_path / "missing.yaml"))
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("default: [unclosed")
+    with pytest.raises(ValueError):
+        load_fuse_config_from_yaml(str(bad))
+    ok = tmp_path / "ok.yaml"
+    ok.write_text("default:\n  bits_w: 2\n  bits_a: 4\nlayers:\n  \"backbone.*conv\":\n    w_symmetric: false\n    bits_w: 4\n")
+    mgr = load_fuse_config_from_yaml(str(ok))
+    assert (mgr.default_config.bits_w, mgr.default_config.bits_a) == (2, 4)
+    assert mgr.get_config_for_layer("backbone.0.conv").w_symmetric is False
+
+
+def test_reference_sample_yaml_loads():
+    ref = "/root/reference/configs/fuse_config.yaml"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present")
+    from vsiquantization_b200.modules.fuse_config import load_fuse_config_from_yaml
+    mgr = load_fuse_config_from_yaml(ref)
+    assert (mgr.default_config.bits_w, mgr.default_config.bits_a) == (2, 4)  # configs/fuse_config.yaml:13-14
+    assert len(mgr.get_all_patterns()) == 5
+
+
+def test_pattern_matching_without_tensors():
+    from tiny_model import make_tiny
+    from vsiquantization_b200.modules.fuse import PATTERN_TO_FUSED, find_fusable_sequences, get_module_type_str
+    model = make_tiny(0)
+    hits = find_fusable_sequences(model, ["conv", "bn", "relu"])
+    assert [(p, n) for p, _, n in hits] == [("stem", ["conv", "norm", "relu"]), ("backbone.0", ["conv", "norm", "relu"]),
+                                            ("backbone.1", ["conv", "norm", "relu"])]  # SiLU counts as 'relu'
+    assert ("", ["head"]) in [(p, n) for p, _, n in find_fusable_sequences(model, ["conv"])]
+    assert find_fusable_sequences(model, ["linear", "bn"]) == []
+    assert len(PATTERN_TO_FUSED) == 8
+    assert get_module_type_str(torch.nn.SiLU()) is None and get_module_type_str(torch.nn.BatchNorm1d(3)) == "bn"
+
+
+def test_dropin_maps_reference_module_paths():
+    from vsiquantization_b200 import dropin
+    reg = dropin.install_plugins(registry={})
+    assert sorted(reg) == ["LSQObserver", "LSQQuantizer", "MinMaxObserver", "UniformQuantizer"]
+    assert set(dropin._TIER2) >= {"modules.fuse", "modules.fuse_config", "utils.quantize_manager", "utils.estimate_bn",
+                                  "quantizers.uniform", "observers.minmax"}

@@ -197,3 +197,21 @@ def test_tiny_e2e_qparams_from_golden_activations():
             s2, z2 = oracle.qparams(mn, mx, 8, True)
             assert (s2, z2) == (s, z)
             assert oracle.lsq_init_scale(G[f"calib_{n}_{kind}_mean_abs"], 8) == float(G[f"init_{n}_{kind}"])
+
+
+def test_torch_port_matches_golden():
+    """The torch-eager port timed as the CPU baseline reproduces the reference's outputs bit for bit."""
+    import torch
+    from oracle import torch_port
+    G = load_golden("uniform_fixed")
+    for tag in list(G["cases"])[:4]:
+        scale, zp, qmin, qmax, bits, sym = G[f"{tag}_qp"]
+        y, dx = torch_port.fwd_bwd(torch.as_tensor(G[f"{tag}_x"]), torch.as_tensor(G[f"{tag}_g"]), float(scale), int(zp),
+                                   int(qmin), int(qmax))
+        assert bits_equal(y.numpy(), G[f"{tag}_y"]) and bits_equal(dx.numpy(), G[f"{tag}_dx"])
+    G = load_golden("uniform_learned")
+    scale, zf, qmin, qmax, bits, sym, gs = G["b8_sym_0_qp"]
+    y, dx, ds = torch_port.fwd_bwd(torch.as_tensor(G["b8_sym_0_x"]), torch.as_tensor(G["b8_sym_0_g"]), scale, 0,
+                                   int(qmin), int(qmax), learn=True)
+    assert bits_equal(y.numpy(), G["b8_sym_0_y"]) and bits_equal(dx.numpy(), G["b8_sym_0_dx"])
+    assert ds.item() == G["b8_sym_0_ds"][0]

@@ -1,0 +1,212 @@
+"""Fused QAT layers: ConvBnReLU, ConvBn, ConvReLU, Conv, LinearBnReLU, LinearBn, LinearReLU, Linear.
+
+Reference: modules/fused.py:32-412.  Same positional constructor order
+``(layers..., observer_w, quantizer_w, observer_a, quantizer_a, w_symmetric, a_symmetric, [is_fuse_bn], bits_w, bits_a)``
+and attributes (conv_fuse / linear_fuse, is_fuse_bn, is_relu, bn, weight_quantizer, activation_quantizer, bits_w, bits_a,
+quantize_out, quantize_inp).  The construction-time BN fold (fused.py:98-108, :292-300) runs on the bn_fold CUDA kernel
+(bit-identical); conv / linear stay on cuDNN / cuBLAS.  The reference's Linear / LinearReLU / bias-less LinearBnReLU do
+not run (``bool(tensor)``, missing get_weight_bias -- SURVEY.md 0.9); they are fixed here."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..quantizers.fake_quantize import FakeQuantize
+
+
+def _activation(x, relu_flag: Optional[bool]):
+    if relu_flag is None:
+        return x
+    return F.relu(x) if relu_flag else F.silu(x)
+
+
+def _fold_bn_into(core: nn.Module, weight: torch.Tensor, bias: Optional[torch.Tensor], bn: nn.Module) -> None:
+    """W' = W*gamma/sqrt(var+eps), b' = beta + (b-mean)*gamma/sqrt(var+eps) written into ``core`` (kernel 5)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("vsiquantization_b200 needs a CUDA device to fold BatchNorm: there is no CPU fallback")
+    home = weight.device
+    dev = home if home.type == "cuda" else torch.device("cuda")
+    to = lambda t: None if t is None else t.detach().to(dev, torch.float32)  # noqa: E731
+    Wf, bf, _, _ = ops.bn_fold(to(weight), to(bias), to(bn.weight), to(bn.bias), to(bn.running_mean),
+                               to(bn.running_var), bn.eps)
+    with torch.no_grad():
+        core.weight.copy_(Wf.to(home))
+        if core.bias is not None:
+            core.bias.copy_(bf.to(home))
+
+
+class _ConvBase(FakeQuantize):
+    def _make_conv(self, cv: nn.Conv2d, bias: bool) -> None:
+        self.conv_fuse = nn.Conv2d(cv.in_channels, cv.out_channels, cv.kernel_size, cv.stride, cv.padding,
+                                   cv.dilation, cv.groups, bias=bias).to(cv.weight.device)
+        with torch.no_grad():
+            self.conv_fuse.weight.copy_(cv.weight)
+            if self.conv_fuse.bias is not None:
+                if cv.bias is not None:
+                    self.conv_fuse.bias.copy_(cv.bias)
+                else:
+                    self.conv_fuse.bias.zero_()
+
+    def _conv(self, x, weights, bias):
+        c = self.conv_fuse
+        return F.conv2d(x, weights, bias, stride=c.stride, padding=c.padding, dilation=c.dilation, groups=c.groups)
+
+
+class ConvBnReLU(_ConvBase):
+    """Conv2d + BatchNorm2d + ReLU/SiLU (fused.py:32-134).  ``relu`` may be nn.ReLU or nn.SiLU."""
+
+    def __init__(self, cv, bn, relu, observer_w_name: str, quantizer_w_name: str, observer_a_name: str,
+                 quantizer_a_name: str, w_symmetric: bool = True, a_symmetric: bool = True, is_fuse_bn=True,
+                 bits_w: int = 8, bits_a: int = 8, **ext):
+        super().__init__(observer_w_name, quantizer_w_name, observer_a_name, quantizer_a_name, w_symmetric, a_symmetric,
+                         bits_w, bits_a, **ext)
+        self._make_conv(cv, bias=bool(is_fuse_bn or cv.bias is not None))
+        self.is_fuse_bn = is_fuse_bn
+        self.is_relu = isinstance(relu, nn.ReLU)  # False means SiLU (fused.py:81)
+        self._has_act = relu is not None
+        if is_fuse_bn:
+            _fold_bn_into(self.conv_fuse, cv.weight, cv.bias, bn)
+        else:
+            self.bn = bn
+        self._bn_reestimate = None  # set by utils.estimate_bn while re-estimating
+
+    def _bn(self, x):
+        if self._bn_reestimate is not None:
+            return self._bn_reestimate(self, x)
+        return self.bn(x)
+
+    def run_forward_core(self, x, weights, bias):
+        x = self._conv(x, weights, bias)
+        if not self.is_fuse_bn:
+            x = self._bn(x)
+        # the reference applies SiLU when relu is not an nn.ReLU -- including relu=None (ConvBn overrides this)
+        return F.relu(x) if self.is_relu else F.silu(x)
+
+
+class ConvBn(ConvBnReLU):
+    """Conv2d + BatchNorm2d, no activation (fused.py:137-156)."""
+
+    def __init__(self, cv, bn, observer_w_name: str, quantizer_w_name: str, observer_a_name: str, quantizer_a_name: str,
+                 w_symmetric: bool = True, a_symmetric: bool = True, is_fuse_bn=True, bits_w: int = 8, bits_a: int = 8,
+                 **ext):
+        super().__init__(cv, bn, None, observer_w_name, quantizer_w_name, observer_a_name, quantizer_a_name, w_symmetric,
+                         a_symmetric, is_fuse_bn, bits_w, bits_a, **ext)
+
+    def run_forward_core(self, x, weights, bias):
+        x = self._conv(x, weights, bias)
+        if not self.is_fuse_bn:
+            x = self._bn(x)
+        return x
+
+
+class ConvReLU(_ConvBase):
+    """Conv2d + ReLU/SiLU (fused.py:159-203)."""
+
+    def __init__(self, cv, relu, observer_w_name: str, quantizer_w_name: str, observer_a_name: str, quantizer_a_name: str,
+                 w_symmetric: bool = True, a_symmetric: bool = True, bits_w: int = 8, bits_a: int = 8, **ext):
+        super().__init__(observer_w_name, quantizer_w_name, observer_a_name, quantizer_a_name, w_symmetric, a_symmetric,
+                         bits_w, bits_a, **ext)
+        self._make_conv(cv, bias=cv.bias is not None)
+        self.is_relu = isinstance(relu, nn.ReLU)
+
+    def run_forward_core(self, x, weights, bias):
+        return _activation(self._conv(x, weights, bias), self.is_relu)
+
+
+class Conv(_ConvBase):
+    """Quantisation-aware Conv2d (fused.py:206-248)."""
+
+    def __init__(self, cv, observer_w_name: str, quantizer_w_name: str, observer_a_name: str, quantizer_a_name: str,
+                 w_symmetric: bool = True, a_symmetric: bool = True, bits_w: int = 8, bits_a: int = 8, **ext):
+        super().__init__(observer_w_name, quantizer_w_name, observer_a_name, quantizer_a_name, w_symmetric, a_symmetric,
+                         bits_w, bits_a, **ext)
+        self._make_conv(cv, bias=cv.bias is not None)
+
+    def run_forward_core(self, x, weights, bias):
+        return self._conv(x, weights, bias)
+
+
+class _LinearBase(FakeQuantize):
+    def _make_linear(self, linear: nn.Linear, bias: bool) -> None:
+        self.linear_fuse = nn.Linear(linear.in_features, linear.out_features, bias=bias).to(linear.weight.device)
+        with torch.no_grad():
+            self.linear_fuse.weight.copy_(linear.weight)
+            if self.linear_fuse.bias is not None:
+                if linear.bias is not None:
+                    self.linear_fuse.bias.copy_(linear.bias)
+                else:
+                    self.linear_fuse.bias.zero_()
+
+
+class LinearBnReLU(_LinearBase):
+    """Linear + BatchNorm1d + ReLU/SiLU (fused.py:251-317); also accepts a bias-less Linear (the reference crashes)."""
+
+    def __init__(self, linear, bn, relu, observer_w_name: str, quantizer_w_name: str, observer_a_name: str,
+                 quantizer_a_name: str, w_symmetric: bool = True, a_symmetric: bool = True, is_fuse_bn: bool = True,
+                 bits_w: int = 8, bits_a: int = 8, **ext):
+        super().__init__(observer_w_name, quantizer_w_name, observer_a_name, quantizer_a_name, w_symmetric, a_symmetric,
+                         bits_w, bits_a, **ext)
+        self._make_linear(linear, bias=bool(is_fuse_bn or linear.bias is not None))
+        self.is_fuse_bn = is_fuse_bn
+        self.is_relu = isinstance(relu, nn.ReLU)
+        if is_fuse_bn:
+            _fold_bn_into(self.linear_fuse, linear.weight, linear.bias, bn)
+        else:
+            self.bn = bn
+
+    def run_forward_core(self, x, weights, bias):
+        x = F.linear(x, weights, bias)
+        if not self.is_fuse_bn:
+            x = self.bn(x)
+        return F.relu(x) if self.is_relu else F.silu(x)
+
+
+class LinearBn(LinearBnReLU):
+    """Linear + BatchNorm1d (fused.py:320-344)."""
+
+    def __init__(self, linear, bn, observer_w_name: str, quantizer_w_name: str, observer_a_name: str,
+                 quantizer_a_name: str, w_symmetric: bool = True, a_symmetric: bool = True, is_fuse_bn: bool = True,
+                 bits_w: int = 8, bits_a: int = 8, **ext):
+        super().__init__(linear, bn, None, observer_w_name, quantizer_w_name, observer_a_name, quantizer_a_name,
+                         w_symmetric, a_symmetric, is_fuse_bn, bits_w, bits_a, **ext)
+
+    def run_forward_core(self, x, weights, bias):
+        x = F.linear(x, weights, bias)
+        if not self.is_fuse_bn:
+            x = self.bn(x)
+        return x
+
+
+class LinearReLU(_LinearBase):
+    """Linear + ReLU/SiLU (fused.py:347-379)."""
+
+    def __init__(self, linear, relu, observer_w_name: str, quantizer_w_name: str, observer_a_name: str,
+                 quantizer_a_name: str, w_symmetric: bool = True, a_symmetric: bool = True, bits_w: int = 8,
+                 bits_a: int = 8, **ext):
+        super().__init__(observer_w_name, quantizer_w_name, observer_a_name, quantizer_a_name, w_symmetric, a_symmetric,
+                         bits_w, bits_a, **ext)
+        self._make_linear(linear, bias=linear.bias is not None)
+        self.is_relu = isinstance(relu, nn.ReLU)
+
+    def run_forward_core(self, x, weights, bias):
+        return _activation(F.linear(x, weights, bias), self.is_relu)
+
+
+class Linear(_LinearBase):
+    """Quantisation-aware Linear (fused.py:382-412)."""
+
+    def __init__(self, linear, observer_w_name: str, quantizer_w_name: str, observer_a_name: str, quantizer_a_name: str,
+                 w_symmetric: bool = True, a_symmetric: bool = True, bits_w: int = 8, bits_a: int = 8, **ext):
+        super().__init__(observer_w_name, quantizer_w_name, observer_a_name, quantizer_a_name, w_symmetric, a_symmetric,
+                         bits_w, bits_a, **ext)
+        self._make_linear(linear, bias=linear.bias is not None)
+
+    def run_forward_core(self, x, weights, bias):
+        return F.linear(x, weights, bias)
+
+
+FUSED_CLASSES = (ConvBnReLU, ConvBn, ConvReLU, Conv, LinearBnReLU, LinearBn, LinearReLU, Linear)

@@ -1,0 +1,167 @@
+"""QuantizationManager: per-tensor state machine between a fused layer and its observer / quantizer plugins.
+
+Reference: quantizers/quantization_manager.py:10-114.  Same constructor, attributes (quantizer, observer, bits_width,
+scale, zero_point, is_observer_qparam, is_learning_scale, is_quantize, is_symmetric, mean_abs_x, mean_x, std) and
+methods (collect_qparameter, quantize, make_learn_qparameter, init_scaling_factor_for_learning); plugins are built
+from the registry by name exactly like :41-42 (so the observer is always 8-bit unless ``observer_bits`` is given --
+SURVEY.md 0.4).  What differs is WHERE the numbers live:
+
+  * calibration (collect_qparameter) is one kernel launch and NO host synchronisation per call: min/max, the three
+    statistics, the running state, scale and zero-point all stay on the device (the reference does 5 reductions and
+    5 ``.item()`` syncs, :66-69).  ``scale`` / ``zero_point`` / ``mean_abs_x`` / ``mean_x`` / ``std`` are read back
+    lazily, only when host code asks for them;
+  * with fixed qparams the kernels read scale / zero-point straight from the observer state on the device;
+  * init_scaling_factor_for_learning + make_learn_qparameter build the learnable Parameter on the device.
+
+Deliberate fixes where the reference cannot run: the constructor's ``is_symmetric`` is stored
+(the reference hard-codes True, :50, so an asymmetric learnable zero-point is unreachable and crashes, uniform.py:50-52);
+asymmetric managers therefore get the learnable zero-point the code at :100-101 intends.  Symmetric flows -- every
+flow the reference can execute -- are unchanged.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from ..observers.minmax import MinMaxObserver  # noqa: F401  (registers the plugin classes)
+from ..quantizers.uniform import UniformQuantizer  # noqa: F401
+from ..utils.registry import CLASS_REGISTRY
+
+_LAZY = ("scale", "zero_point")
+
+
+class QuantizationManager(nn.Module):
+    def __init__(self, quantizer_name: str, observer_name: str, bits_width: int, is_symmetric: bool,
+                 is_learning_scale: bool = True, observer_bits: Optional[int] = None, ch_axis: Optional[int] = None,
+                 param_dtype: torch.dtype = torch.float64) -> None:
+        super().__init__()
+        self.quantizer = CLASS_REGISTRY[quantizer_name](bits_width, is_symmetric)
+        if observer_bits is None:
+            self.observer = CLASS_REGISTRY[observer_name](is_symmetric)  # num_bits stays 8, like the reference
+        else:
+            self.observer = CLASS_REGISTRY[observer_name](is_symmetric, observer_bits)
+        if ch_axis is not None:
+            self.quantizer.ch_axis = ch_axis
+            self.observer.ch_axis = ch_axis
+        self.ch_axis = ch_axis
+        self.bits_width = bits_width
+        self.param_dtype = param_dtype  # the reference's learned scale is a 0-dim float64 Parameter
+        self.scale = 1
+        self.zero_point = 0
+        self.is_observer_qparam = True
+        self.is_learning_scale = is_learning_scale
+        self.is_quantize = True
+        self.is_symmetric = is_symmetric
+        self._call_stats: List = []   # (device stats [C,5], elements per channel) per calibration call
+        self._calibrated = False      # the observer state on the device is the source of scale / zero_point
+
+    # ---- lazily materialised host views ---------------------------------------------------------------
+    def __getattr__(self, name):
+        # reached only when normal lookup fails: scale / zero_point were invalidated by a calibration call
+        if name in _LAZY and "_calibrated" in self.__dict__ and self.__dict__["_calibrated"]:
+            s, z = self.observer.get_scale_zero_point()  # one D2H copy
+            self.__dict__["scale"], self.__dict__["zero_point"] = s, z
+            return self.__dict__[name]
+        return super().__getattr__(name)
+
+    def _invalidate(self) -> None:
+        self.__dict__.pop("scale", None)
+        self.__dict__.pop("zero_point", None)
+
+    def _stats_host(self):
+        if not self._call_stats:
+            return []
+        st = torch.stack([s[0] for s, _ in self._call_stats]).cpu()  # per-tensor view: channel 0
+        return [(st[i], n) for i, (_, n) in enumerate(self._call_stats)]
+
+    @property
+    def mean_abs_x(self):
+        """Per-call mean|x| (reference: a list of floats, :66)."""
+        return [float(s[2]) / n for s, n in self._stats_host()]
+
+    @property
+    def mean_x(self):
+        return [float(s[3]) / n for s, n in self._stats_host()]
+
+    @property
+    def std(self):
+        out = []
+        for s, n in self._stats_host():
+            mean = float(s[3]) / n
+            var = (float(s[4]) - n * mean * mean) / (n - 1) if n > 1 else float("nan")
+            out.append(max(var, 0.0) ** 0.5)
+        return out
+
+    # ---- reference interface -----------------------------------------------------------------------------
+    def collect_qparameter(self, x):
+        """Observe x while calibrating (:55-71): one launch, no synchronisation."""
+        if not self.is_learning_scale and self.is_observer_qparam:
+            self.observer.observe(x)
+            self._call_stats.append((self.observer.last_stats, self.observer.last_count))
+            self._calibrated = True
+            self._invalidate()
+
+    def quantize(self, x):
+        """collect (if calibrating) then fake-quantise (if enabled) -- :73-90."""
+        self.collect_qparameter(x)
+        if not self.is_quantize:
+            return x
+        if "scale" in self._parameters or "zero_point" in self._parameters or not self._calibrated \
+                or "scale" in self.__dict__:
+            # learned Parameters, never-calibrated defaults, or values host code has set / read back
+            return self.quantizer.quantize(x, self.scale, self.zero_point, self.is_learning_scale)
+        # calibrated, fixed qparams: feed the kernels from the observer state on the device (no sync)
+        s, z = self.observer.device_qparams()
+        return self.quantizer.quantize(x, s, z, self.is_learning_scale)
+
+    def init_scaling_factor_for_learning(self):
+        """scale = 2*mean(mean|x|)/sqrt(2^(b-1)-1) (:105-114), computed on the device; becomes a 0-dim (per tensor)
+        or [C] tensor of ``param_dtype``.  Without calibration data the current scale is kept."""
+        st = self.observer.state
+        if st is None or not self._call_stats:
+            return
+        out = torch.empty(st.shape[0], dtype=self.param_dtype, device=st.device)
+        self.observer.lsq_init_scale(self.bits_width, out)
+        self._calibrated = False
+        self.__dict__.pop("zero_point", None)
+        self.__dict__["scale"] = out.reshape(()) if out.numel() == 1 else out
+        self.__dict__["zero_point"] = self._current_zero_point()
+
+    def _current_zero_point(self):
+        st = self.observer.state
+        if st is None:
+            return 0
+        z = st[:, 3]
+        return z.reshape(()) if z.numel() == 1 else z.clone()
+
+    def make_learn_qparameter(self):
+        """scale -> nn.Parameter; asymmetric: zero_point -> float nn.Parameter initialised at zp + 1e-9 (:92-103);
+        symmetric: zero_point = 0."""
+        scale = self.scale
+        if isinstance(scale, nn.Parameter):
+            pass
+        elif isinstance(scale, torch.Tensor):
+            self.__dict__.pop("scale", None)
+            self.scale = nn.Parameter(scale.detach().clone().to(self.param_dtype), requires_grad=True)
+        else:
+            dev = self.observer.state.device if self.observer.state is not None else None
+            self.__dict__.pop("scale", None)
+            # torch.tensor(python float) is float32, torch.tensor(np.float64) is float64 -- the reference gets fp64
+            # after init_scaling_factor_for_learning and fp32 otherwise (:99); param_dtype decides here.
+            self.scale = nn.Parameter(torch.tensor(float(scale), dtype=self.param_dtype, device=dev), requires_grad=True)
+        if not self.is_symmetric:
+            zp = self.zero_point
+            if not isinstance(zp, nn.Parameter):
+                self.__dict__.pop("zero_point", None)
+                if isinstance(zp, torch.Tensor):
+                    z0 = zp.detach().to(torch.float32) + 1e-9
+                else:
+                    z0 = torch.tensor(float(zp) + 1e-9, dtype=torch.float32, device=self.scale.device)
+                self.zero_point = nn.Parameter(z0.to(self.scale.device).reshape(self.scale.shape), requires_grad=True)
+        else:
+            self.__dict__.pop("zero_point", None)
+            if "zero_point" not in self._parameters:
+                self.zero_point = 0
+        self._calibrated = False

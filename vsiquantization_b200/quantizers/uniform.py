@@ -1,0 +1,122 @@
+"""UniformQuantizer / LSQQuantizer: the reference's fake-quant plugins on the CUDA kernels.
+
+Reference: quantizers/uniform.py:8-102 (UniformQuantizer), :242-271 (ScaleGradient, RoundStraightThrough),
+:105-151 (FunLSQ, dead code -> ``mask_mode='funlsq'``), quantizers/lsq_module.py:147-173,254-274,317-358
+(per-channel learnable scale / zero-point -> ``ch_axis``).  Same constructor ``(num_bits, symmetric)``, attributes
+``num_bits, symmetric, qmin, qmax, calib_grad_scale`` and ``quantize(x, scale, zero_point, is_learning_scale)``.
+
+The six eager forward kernels and ~14 backward kernels of the reference become ONE forward kernel and ONE backward
+kernel (dx + per-channel dscale/dzero_point in the same pass); outputs are bit-identical to the reference on CPU.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .. import _lib, ops
+from ..utils.registry import register_class
+from .base import BaseQuantizer
+
+
+def _as_cuda(x: torch.Tensor) -> torch.Tensor:
+    if x.is_cuda:
+        return x
+    if not torch.cuda.is_available():
+        raise RuntimeError("vsiquantization_b200 needs a CUDA device: there is no CPU fallback")
+    return x.cuda()  # differentiable: gradients flow back to the host tensor
+
+
+@register_class
+class UniformQuantizer(BaseQuantizer):
+    """Uniform affine fake-quantiser with straight-through / LSQ gradients.
+
+    Extension attributes (defaults reproduce the reference): ``ch_axis`` (None = per tensor; inferred from the
+    shape of a multi-element scale), ``mask_mode`` ('rounded' = the reference's autograd semantics, 'funlsq' =
+    quantizers/uniform.py:144-150), ``grad_boost`` (the x5000 activation hack of lsq_module.py:151-152; 1.0)."""
+
+    def __init__(self, num_bits=8, symmetric=True, ch_axis: Optional[int] = None, mask_mode: str = "rounded",
+                 grad_boost: float = 1.0):
+        self.num_bits = num_bits
+        self.symmetric = symmetric
+        self.qmin = 0
+        self.qmax = 2 ** self.num_bits - 1
+        if self.symmetric:
+            self.qmin = -(2 ** (self.num_bits - 1))
+            self.qmax = 2 ** (self.num_bits - 1) - 1
+        self.calib_grad_scale = 1
+        self.ch_axis = ch_axis
+        self.mask_mode = mask_mode
+        self.grad_boost = grad_boost
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def calculate_grad_scale(self, quant_tensor, channels: int = 1):
+        """1/sqrt(Qp * numel) (uniform.py:58-71); per channel 1/sqrt(Qp * numel / C) (lsq_module.py:327-340)."""
+        return ops.lsq_grad_scale(self.qmax, quant_tensor.numel(), channels)
+
+    def _resolve_axis(self, x: torch.Tensor, scale) -> Optional[int]:
+        if not isinstance(scale, torch.Tensor) or scale.numel() == 1:
+            return None
+        if self.ch_axis is not None:
+            return self.ch_axis
+        if scale.dim() == x.dim():  # broadcast shape such as [1, C, 1, 1]
+            axes = [i for i, d in enumerate(scale.shape) if d != 1]
+            if len(axes) == 1:
+                return axes[0]
+        raise ValueError("per-channel scale: set quantizer.ch_axis or pass a broadcast-shaped scale")
+
+    def _spec(self, ch_axis, zp_learned=False) -> ops.QSpec:
+        mode = _lib.MASK_FUNLSQ if self.mask_mode == "funlsq" else _lib.MASK_ROUNDED
+        return ops.QSpec(self.qmin, self.qmax, ch_axis=ch_axis, zp_learned=zp_learned, mask_mode=mode)
+
+    # -- the plugin entry point ------------------------------------------------------------------------
+    def quantize(self, x, scale, zero_point, is_learning_scale=False):
+        """Fake-quantise x (uniform.py:34-56).
+
+        scale: Python int/float, np.float64, or a tensor / nn.Parameter with 1 or C entries (fp32 or the reference's
+        0-dim fp64, on any device).  zero_point: Python int, or a float tensor / nn.Parameter (learnable: the forward
+        uses clamp(round(z)), uniform.py:98-102).  The result is autograd-connected to x and to every qparam that
+        requires grad."""
+        if not x.is_cuda:
+            y = self.quantize(_as_cuda(x), scale, zero_point, is_learning_scale)
+            return y.to(x.device)
+        ch_axis = self._resolve_axis(x, scale)
+        scale_learn = isinstance(scale, torch.Tensor) and scale.requires_grad and torch.is_grad_enabled()
+        zp_tensor = isinstance(zero_point, torch.Tensor)
+        # the reference rounds / clamps a tensor zero-point only on the asymmetric learning path (uniform.py:50-52)
+        zp_round = zp_tensor and is_learning_scale and not self.symmetric and zero_point.is_floating_point()
+        zp_learn = zp_round and zero_point.requires_grad and torch.is_grad_enabled()
+        if not (scale_learn or zp_learn):
+            s = scale.detach() if isinstance(scale, torch.Tensor) else scale
+            z = zero_point.detach() if zp_tensor else zero_point
+            return ops.FakeQuantFixed.apply(x, s, z, self._spec(ch_axis, zp_learned=zp_round))
+        if not isinstance(scale, torch.Tensor):
+            raise TypeError("a learnable zero_point needs a tensor scale")
+        C = scale.numel()
+        gs_host, gs_dev = 1.0, None
+        if is_learning_scale:  # ScaleGradient (uniform.py:48-49); otherwise plain autograd, factor 1
+            gs_host = self.calculate_grad_scale(x, C) * float(self.grad_boost)
+            cgs = self.calib_grad_scale
+            if isinstance(cgs, torch.Tensor):
+                # a [C] calib_grad_scale (utils/estimate_bn.py:136) is sum-reduced onto the scale by autograd
+                gs_dev = cgs.detach().to(device=x.device, dtype=torch.float32).sum().reshape(1)
+            else:
+                gs_host *= float(cgs)
+        zp_arg = zero_point if zp_learn else (zero_point.detach() if zp_tensor else zero_point)
+        return ops.FakeQuantLearned.apply(x, scale, zp_arg, self._spec(ch_axis, zp_learned=zp_round), gs_host, gs_dev)
+
+    def quantize_codes(self, x, scale, zero_point):
+        """(fake-quantised tensor, integer codes as int8/uint8) -- the reference keeps codes as floats (uniform.py:54)."""
+        x = _as_cuda(x)
+        ch_axis = self._resolve_axis(x, scale)
+        zp_round = isinstance(zero_point, torch.Tensor) and not self.symmetric and zero_point.is_floating_point() \
+            and zero_point.requires_grad
+        return ops.fake_quant_forward(x.detach(), scale, zero_point, self._spec(ch_axis, zp_round), want_codes=True)
+
+
+@register_class
+class LSQQuantizer(UniformQuantizer):
+    """Learned-step-size quantiser.  Named by the reference (README.md:70-71, modules/fuse_config.py:183) but never
+    defined there: ``CLASS_REGISTRY['LSQQuantizer']`` is a KeyError in the reference.  Here it is the learnable path
+    of UniformQuantizer (uniform.py:47-52) -- which is what actually runs in the reference -- with the per-channel
+    form of quantizers/lsq_module.py available through ``ch_axis``; identical arithmetic, same kernels."""

@@ -1,0 +1,110 @@
+"""BN statistics re-estimation and gradient-scale calibration (reference: utils/estimate_bn.py:8-161).
+
+reestimate_BN_stats: for every ConvBnReLU that kept its BatchNorm (is_fuse_bn=False) the running mean / variance are
+replaced by the average over ``num_batches`` batches of the per-batch mean and UNBIASED variance of the conv output
+(the reference gets these by running the BN layer in training mode with momentum 1, :60-65, :82-87, :96-97).  Here the
+per-batch moments come from ONE pass of the observer kernel over the conv output (min/max ride along for free), the
+sums are accumulated and finalised by small kernels, and the layer's output during re-estimation is normalised with
+the batch statistics exactly as training-mode BN would.  With torch.distributed initialised (``sync=True``) the
+per-channel sums are all-reduced first (SyncBN-style), so the result equals single-process re-estimation over the
+global batch."""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from ..modules.fused import ConvBnReLU
+from ..quantizers.fake_quantize import FakeQuantize
+
+
+class ReestimateBNStats:
+    """Callable wrapper for training engines (estimate_bn.py:8-35)."""
+
+    def __init__(self, model, data_loader, num_batches=50):
+        self.model = model
+        self.data_loader = data_loader
+        self.num_batches = num_batches
+
+    def __call__(self, engine):
+        print("-- Reestimate current BN statistics --")
+        reestimate_BN_stats(self.model, self.data_loader, self.num_batches)
+
+
+def _make_hook(sync: bool):
+    def hook(module: ConvBnReLU, x: torch.Tensor) -> torch.Tensor:
+        bn = module.bn
+        stats = ops.observe(x, ch_axis=1)                      # [C,5]: .., sum x, sum x^2  -- one read of x
+        count = float(x.numel() // x.shape[1])
+        if sync and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(stats[:, 2:], op=torch.distributed.ReduceOp.SUM)
+            count *= torch.distributed.get_world_size()
+        mean, var_b, _ = ops.bn_moments_finalize(stats, count, module.running_mean_sum, module.running_var_sum)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        # training-mode BN normalises with the batch mean and the BIASED batch variance
+        return F.batch_norm(x, mean, var_b, bn.weight, bn.bias, False, 0.0, bn.eps)
+    return hook
+
+
+def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=False, sync=True):
+    """Same signature as estimate_bn.py:38 (+ ``sync``).  Requires layers built with is_fuse_bn=False (the reference
+    needs ``module.bn`` too, :60)."""
+    model.eval()
+    layers = [(n, m) for n, m in model.named_modules() if isinstance(m, ConvBnReLU) and hasattr(m, "bn")]
+    hook = _make_hook(sync)
+    for _, m in layers:
+        m.running_mean_sum = torch.zeros_like(m.bn.running_mean)
+        m.running_var_sum = torch.zeros_like(m.bn.running_var)
+        if store_ema_stats:
+            if not hasattr(m, "running_mean_ema"):
+                m.register_buffer("running_mean_ema", copy.deepcopy(m.bn.running_mean))
+                m.register_buffer("running_var_ema", copy.deepcopy(m.bn.running_var))
+            else:
+                m.running_mean_ema = copy.deepcopy(m.bn.running_mean)
+                m.running_var_ema = copy.deepcopy(m.bn.running_var)
+        m._bn_reestimate = hook
+    device = next(model.parameters()).device
+    batch_count = 0
+    try:
+        with torch.no_grad():
+            for imgs, _targets in data_loader:
+                imgs = imgs.to(device, non_blocking=True).float() / 255.0
+                model(imgs)
+                batch_count += 1
+                if batch_count == num_batches:
+                    break
+    finally:
+        for _, m in layers:
+            m._bn_reestimate = None
+    if batch_count:
+        for _, m in layers:
+            ops.bn_reestimate_finish(m.running_mean_sum, m.running_var_sum, batch_count, m.bn.running_mean,
+                                     m.bn.running_var)
+    model.eval()
+
+
+def pdf_cdf(x, mu, sigma):
+    """Normal pdf / cdf (estimate_bn.py:145-162)."""
+    dist = torch.distributions.Normal(loc=mu, scale=sigma)
+    return torch.exp(dist.log_prob(x)), dist.cdf(x)
+
+
+def compute_scale(model, data_loader=None, num_batches=50, store_ema_stats=False):
+    """Per-channel calib_grad_scale of the activation quantiser from the BN affine parameters and the weight moments
+    (estimate_bn.py:104-139).  [C]-sized host-of-the-hot-path math: plain torch ops on tiny vectors."""
+    model.eval()
+    for _, m in model.named_modules():
+        if isinstance(m, ConvBnReLU) and hasattr(m, "bn"):
+            w = m.conv_fuse.weight.data.detach()
+            mu_w, sigma_w = w.mean(), w.std()
+            mu_a, sigma_a = m.bn.bias.data.clone(), m.bn.weight.data.clone()
+            pdf, cdf = pdf_cdf(mu_a / sigma_a, 0, 1)
+            m.activation_quantizer.quantizer.calib_grad_scale = 1 / (
+                (mu_w ** 2 + sigma_w ** 2) / ((mu_a ** 2 + sigma_a ** 2) * cdf + mu_a * sigma_a * pdf))
+    model.eval()
+
+
+__all__ = ["ReestimateBNStats", "reestimate_BN_stats", "compute_scale", "pdf_cdf", "FakeQuantize"]
