@@ -37,13 +37,14 @@ QMIN, QMAX, SCALE, ZP = -128, 127, 3.0 / 127, 0  # W8 symmetric, ~0.3 % of randn
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--log2n", type=int, default=28, help="log2 of the tensor size (elements) per GPU")
     ap.add_argument("--cpu-log2n", type=int, default=25, help="log2 of the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     return ap.parse_args()
 
 
@@ -216,26 +217,30 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        y = ops.fake_quant_forward(x, SCALE, ZP, spec)
-        dx = ops.fake_quant_backward_ste(x, g, SCALE, ZP, spec)
-        return y, dx
+    # outputs are allocated once: a QAT step reuses its activation / gradient buffers through the caching allocator
+    y = torch.empty_like(x)
+    dx = torch.empty_like(x)
 
+    def step():
+        ops.fake_quant_forward(x, SCALE, ZP, spec, out=y)
+        ops.fake_quant_backward_ste(x, g, SCALE, ZP, spec, out=dx)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not args.no_clocks:
+        sampler.start()  # started before the warm-up so nvidia-smi's own start-up is outside the timed region
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
+    if rank == 0 and not args.no_clocks:
+        time.sleep(0.3)
     launches0 = _lib.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     barrier()
     ev[0].record()
     for i in range(args.steps):
-        y = ops.fake_quant_forward(x, SCALE, ZP, spec)
+        ops.fake_quant_forward(x, SCALE, ZP, spec, out=y)
         ev[3 * i + 1].record()
-        dx = ops.fake_quant_backward_ste(x, g, SCALE, ZP, spec)
+        ops.fake_quant_backward_ste(x, g, SCALE, ZP, spec, out=dx)
         ev[3 * i + 2].record()
         ev[3 * i + 3].record()
     barrier()
@@ -243,7 +248,8 @@ def run_native(args):
     total_ms = ev[0].elapsed_time(ev[3 * args.steps])
     fwd_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)) / args.steps
     bwd_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    step_ms = sorted(ev[3 * i].elapsed_time(ev[3 * i + 3]) for i in range(args.steps))
+    clocks = sampler.stop() if (rank == 0 and not args.no_clocks) else None
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -309,6 +315,7 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
+        "step_ms": {"median": step_ms[len(step_ms) // 2], "min": step_ms[0], "max": step_ms[-1]},
         "config": {"workload": f"fake-quant microbench (BASELINE configs[1]): per-tensor W8 symmetric UniformQuantizer, "
                                f"2^{args.log2n} fp32 elements per GPU, step = forward kernel + STE backward kernel",
                    "elements_per_gpu": n, "qmin": QMIN, "qmax": QMAX, "scale": SCALE,

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads)
             }
         }
     }
-    if (!last_cta_ticket((unsigned int*)ws)) return;
+    if (!last_cta_ticket((unsigned int*)ws, GROUP == 32 ? lane == 0 : threadIdx.x == 0)) return;
     if (warp == 0) {
         const uint32_t n_slots = group_count<GROUP>();
         float mn = INFINITY, mx = -INFINITY;

@@ -256,9 +256,15 @@ __host__ __device__ inline bool make_tiles(int64_t outer, int64_t channels, int6
     t->rows = outer * channels;
     t->channels = channels;
     t->inner = inner;
-    const int64_t tile = (int64_t)TileGeom<GROUP>::kTile * tile_mult;
+    const int64_t max_tile = (int64_t)TileGeom<GROUP>::kTile * tile_mult;
+    int64_t chunks = (inner + max_tile - 1) / max_tile;
+    if (chunks <= 0) return false;
+    // even out the chunks of a row: the smallest multiple of one batch that still covers the row in `chunks` tiles
+    const int64_t batch = TileGeom<GROUP>::kBatch;
+    int64_t tile = ((inner + chunks - 1) / chunks + batch - 1) / batch * batch;
+    if (tile > max_tile) tile = max_tile;
+    chunks = (inner + tile - 1) / tile;
     t->tile = (int)tile;
-    int64_t chunks = (inner + tile - 1) / tile;
     int64_t n = t->rows * chunks;
     if (chunks <= 0 || n <= 0 || n >= (int64_t(1) << 31)) return false;
     t->chunks = (uint32_t)chunks;
@@ -432,11 +438,12 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// "last CTA finishes" ticket: returns true in every thread of the CTA that arrives last.  All global
-// writes issued by this CTA before the call are visible to the last CTA after it.
-__device__ __forceinline__ bool last_cta_ticket(unsigned int* counter) {
+// "last CTA finishes" ticket: returns true in every thread of the CTA that arrives last.  The partial
+// records written by this CTA before the call are visible to the last CTA after it: only the threads that
+// wrote a record fence (a fence in every thread would make each CTA wait for all of its streaming stores).
+__device__ __forceinline__ bool last_cta_ticket(unsigned int* counter, bool wrote_record) {
     __shared__ int s_last;
-    __threadfence();
+    if (wrote_record) __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int t = atomicAdd(counter, 1u);
@@ -452,6 +459,16 @@ __device__ __forceinline__ bool last_cta_ticket(unsigned int* counter) {
 // Workspace layout shared by the reducing kernels: a 256-byte header (ticket) then fp64 partials.
 constexpr size_t kWsHeader = 256;
 __device__ __forceinline__ double* ws_partials(void* ws) { return (double*)((char*)ws + kWsHeader); }
+
+// Record index of (channel c, item i) where a channel owns outer * chunks records: tile index is
+// (o * C + c) * chunks + k.  32-bit math (n_tiles < 2^31); outer == 1 needs no division.
+__device__ __forceinline__ uint32_t record_slot(const Tiles& t, uint32_t outer, uint32_t c, uint32_t i) {
+    if (outer == 1) return c * t.chunks + i;
+    const uint32_t o = i / t.chunks, k = i - o * t.chunks;
+    return (o * (uint32_t)t.channels + c) * t.chunks + k;
+}
+constexpr uint32_t kTicketMaxRecords = 8192;     // above this the combine step gets its own multi-CTA launch
+constexpr uint32_t kThreadCombineMaxItems = 32;  // <= this many records per channel: one thread per channel
 
 // ---------------------------------------------------------------------------------------------
 // Host-side helpers (abi)

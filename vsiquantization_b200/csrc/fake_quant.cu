@@ -188,15 +188,27 @@ __device__ __forceinline__ void lsq_store_channel(const LsqOut& o, const QPDev& 
     }
 }
 
+// one THREAD combines channel c (few records per channel, many channels)
+__device__ __forceinline__ void lsq_combine_thread(const double* partials, const Tiles& tiles, int64_t outer, int64_t c,
+                                                   const LsqOut& o, const QPDev& qpd) {
+    const uint32_t items = (uint32_t)outer * tiles.chunks;
+    double e = 0.0, b = 0.0;
+    for (uint32_t i = 0; i < items; ++i) {
+        const size_t slot = record_slot(tiles, (uint32_t)outer, (uint32_t)c, i);
+        e += __ldcg(partials + 2 * slot);
+        b += __ldcg(partials + 2 * slot + 1);
+    }
+    lsq_store_channel(o, qpd, c, e, b);
+}
+
 // one warp combines channel c
 __device__ __forceinline__ void lsq_combine_warp(const double* partials, const Tiles& tiles, int64_t outer, int64_t c,
                                                  const LsqOut& o, const QPDev& qpd) {
     const int lane = threadIdx.x & 31;
-    const int64_t C = tiles.channels, items = outer * (int64_t)tiles.chunks;
+    const uint32_t items = (uint32_t)outer * tiles.chunks;
     double e = 0.0, b = 0.0;
-    for (int64_t i = lane; i < items; i += 32) {
-        const int64_t oo = i / tiles.chunks, k = i - oo * tiles.chunks;
-        const size_t slot = (size_t)((oo * C + c) * tiles.chunks + k);
+    for (uint32_t i = lane; i < items; i += 32) {
+        const size_t slot = record_slot(tiles, (uint32_t)outer, (uint32_t)c, i);
         e += __ldcg(partials + 2 * slot);
         b += __ldcg(partials + 2 * slot + 1);
     }
@@ -209,11 +221,11 @@ __device__ __forceinline__ void lsq_combine_warp(const double* partials, const T
 __device__ __forceinline__ void lsq_combine_cta(const double* partials, const Tiles& tiles, int64_t outer, int64_t c,
                                                 const LsqOut& o, const QPDev& qpd, double (*s_red)[2]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t C = tiles.channels, items = outer * (int64_t)tiles.chunks;
+    const uint32_t items = (uint32_t)outer * tiles.chunks;
     double e = 0.0, b = 0.0;
-    for (int64_t i = threadIdx.x; i < items; i += kThreads) {
-        const int64_t oo = i / tiles.chunks, k = i - oo * tiles.chunks;
-        const size_t slot = (size_t)((oo * C + c) * tiles.chunks + k);
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < items; i += kThreads) {
+        const size_t slot = record_slot(tiles, (uint32_t)outer, (uint32_t)c, i);
         e += __ldcg(partials + 2 * slot);
         b += __ldcg(partials + 2 * slot + 1);
     }
@@ -284,16 +296,26 @@ __global__ void __launch_bounds__(kThreads)
         }
     }
     if (!use_ticket) return;
-    if (!last_cta_ticket((unsigned int*)ws)) return;
-    for (int64_t c = warp; c < tiles.channels; c += kWarps) lsq_combine_warp(partials, tiles, outer, c, o, qpd);
+    if (!last_cta_ticket((unsigned int*)ws, GROUP == 32 ? lane == 0 : threadIdx.x == 0)) return;
+    if ((uint32_t)outer * tiles.chunks <= kThreadCombineMaxItems) {
+        for (int64_t c = threadIdx.x; c < tiles.channels; c += kThreads) lsq_combine_thread(partials, tiles, outer, c, o, qpd);
+    } else if (tiles.channels < kWarps) {
+        for (int64_t c = 0; c < tiles.channels; ++c) lsq_combine_cta(partials, tiles, outer, c, o, qpd, s_red);
+    } else {
+        for (int64_t c = warp; c < tiles.channels; c += kWarps) lsq_combine_warp(partials, tiles, outer, c, o, qpd);
+    }
 }
 
-template <bool CTA_WIDE>
+// MODE 0: thread per channel, 1: warp per channel, 2: CTA per channel
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
     lsq_finalize_kernel(Tiles tiles, QPDev qpd, const void* ws, LsqOut o, int64_t outer) {
     __shared__ double s_red[kWarps][2];
     const double* partials = (const double*)((const char*)ws + kWsHeader);
-    if (CTA_WIDE) {
+    if (MODE == 0) {
+        for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < tiles.channels; c += (int64_t)gridDim.x * kThreads)
+            lsq_combine_thread(partials, tiles, outer, c, o, qpd);
+    } else if (MODE == 2) {
         for (int64_t c = blockIdx.x; c < tiles.channels; c += gridDim.x)
             lsq_combine_cta(partials, tiles, outer, c, o, qpd, s_red);
     } else {
@@ -462,18 +484,22 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
             return VSIQ_ERR_INVALID_ARG;                                                                       \
         int grid = launch_grid(ctas_for_tiles<G>(tiles.n_tiles));                                              \
         if (grid < 0) return -grid;                                                                            \
-        const int use_ticket = grid <= single_wave_ctas() ? 1 : 0;                                             \
+        const int use_ticket = tiles.n_tiles <= kTicketMaxRecords ? 1 : 0;                                     \
         lsq_bwd_kernel<G, V, M, Z><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd, workspace, lo,             \
                                                               layout->outer, use_ticket);                      \
         if (!use_ticket) {                                                                                     \
             const int64_t items = layout->outer * (int64_t)tiles.chunks;                                       \
-            if (items >= 512) {                                                                                \
+            if (items <= kThreadCombineMaxItems) {                                                             \
+                int64_t fg = (layout->channels + kThreads - 1) / kThreads;                                     \
+                lsq_finalize_kernel<0><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, qpd, workspace, lo, \
+                                                                                          layout->outer);      \
+            } else if (items >= 512) {                                                                         \
                 int fgrid = (int)(layout->channels < 1024 ? layout->channels : 1024);                          \
-                lsq_finalize_kernel<true><<<fgrid, kThreads, 0, st>>>(tiles, qpd, workspace, lo, layout->outer); \
+                lsq_finalize_kernel<2><<<fgrid, kThreads, 0, st>>>(tiles, qpd, workspace, lo, layout->outer);  \
             } else {                                                                                           \
                 int64_t fg = (layout->channels + kWarps - 1) / kWarps;                                         \
-                lsq_finalize_kernel<false><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, qpd, workspace, \
-                                                                                              lo, layout->outer); \
+                lsq_finalize_kernel<1><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, qpd, workspace, lo, \
+                                                                                          layout->outer);      \
             }                                                                                                  \
         }                                                                                                      \
     }

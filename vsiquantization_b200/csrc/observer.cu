@@ -153,18 +153,22 @@ template <int STRIDE>
 __device__ __forceinline__ void observe_combine(const double* partials, const Tiles& tiles, int64_t outer, int64_t c,
                                                 const ObserveOut& o, double (*s_red)[kPartialWidth]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tid = STRIDE == 32 ? lane : (int)threadIdx.x;
-    const int64_t C = tiles.channels, items = outer * (int64_t)tiles.chunks;
+    const int tid = STRIDE == 1 ? 0 : (STRIDE == 32 ? lane : (int)threadIdx.x);
+    const uint32_t items = (uint32_t)outer * tiles.chunks;
     float mn = INFINITY, mx = -INFINITY;
     double sa = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int64_t i = tid; i < items; i += STRIDE) {
-        const int64_t oo = i / tiles.chunks, k = i - oo * tiles.chunks;
-        const double* p = partials + (size_t)((oo * C + c) * tiles.chunks + k) * kPartialWidth;
+#pragma unroll 2
+    for (uint32_t i = tid; i < items; i += STRIDE) {
+        const double* p = partials + (size_t)record_slot(tiles, (uint32_t)outer, (uint32_t)c, i) * kPartialWidth;
         mn = nanmin(mn, (float)__ldcg(p));
         mx = nanmax(mx, (float)__ldcg(p + 1));
         sa += __ldcg(p + 2);
         s1 += __ldcg(p + 3);
         s2 += __ldcg(p + 4);
+    }
+    if (STRIDE == 1) {  // one thread owns the channel
+        observe_store_channel(o, c, mn, mx, sa, s1, s2);
+        return;
     }
     mn = warp_min(mn);
     mx = warp_max(mx);
@@ -222,16 +226,26 @@ __global__ void __launch_bounds__(kThreads)
         }
     }
     if (!use_ticket) return;
-    if (!last_cta_ticket((unsigned int*)ws)) return;
-    for (int64_t c = warp; c < tiles.channels; c += kWarps) observe_combine<32>(partials, tiles, outer, c, o, s_red);
+    if (!last_cta_ticket((unsigned int*)ws, GROUP == 32 ? lane == 0 : threadIdx.x == 0)) return;
+    if ((uint32_t)outer * tiles.chunks <= kThreadCombineMaxItems) {
+        for (int64_t c = threadIdx.x; c < tiles.channels; c += kThreads) observe_combine<1>(partials, tiles, outer, c, o, s_red);
+    } else if (tiles.channels < kWarps) {
+        for (int64_t c = 0; c < tiles.channels; ++c) observe_combine<kThreads>(partials, tiles, outer, c, o, s_red);
+    } else {
+        for (int64_t c = warp; c < tiles.channels; c += kWarps) observe_combine<32>(partials, tiles, outer, c, o, s_red);
+    }
 }
 
-template <bool CTA_WIDE>
+// MODE 0: thread per channel, 1: warp per channel, 2: CTA per channel
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
     observe_finalize_kernel(Tiles tiles, int64_t outer, const void* ws, ObserveOut o) {
     __shared__ double s_red[kWarps][kPartialWidth];
     const double* partials = (const double*)((const char*)ws + kWsHeader);
-    if (CTA_WIDE) {
+    if (MODE == 0) {
+        for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < tiles.channels; c += (int64_t)gridDim.x * kThreads)
+            observe_combine<1>(partials, tiles, outer, c, o, s_red);
+    } else if (MODE == 2) {
         for (int64_t c = blockIdx.x; c < tiles.channels; c += gridDim.x)
             observe_combine<kThreads>(partials, tiles, outer, c, o, s_red);
     } else {
@@ -331,17 +345,21 @@ extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* s
         uint32_t want = G == kThreads ? tiles.n_tiles : (tiles.n_tiles + kWarps - 1) / kWarps;                  \
         int grid = launch_grid(want);                                                                           \
         if (grid < 0) return -grid;                                                                             \
-        const int use_ticket = grid <= single_wave_ctas() ? 1 : 0;                                              \
+        const int use_ticket = tiles.n_tiles <= kTicketMaxRecords ? 1 : 0;                                      \
         observe_kernel<G, V><<<grid, kThreads, 0, st>>>(x, tiles, layout->outer, workspace, oo, use_ticket);    \
         if (!use_ticket) {                                                                                      \
             const int64_t items = layout->outer * (int64_t)tiles.chunks;                                        \
-            if (items >= 512) {                                                                                 \
+            if (items <= kThreadCombineMaxItems) {                                                              \
+                int64_t fg = (layout->channels + kThreads - 1) / kThreads;                                      \
+                observe_finalize_kernel<0><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, layout->outer, \
+                                                                                              workspace, oo);   \
+            } else if (items >= 512) {                                                                          \
                 int fgrid = (int)(layout->channels < 1024 ? layout->channels : 1024);                           \
-                observe_finalize_kernel<true><<<fgrid, kThreads, 0, st>>>(tiles, layout->outer, workspace, oo); \
+                observe_finalize_kernel<2><<<fgrid, kThreads, 0, st>>>(tiles, layout->outer, workspace, oo);    \
             } else {                                                                                            \
                 int64_t fg = (layout->channels + kWarps - 1) / kWarps;                                          \
-                observe_finalize_kernel<false><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(              \
-                    tiles, layout->outer, workspace, oo);                                                       \
+                observe_finalize_kernel<1><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, layout->outer, \
+                                                                                              workspace, oo);   \
             }                                                                                                   \
         }                                                                                                       \
     }

@@ -133,7 +133,18 @@ def _count_launch(n: int = 1) -> None:
 # ----------------------------------------------------------------------------------------------
 # raw ops
 # ----------------------------------------------------------------------------------------------
-def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_codes: bool = False):
+def _out_like(x: torch.Tensor, out: Optional[torch.Tensor], name: str) -> torch.Tensor:
+    if out is None:
+        return torch.empty_like(x)
+    if out.shape != x.shape or out.dtype != torch.float32 or out.device != x.device or not out.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous float32 tensor shaped like the input, on the same device")
+    if out.data_ptr() == x.data_ptr():
+        raise ValueError(f"{name} must not alias the input")
+    return out
+
+
+def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_codes: bool = False,
+                       out: Optional[torch.Tensor] = None):
     """y = (clamp(rint(x/s + z), qmin, qmax) - z) * s  [reference: quantizers/uniform.py:54-55,95]."""
     x = _require_cuda_f32(x, "x")
     outer, C, inner = layout_of(x.shape, spec.ch_axis)
@@ -141,7 +152,7 @@ def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_cod
     keep: list = []
     with torch.cuda.device(x.device):
         qp = _make_qparams(spec, scale, zero_point, max(C, 1), x.device, keep)
-        y = torch.empty_like(x)
+        y = _out_like(x, out, "out")
         codes = None
         if want_codes:
             codes = torch.empty(x.shape, dtype=torch.int8 if spec.qmin < 0 else torch.uint8, device=x.device)
@@ -151,7 +162,8 @@ def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_cod
     return (y, codes) if want_codes else y
 
 
-def fake_quant_backward_ste(x: torch.Tensor, g: torch.Tensor, scale, zero_point, spec: QSpec) -> torch.Tensor:
+def fake_quant_backward_ste(x: torch.Tensor, g: torch.Tensor, scale, zero_point, spec: QSpec,
+                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dx of the forward through the straight-through estimator [uniform.py:258-271 + clamp backward]."""
     x = _require_cuda_f32(x, "x")
     g = _require_cuda_f32(g, "grad_output")
@@ -160,14 +172,14 @@ def fake_quant_backward_ste(x: torch.Tensor, g: torch.Tensor, scale, zero_point,
     keep: list = []
     with torch.cuda.device(x.device):
         qp = _make_qparams(spec, scale, zero_point, C, x.device, keep)
-        dx = torch.empty_like(x)
+        dx = _out_like(x, out, "out")
         check(lib.vsiq_fake_quant_bwd_ste(x.data_ptr(), g.data_ptr(), dx.data_ptr(), ctypes.byref(lay),
                                           ctypes.byref(qp), _stream_ptr()), "vsiq_fake_quant_bwd_ste")
         _count_launch()
     return dx
 
 
-def fake_quant_forward_backward(x, g, scale, zero_point, spec: QSpec):
+def fake_quant_forward_backward(x, g, scale, zero_point, spec: QSpec, y_out=None, dx_out=None):
     """Fused forward + STE backward sweep (16 B/element) -- used by the host pipeline and the bench."""
     x = _require_cuda_f32(x, "x")
     g = _require_cuda_f32(g, "grad_output")
@@ -176,7 +188,7 @@ def fake_quant_forward_backward(x, g, scale, zero_point, spec: QSpec):
     keep: list = []
     with torch.cuda.device(x.device):
         qp = _make_qparams(spec, scale, zero_point, C, x.device, keep)
-        y, dx = torch.empty_like(x), torch.empty_like(x)
+        y, dx = _out_like(x, y_out, "y_out"), _out_like(x, dx_out, "dx_out")
         check(lib.vsiq_fake_quant_fwd_bwd(x.data_ptr(), g.data_ptr(), y.data_ptr(), dx.data_ptr(), ctypes.byref(lay),
                                           ctypes.byref(qp), _stream_ptr()), "vsiq_fake_quant_fwd_bwd")
         _count_launch()
@@ -185,7 +197,8 @@ def fake_quant_forward_backward(x, g, scale, zero_point, spec: QSpec):
 
 def lsq_backward(x, g, scale, zero_point, spec: QSpec, grad_scale: float, grad_scale_dev: Optional[torch.Tensor] = None,
                  ds_out: Optional[torch.Tensor] = None, dz_out: Optional[torch.Tensor] = None, want_dz: bool = False,
-                 ds_dtype: torch.dtype = torch.float32, dz_dtype: torch.dtype = torch.float32):
+                 ds_dtype: torch.dtype = torch.float32, dz_dtype: torch.dtype = torch.float32,
+                 dx_out: Optional[torch.Tensor] = None):
     """dx + per-channel dscale (+ dzero_point) in one pass [uniform.py:47-55,242-255; lsq_module.py:147-173,317-340].
 
     ds_out / dz_out let the caller point the kernel at slices of a flat gradient buffer (parallel.py)."""
@@ -196,7 +209,7 @@ def lsq_backward(x, g, scale, zero_point, spec: QSpec, grad_scale: float, grad_s
     keep: list = []
     with torch.cuda.device(x.device):
         qp = _make_qparams(spec, scale, zero_point, C, x.device, keep)
-        dx = torch.empty_like(x)
+        dx = _out_like(x, dx_out, "dx_out")
         ds = ds_out if ds_out is not None else torch.empty(C, dtype=ds_dtype, device=x.device)
         dz = dz_out if dz_out is not None else (torch.empty(C, dtype=dz_dtype, device=x.device) if want_dz else None)
         if ds.numel() != C or (dz is not None and dz.numel() != C):
