@@ -122,6 +122,10 @@ def cpu_baseline(log2n: int, iters: int = 5, warm: int = 2):
     """The reference's op sequence on the host cores (torch eager, all threads) over 2^log2n elements."""
     import torch
     from oracle import torch_port
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     n = 1 << log2n
     torch.manual_seed(0)
     x, g = torch.randn(n), torch.randn(n)
@@ -165,6 +169,11 @@ def run_reference(args):
         return 0  # the reference arm runs on rank 0 alone
     import torch
     from oracle import torch_port
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core it can use
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     n = 1 << args.cpu_log2n
     torch.manual_seed(0)
     x, g = torch.randn(n), torch.randn(n)

@@ -1,0 +1,266 @@
+"""YOLOv8 QAT step benchmark (BASELINE.json configs 0/2/3/4): images/s of fwd + bwd + optimizer step through the fused
+QAT layers, synthetic data, one process per GPU.
+
+    python -m benchmarks.yolo_qat --model s --batch 64 --imgsz 640 [--w-bits 4 --a-bits 8 --asym --per-channel]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 -m benchmarks.yolo_qat --model l --batch 16
+
+Every step copies its uint8 image batch from pinned host memory, runs forward / backward / (flat qparam-gradient
+all-reduce) / SGD step and reads the loss back to the host: the number is end to end.  Loss = sum over the three
+heads of mean(out^2) (the reference's ComputeLoss needs box targets; the detection loss is out of scope).
+`--quant-impl eager` swaps the two plugins for torch-eager restatements of the reference's op sequence on the SAME
+GPU -- the GPU-vs-GPU yardstick of SURVEY 8(d) -- everything else (fused layers, manager, cuDNN convs) unchanged.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def install_eager_plugins():
+    """Reference-composition plugins (torch eager on the current device) under the reference's registry names."""
+    from oracle import torch_port
+    from vsiquantization_b200.utils.registry import CLASS_REGISTRY
+
+    class EagerUniformQuantizer:
+        def __init__(self, num_bits=8, symmetric=True):
+            self.num_bits, self.symmetric = num_bits, symmetric
+            self.qmin, self.qmax = (-(2 ** (num_bits - 1)), 2 ** (num_bits - 1) - 1) if symmetric else (0, 2 ** num_bits - 1)
+            self.calib_grad_scale = 1
+            self.ch_axis = None
+
+        def quantize(self, x, scale, zero_point, is_learning_scale=False):
+            if is_learning_scale and isinstance(scale, torch.Tensor):
+                gs = (self.qmax * x.numel()) ** -0.5 * self.calib_grad_scale
+                scale = torch_port._ScaleGrad.apply(scale, gs)
+                if not self.symmetric and isinstance(zero_point, torch.Tensor):
+                    zero_point = torch.clamp(torch_port._RoundSTE.apply(zero_point), self.qmin, self.qmax)
+                    zero_point = torch_port._ScaleGrad.apply(zero_point, gs)
+            x_int = torch.clamp(torch_port._RoundSTE.apply(x / scale + zero_point), self.qmin, self.qmax)
+            return (x_int - zero_point) * scale
+
+    class EagerMinMaxObserver:
+        """observers/minmax.py:25-88 verbatim in behaviour: two reductions + two .item() syncs per call."""
+
+        def __init__(self, symmetric=True, num_bits=8, eps=1e-8):
+            self.symmetric, self.num_bits, self.eps = symmetric, num_bits, eps
+            self.min_val = self.max_val = 0
+            self.ch_axis = None
+            self.state = None
+            self._abs = []
+
+        def observe(self, x):
+            mn, mx = x.min().item(), x.max().item()
+            self._abs.append(x.abs().mean().item())
+            self.last_stats, self.last_count = None, x.numel()
+            self.min_val, self.max_val = min(self.min_val, mn), max(self.max_val, mx)
+
+        def get_scale_zero_point(self):
+            if self.symmetric:
+                return max(abs(self.min_val), abs(self.max_val)) / (2 ** (self.num_bits - 1) - 1 + self.eps), 0
+            s = (self.max_val - self.min_val) / (2 ** self.num_bits - 1 + self.eps)
+            return s, round(-self.min_val / (s + self.eps))
+
+        def forward(self, x):
+            self.observe(x)
+            return self.get_scale_zero_point()
+
+    CLASS_REGISTRY["UniformQuantizer"] = EagerUniformQuantizer
+    CLASS_REGISTRY["LSQQuantizer"] = EagerUniformQuantizer
+    CLASS_REGISTRY["MinMaxObserver"] = EagerMinMaxObserver
+    CLASS_REGISTRY["LSQObserver"] = EagerMinMaxObserver
+
+
+def _eager_manager_patch():
+    """The eager observers keep host floats; give the manager the reference's host-side calibration / LSQ init."""
+    import numpy as np
+    from vsiquantization_b200.quantizers.quantization_manager import QuantizationManager as M
+
+    def collect(self, x):
+        if not self.is_learning_scale and self.is_observer_qparam:
+            self.scale, self.zero_point = self.observer.forward(x.detach())
+
+    def init(self):
+        if self.observer._abs:
+            self.scale = float(2 * np.mean(self.observer._abs) / np.sqrt(2 ** (self.bits_width - 1) - 1))
+
+    M.collect_qparameter, M.init_scaling_factor_for_learning = collect, init
+
+
+def build_model(args, device):
+    from vsiquantization_b200.modules.fuse import fuse_modules_unified
+    from vsiquantization_b200.modules.fuse_config import FuseConfig, create_fuse_config_manager
+    from vsiquantization_b200.nets import yolov8
+    from vsiquantization_b200.utils.quantize_manager import activate_learning_qparam, activate_quantizer, calibrate_qat_model
+    torch.manual_seed(0)
+    model = getattr(yolov8, f"yolo_v8_{args.model}")(num_classes=20).to(device)
+    qname = "LSQQuantizer" if args.lsq else "UniformQuantizer"
+    oname = "LSQObserver" if args.lsq else "MinMaxObserver"
+    cfg = FuseConfig(observer_w_name=oname, quantizer_w_name=qname, observer_a_name=oname, quantizer_a_name=qname,
+                     w_symmetric=not args.asym, a_symmetric=not args.asym, is_fuse_bn=not args.keep_bn,
+                     bits_w=args.w_bits, bits_a=args.a_bits,
+                     w_ch_axis=0 if args.per_channel else None, a_ch_axis=1 if args.per_channel else None)
+    layer_cfgs = {}
+    if args.mixed:  # BASELINE configs[4]: backbone LSQ W4, head UniformQuantizer W8
+        layer_cfgs = {r"^net\..*conv": FuseConfig(observer_w_name="LSQObserver", quantizer_w_name="LSQQuantizer",
+                                                  observer_a_name="LSQObserver", quantizer_a_name="LSQQuantizer",
+                                                  bits_w=4, bits_a=8),
+                      r"^head\.": FuseConfig(bits_w=8, bits_a=8)}
+    model = fuse_modules_unified(model, [["conv", "bn", "relu"]], config_manager=create_fuse_config_manager(cfg, layer_cfgs))
+    n_fused = sum(1 for m in model.modules() if hasattr(m, "weight_quantizer"))
+    g = torch.Generator().manual_seed(1)
+    calib = [(torch.randint(0, 256, (args.calib_batch, 3, args.imgsz, args.imgsz), generator=g, dtype=torch.uint8), None)
+             for _ in range(args.calib_batches)]
+
+    def data_calib(m, loader, dev):
+        m.eval()
+        with torch.no_grad():
+            for imgs, _ in loader:
+                m(imgs.to(dev, non_blocking=True).float() / 255.0)
+
+    t0 = time.perf_counter()
+    calibrate_qat_model(model, calib, data_calib, device)
+    torch.cuda.synchronize()
+    calib_s = time.perf_counter() - t0
+    if dist.is_initialized() and args.quant_impl == "native":
+        from vsiquantization_b200.parallel import sync_observers
+        sync_observers(model)
+    activate_learning_qparam(model, use_init=True)
+    activate_quantizer(model)
+    model.to(device)
+    return model, n_fused, calib_s
+
+
+def run(args) -> dict:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=device)
+    torch.backends.cudnn.benchmark = True
+    if args.quant_impl == "eager":
+        import vsiquantization_b200.quantizers.quantization_manager  # noqa: F401  (registers the native plugins first)
+        install_eager_plugins()
+        _eager_manager_patch()
+    from vsiquantization_b200 import _lib
+    model, n_fused, calib_s = build_model(args, device)
+    model.train()
+    bucket = None
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        if args.quant_impl == "native":
+            from vsiquantization_b200.parallel import QParamGradBucket
+            bucket = QParamGradBucket(model)
+            bucket.ddp_ignore(model)
+        net = DDP(model, device_ids=[local])
+    opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.9, nesterov=True)
+    g = torch.Generator().manual_seed(100 + rank)
+    host = [torch.randint(0, 256, (args.batch, 3, args.imgsz, args.imgsz), generator=g, dtype=torch.uint8).pin_memory()
+            for _ in range(2)]
+
+    def step(i):
+        imgs = host[i % 2].to(device, non_blocking=True).float() / 255.0
+        outs = net(imgs)
+        loss = sum((o.float() ** 2).mean() for o in outs)
+        if world > 1:
+            loss = loss * world  # the reference undoes DDP's averaging the same way (yolov8_qat.py:235-236)
+        loss.backward()
+        if bucket is not None:
+            bucket.all_reduce()
+        opt.step()
+        if bucket is not None:
+            bucket.zero()
+            for p in model.parameters():
+                if p.grad is not None and p not in bucket_params:
+                    p.grad = None
+        else:
+            opt.zero_grad(set_to_none=True)
+        return float(loss.item())  # device -> host read of the step's result
+
+    bucket_params = set(bucket.params) if bucket is not None else set()
+    if args.cuda_graph:
+        if world > 1:
+            raise SystemExit("--cuda-graph is single-GPU for now (DDP's bucketed all-reduce is not captured)")
+        from vsiquantization_b200.graph import GraphedQATStep
+        graphed = GraphedQATStep(model, opt, lambda outs: sum((o.float() ** 2).mean() for o in outs),
+                                 host[0].to(device).float() / 255.0)
+
+        def step(i):  # noqa: F811
+            imgs = host[i % 2].to(device, non_blocking=True).float() / 255.0
+            return float(graphed(imgs).item())
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = 0.0
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = _lib.launch_count - l0
+    res = {"model": f"yolov8{args.model}", "fused_layers": n_fused, "batch_per_gpu": args.batch, "imgsz": args.imgsz,
+           "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps,
+           "images_per_s": args.batch * world * args.steps / (ms * 1e-3), "quant_impl": args.quant_impl,
+           "w_bits": args.w_bits, "a_bits": args.a_bits, "asymmetric": args.asym, "per_channel": args.per_channel,
+           "lsq": args.lsq, "mixed": args.mixed, "cuda_graph": args.cuda_graph, "loss": loss, "vsiq_launches_per_step": launches / args.steps,
+           "calibration_s": calib_s, "calib_batches": args.calib_batches,
+           "h2d_bytes_per_step": args.batch * 3 * args.imgsz * args.imgsz, "d2h_bytes_per_step": 4,
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    return res
+
+
+def parse(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="n", choices=list("ntsmlx"))
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--imgsz", type=int, default=320)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--w-bits", type=int, default=8)
+    ap.add_argument("--a-bits", type=int, default=8)
+    ap.add_argument("--asym", action="store_true")
+    ap.add_argument("--per-channel", action="store_true")
+    ap.add_argument("--lsq", action="store_true")
+    ap.add_argument("--mixed", action="store_true")
+    ap.add_argument("--keep-bn", action="store_true")
+    ap.add_argument("--calib-batches", type=int, default=2)
+    ap.add_argument("--calib-batch", type=int, default=2)
+    ap.add_argument("--quant-impl", default="native", choices=["native", "eager"])
+    ap.add_argument("--cuda-graph", action="store_true", help="capture fwd+bwd+optimizer once, replay per step")
+    return ap.parse_args(argv)
+
+
+def main():
+    args = parse()
+    res = run(args)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps(res), flush=True)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -54,6 +54,10 @@ enum {
 
 enum { VSIQ_F32 = 0, VSIQ_F64 = 1 };
 
+/* activation fused in front of the quantiser (fwd, STE bwd, LSQ bwd): the fused layer's F.relu (modules/fused.py:133)
+ * followed by quantize_activation (quantizers/fake_quantize.py:49-50) becomes one pass over the conv output */
+enum { VSIQ_PRE_NONE = 0, VSIQ_PRE_RELU = 1 };
+
 /* mask semantics of the LSQ backward */
 enum {
     VSIQ_MASK_ROUNDED = 0, /* reference autograd: qmin <= rint(x/s+z) <= qmax, inclusive (uniform.py:54,95) */
@@ -83,6 +87,7 @@ typedef struct vsiq_qparams {
     int32_t zp_learned;
     int32_t qmin;
     int32_t qmax;
+    int32_t pre_op; /* VSIQ_PRE_NONE, or VSIQ_PRE_RELU: quantise relu(x) and apply relu's backward mask [x > 0] too */
 } vsiq_qparams;
 
 /* ---- library ---------------------------------------------------------------------------- */

@@ -334,3 +334,66 @@ def test_per_layer_config_qualified_names_and_yaml(tmp_path):
     assert model.backbone[0].conv.bits_w == 4 and model.backbone[0].conv.weight_quantizer.is_symmetric is False
     assert type(model.backbone[1].conv.weight_quantizer.quantizer).__name__ == "LSQQuantizer"
     assert isinstance(model.stem.norm, torch.nn.Identity) and isinstance(model.head, torch.nn.Conv2d)
+
+
+@pytest.mark.parametrize("learn,per_channel", [(False, False), (True, False), (True, True)])
+def test_fused_relu_quant_equals_relu_then_quant(learn, per_channel):
+    """quantize(x, pre_relu=True) == quantize(relu(x)) bit for bit: y, the gradient w.r.t. the pre-activation, dscale, dzp."""
+    from vsiquantization_b200.quantizers.uniform import LSQQuantizer
+    torch.manual_seed(3)
+    x0 = torch.randn(3, 8, 33, 31, device="cuda") * 2
+    x0.view(-1)[:7] = torch.tensor([0.0, -0.0, float("nan"), 1e-40, -1e-40, float("inf"), -float("inf")], device="cuda")
+    g = torch.randn_like(x0)
+    q = LSQQuantizer(8, False)
+
+    def run(fused):
+        x = x0.clone().requires_grad_(True)
+        if per_channel:
+            s = torch.nn.Parameter(torch.linspace(0.01, 0.03, 8, device="cuda").view(1, 8, 1, 1))
+            z = torch.nn.Parameter(torch.linspace(-2.0, 9.0, 8, device="cuda").view(1, 8, 1, 1))
+        else:
+            s = torch.nn.Parameter(torch.tensor(0.02, dtype=torch.float64, device="cuda")) if learn else 0.02
+            z = torch.nn.Parameter(torch.tensor(3.3, device="cuda")) if learn else 3
+        y = q.quantize(x, s, z, learn, pre_relu=True) if fused else q.quantize(torch.relu(x), s, z, learn)
+        y.backward(g)
+        outs = [y.detach(), x.grad]
+        if learn:
+            outs += [s.grad, z.grad]
+        return [o.cpu().numpy() for o in outs]
+
+    a, b = run(True), run(False)
+    assert bits_equal(a[0], b[0]), first_mismatch(a[0], b[0])
+    fin = np.isfinite(x0.cpu().numpy())
+    assert bits_equal(a[1][fin], b[1][fin]), first_mismatch(a[1][fin], b[1][fin])
+    if learn:  # the NaN / inf inputs poison the sums identically in both paths; compare the finite channels
+        for u, w in zip(a[2:], b[2:]):
+            ok = np.isfinite(w)
+            np.testing.assert_allclose(u[ok], w[ok], rtol=1e-6, atol=1e-12)
+
+
+def test_fused_layer_relu_fusion_is_transparent():
+    """ConvBnReLU with the ReLU folded into the output quantiser gives the same output and gradients as the two-pass form."""
+    from vsiquantization_b200.modules.fused import ConvBnReLU
+    torch.manual_seed(0)
+    args = ("MinMaxObserver", "UniformQuantizer", "MinMaxObserver", "UniformQuantizer", True, True, True, 8, 8)
+    cv, bn = torch.nn.Conv2d(4, 8, 3, 1, 1, bias=False), torch.nn.BatchNorm2d(8)
+    layer = ConvBnReLU(cv, bn, torch.nn.ReLU(), *args).cuda()
+    x = torch.randn(2, 4, 16, 16, device="cuda")
+    for qm in (layer.weight_quantizer, layer.activation_quantizer):
+        qm.is_learning_scale, qm.is_quantize = False, False
+    layer.eval()(x)
+    for qm in (layer.weight_quantizer, layer.activation_quantizer):
+        qm.is_learning_scale, qm.is_quantize = True, True
+        qm.init_scaling_factor_for_learning()
+        qm.make_learn_qparameter()
+    res = []
+    for fuse in (True, False):
+        layer.fuse_relu_into_quant = fuse
+        layer.zero_grad(set_to_none=True)
+        xin = x.clone().requires_grad_(True)
+        y = layer(xin)
+        (y ** 2).sum().backward()
+        res.append([y.detach(), xin.grad, layer.conv_fuse.weight.grad.clone(), layer.activation_quantizer.scale.grad.clone()])
+    for u, w in zip(*res):
+        assert torch.allclose(u, w, rtol=1e-6, atol=1e-7)
+    assert torch.equal(res[0][0], res[1][0])

@@ -1,0 +1,132 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: observer MIN/MAX/SUM exchange and the flat qparam-gradient
+bucket.  The collectives are device-agnostic torch.distributed code; the GPU-only step (recomputing scales from the
+reduced extrema) is checked here against the oracle's formula."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(fn, world=2):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_entry, args=(fn, r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0, f"rank exited with {p.exitcode}"
+    return [q.get() for _ in range(world)]
+
+
+def _entry(fn, rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q.put(fn(rank, world))
+    finally:
+        dist.destroy_process_group()
+
+
+def _observer_case(rank, world):
+    from vsiquantization_b200.parallel import reduce_observer_states
+    rng = np.random.default_rng(7)
+    batches = [rng.standard_normal((4, 50)).astype(np.float32) * (1 + i) for i in range(4)]  # same on every rank
+    mine = batches[rank::world]  # calibration batches sharded across ranks
+    states = np.zeros((3, 8))
+    states[:, 2] = 1.0
+    for row in range(3):  # three quantisers looking at different slices
+        run_min = run_max = 0.0
+        for b in mine:
+            st = oracle.minmax_stats(b[:, row * 10:(row + 1) * 10 + 20])
+            run_min, run_max = oracle.minmax_update(run_min, run_max, st[0, 0], st[0, 1])
+            n = b[:, row * 10:(row + 1) * 10 + 20].size
+            states[row, 4] += 1
+            states[row, 5] += st[0, 2] / n
+            states[row, 6] += st[0, 3] / n
+        states[row, 0], states[row, 1] = run_min, run_max
+    t = torch.tensor(states, dtype=torch.float64)
+    reduce_observer_states(t)
+    return t.numpy()
+
+
+def test_observer_allreduce_equals_single_process_union():
+    res = _run(_observer_case)
+    assert np.array_equal(res[0], res[1])  # all ranks agree
+    rng = np.random.default_rng(7)
+    batches = [rng.standard_normal((4, 50)).astype(np.float32) * (1 + i) for i in range(4)]
+    for row in range(3):
+        run_min = run_max = 0.0
+        mean_abs = []
+        for b in batches:
+            st = oracle.minmax_stats(b[:, row * 10:(row + 1) * 10 + 20])
+            run_min, run_max = oracle.minmax_update(run_min, run_max, st[0, 0], st[0, 1])
+            mean_abs.append(st[0, 2] / b[:, row * 10:(row + 1) * 10 + 20].size)
+        # MIN/MAX are exact: extrema -- and therefore the scales derived from them -- are bit-identical
+        assert (res[0][row, 0], res[0][row, 1]) == (run_min, run_max)
+        assert oracle.qparams(res[0][row, 0], res[0][row, 1], 8, True) == oracle.qparams(run_min, run_max, 8, True)
+        assert oracle.qparams(res[0][row, 0], res[0][row, 1], 4, False) == oracle.qparams(run_min, run_max, 4, False)
+        assert res[0][row, 4] == 4  # calls summed over ranks
+        # LSQ init from summed statistics: order-dependent sum, tolerance
+        assert 2 * res[0][row, 5] / res[0][row, 4] == pytest.approx(2 * np.mean(mean_abs), rel=1e-12)
+
+
+class _Q(torch.nn.Module):
+    def __init__(self, asym):
+        super().__init__()
+        self.scale = torch.nn.Parameter(torch.tensor(0.05, dtype=torch.float64))
+        if asym:
+            self.zero_point = torch.nn.Parameter(torch.tensor(3.0))
+
+
+class _Layer(torch.nn.Module):
+    def __init__(self, asym):
+        super().__init__()
+        self.weight_quantizer = _Q(False)
+        self.activation_quantizer = _Q(asym)
+        self.lin = torch.nn.Linear(4, 4)
+
+
+def _bucket_case(rank, world):
+    from vsiquantization_b200.parallel import QParamGradBucket
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(_Layer(False), _Layer(True))
+    bucket = QParamGradBucket(model, average=True)
+    assert len(bucket) == 5 and bucket.numel() == 5 and len(bucket.flat) == 2  # 4 fp64 scales, 1 fp32 zero-point
+    out = []
+    for step in range(2):
+        bucket.zero()
+        loss = sum((p * (rank + 1 + step)).sum() for p in bucket.params)  # d/dp = rank + 1 + step
+        loss.backward()
+        for p in bucket.params:  # autograd accumulated in place: .grad is still a view of the flat buffer
+            assert p.grad.data_ptr() in {f[i:].data_ptr() for f in bucket.flat.values() for i in range(f.numel())}
+        bucket.all_reduce()
+        out.append([float(p.grad) for p in bucket.params])
+    names = list(bucket.names)
+    bucket.ddp_ignore(model)
+    ignored = sorted(getattr(model, "_ddp_params_and_buffers_to_ignore"))
+    return out, names, ignored
+
+
+def test_qparam_grad_bucket_single_collective_per_dtype():
+    res = _run(_bucket_case)
+    (g0, names0, ign0), (g1, _, _) = res
+    assert g0 == g1
+    assert g0[0] == [1.5] * 5 and g0[1] == [2.5] * 5  # mean over ranks of (rank + 1 + step)
+    assert all(n.endswith(("quantizer.scale", "quantizer.zero_point")) for n in names0)
+    assert ign0 == sorted(names0)

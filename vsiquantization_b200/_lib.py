@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("VSIQ_LIB") or os.path.join(_HERE, "libvsiq.so")  # VS
 
 F32, F64 = 0, 1
 MASK_ROUNDED, MASK_FUNLSQ = 0, 1
+PRE_NONE, PRE_RELU = 0, 1
 STATS_WIDTH, STATE_WIDTH = 5, 8
 
 c_void_p, c_int, c_int64, c_float, c_double, c_size_t = (
@@ -27,7 +28,8 @@ class Layout(ctypes.Structure):
 class QParams(ctypes.Structure):
     _fields_ = [("scale", c_void_p), ("zero_point", c_void_p), ("scale_dtype", ctypes.c_int32),
                 ("zp_dtype", ctypes.c_int32), ("scale_host", c_float), ("zp_host", c_float),
-                ("zp_learned", ctypes.c_int32), ("qmin", ctypes.c_int32), ("qmax", ctypes.c_int32)]
+                ("zp_learned", ctypes.c_int32), ("qmin", ctypes.c_int32), ("qmax", ctypes.c_int32),
+                ("pre_op", ctypes.c_int32)]
 
 
 class VsiqError(RuntimeError):

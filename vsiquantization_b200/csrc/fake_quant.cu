@@ -21,22 +21,32 @@ struct QuantOpBase : OpBase {
     __device__ __forceinline__ bool vec_bad() const { return bad; }
 };
 
+// RELU = true fuses the preceding activation into the quantiser: the kernels see the conv output x, quantise
+// relu(x) = max(x, 0) (NaN propagates like torch.relu) and, in the backward, also apply relu's mask [x > 0]
+// (threshold_backward) -- one pass instead of relu + fake-quant (fused.py:133 then fake_quantize.py:49-50).
+template <bool RELU>
+__device__ __forceinline__ float pre_act(float x) { return RELU ? max_nan(x, 0.0f) : x; }
+
+template <bool RELU>
 struct FwdOp : QuantOpBase {
     __device__ __forceinline__ void apply(const float (&a)[1], float (&o)[1]) {
-        o[0] = dequant(elem_fast(a[0], p, bad).q, p);
+        o[0] = dequant(elem_fast(pre_act<RELU>(a[0]), p, bad).q, p);
     }
     __device__ __forceinline__ void apply_slow(const float (&a)[1], float (&o)[1]) {
-        o[0] = dequant(elem_slow(a[0], p).q, p);
+        o[0] = dequant(elem_slow(pre_act<RELU>(a[0]), p).q, p);
     }
 };
 
+template <bool RELU>
 struct SteBwdOp : QuantOpBase {
     __device__ __forceinline__ void apply(const float (&a)[2], float (&o)[1]) {
-        const Elem e = elem_fast(a[0], p, bad);
-        o[0] = dx_fast(a[1], e.m, p, bad);
+        const Elem e = elem_fast(pre_act<RELU>(a[0]), p, bad);
+        const float dx = dx_fast(a[1], e.m, p, bad);
+        o[0] = (!RELU || a[0] > 0.0f) ? dx : 0.0f;
     }
     __device__ __forceinline__ void apply_slow(const float (&a)[2], float (&o)[1]) {
-        o[0] = dx_slow(a[1], elem_slow(a[0], p).m, p);
+        const float dx = dx_slow(a[1], elem_slow(pre_act<RELU>(a[0]), p).m, p);
+        o[0] = (!RELU || a[0] > 0.0f) ? dx : 0.0f;
     }
 };
 
@@ -53,7 +63,7 @@ struct FwdBwdOp : QuantOpBase {
     }
 };
 
-template <int MASK_MODE, bool WANT_DZ>
+template <int MASK_MODE, bool WANT_DZ, bool RELU>
 struct LsqBwdOp : QuantOpBase {
     float e_acc;  // sum g * ((q - z) - m * x/s)   over this thread's elements of the current tile
     float b_acc;  // sum g over clamped-out elements
@@ -86,14 +96,16 @@ struct LsqBwdOp : QuantOpBase {
         }
     }
     __device__ __forceinline__ void apply(const float (&a)[2], float (&o)[1]) {
-        const Elem e = elem_fast(a[0], p, bad);
+        const Elem e = elem_fast(pre_act<RELU>(a[0]), p, bad);
         if (MASK_MODE == VSIQ_MASK_ROUNDED) o[0] = dx_fast(a[1], e.m, p, bad);
         accumulate(a[1], e, o);
+        if (RELU) o[0] = a[0] > 0.0f ? o[0] : 0.0f;
     }
     __device__ __forceinline__ void apply_slow(const float (&a)[2], float (&o)[1]) {
-        const Elem e = elem_slow(a[0], p);
+        const Elem e = elem_slow(pre_act<RELU>(a[0]), p);
         if (MASK_MODE == VSIQ_MASK_ROUNDED) o[0] = dx_slow(a[1], e.m, p);
         accumulate(a[1], e, o);
+        if (RELU) o[0] = a[0] > 0.0f ? o[0] : 0.0f;
     }
 };
 
@@ -113,21 +125,21 @@ __device__ __forceinline__ void run_elementwise(const float* const (&in)[NIN], f
     }
 }
 
-template <int GROUP, int V>
+template <int GROUP, int V, bool RELU>
 __global__ void __launch_bounds__(kThreads) fq_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                           Tiles tiles, QPDev qpd) {
     const float* const in[1] = {x};
     float* const out[1] = {y};
-    run_elementwise<GROUP, V, FwdOp, 1, 1>(in, out, tiles, qpd);
+    run_elementwise<GROUP, V, FwdOp<RELU>, 1, 1>(in, out, tiles, qpd);
 }
 
-template <int GROUP, int V>
+template <int GROUP, int V, bool RELU>
 __global__ void __launch_bounds__(kThreads) fq_bwd_ste_kernel(const float* __restrict__ x,
                                                               const float* __restrict__ g,
                                                               float* __restrict__ dx, Tiles tiles, QPDev qpd) {
     const float* const in[2] = {x, g};
     float* const out[1] = {dx};
-    run_elementwise<GROUP, V, SteBwdOp, 2, 1>(in, out, tiles, qpd);
+    run_elementwise<GROUP, V, SteBwdOp<RELU>, 2, 1>(in, out, tiles, qpd);
 }
 
 template <int GROUP, int V>
@@ -248,7 +260,7 @@ __device__ __forceinline__ void lsq_combine_cta(const double* partials, const Ti
     }
 }
 
-template <int GROUP, int V, int MASK_MODE, bool WANT_DZ>
+template <int GROUP, int V, int MASK_MODE, bool WANT_DZ, bool RELU>
 __global__ void __launch_bounds__(kThreads)
     lsq_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, Tiles tiles,
                    QPDev qpd, void* ws, LsqOut o, int64_t outer, int use_ticket) {
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(kThreads)
     double* partials = ws_partials(ws);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    LsqBwdOp<MASK_MODE, WANT_DZ> op;
+    LsqBwdOp<MASK_MODE, WANT_DZ, RELU> op;
     int64_t cur_channel = -1;
     for (uint32_t t = group_index<GROUP>(); t < tiles.n_tiles; t += group_count<GROUP>()) {
         const TileCursor<GROUP> c = tile_at<GROUP>(tiles, t);
@@ -362,6 +374,7 @@ extern "C" int vsiq_fake_quant_fwd(const float* x, float* y, void* codes, const 
     if (!x || (!y && !codes)) return VSIQ_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (codes) {
+        if (qp->pre_op != VSIQ_PRE_NONE) return VSIQ_ERR_UNSUPPORTED;
         if (qp->qmin < -128 || qp->qmax > 255 || (qp->qmin < 0 && qp->qmax > 127)) return VSIQ_ERR_UNSUPPORTED;
         int64_t blocks = (n + kThreads - 1) / kThreads;
         int grid = (int)(blocks > (1 << 20) ? (1 << 20) : blocks);
@@ -378,7 +391,10 @@ extern "C" int vsiq_fake_quant_fwd(const float* x, float* y, void* codes, const 
             return VSIQ_ERR_INVALID_ARG;                                                    \
         int grid = launch_grid(ctas_for_tiles<G>(tiles.n_tiles));   \
         if (grid < 0) return -grid;                                                         \
-        fq_fwd_kernel<G, V><<<grid, kThreads, 0, st>>>(x, y, tiles, qpd);                   \
+        if (qp->pre_op == VSIQ_PRE_RELU)                                                    \
+            fq_fwd_kernel<G, V, true><<<grid, kThreads, 0, st>>>(x, y, tiles, qpd);         \
+        else                                                                                \
+            fq_fwd_kernel<G, V, false><<<grid, kThreads, 0, st>>>(x, y, tiles, qpd);        \
     }
     VSIQ_DISPATCH_GROUP_VEC(warp_group, vec8, CALL);
 #undef CALL
@@ -402,7 +418,10 @@ extern "C" int vsiq_fake_quant_bwd_ste(const float* x, const float* g, float* dx
             return VSIQ_ERR_INVALID_ARG;                                                      \
         int grid = launch_grid(ctas_for_tiles<G>(tiles.n_tiles)); \
         if (grid < 0) return -grid;                                                           \
-        fq_bwd_ste_kernel<G, V><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd);             \
+        if (qp->pre_op == VSIQ_PRE_RELU)                                                      \
+            fq_bwd_ste_kernel<G, V, true><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd);   \
+        else                                                                                  \
+            fq_bwd_ste_kernel<G, V, false><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd);  \
     }
     VSIQ_DISPATCH_GROUP_VEC(warp_group, vec8, CALL);
 #undef CALL
@@ -416,6 +435,7 @@ extern "C" int vsiq_fake_quant_fwd_bwd(const float* x, const float* g, float* y,
     if (int e = fill_qp(qp, &qpd)) return e;
     if (layout->outer * layout->channels * layout->inner == 0) return VSIQ_OK;
     if (!x || !g || !y || !dx) return VSIQ_ERR_INVALID_ARG;
+    if (qp->pre_op != VSIQ_PRE_NONE) return VSIQ_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const bool warp_group = layout->inner < kWarpGroupMaxInner;
     const bool vec8 = aligned32(x) && aligned32(g) && aligned32(y) && aligned32(dx);
@@ -452,7 +472,7 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
     if (!dscale) return VSIQ_ERR_INVALID_ARG;
     if (int e = check_layout(layout)) return e;
     if (mask_mode != VSIQ_MASK_ROUNDED && mask_mode != VSIQ_MASK_FUNLSQ) return VSIQ_ERR_INVALID_ARG;
-    if (mask_mode == VSIQ_MASK_FUNLSQ && dzp) return VSIQ_ERR_UNSUPPORTED;
+    if (mask_mode == VSIQ_MASK_FUNLSQ && (dzp || (qp && qp->pre_op != VSIQ_PRE_NONE))) return VSIQ_ERR_UNSUPPORTED;
     if ((dscale_dtype != VSIQ_F32 && dscale_dtype != VSIQ_F64) || (dzp && dzp_dtype != VSIQ_F32 && dzp_dtype != VSIQ_F64))
         return VSIQ_ERR_INVALID_ARG;
     QPDev qpd;
@@ -479,13 +499,21 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
     lo.want_dz = dzp != nullptr;
 #define LAUNCH(G, V, M, Z)                                                                                     \
     {                                                                                                          \
+        if (qp->pre_op == VSIQ_PRE_RELU) {                                                                     \
+            LAUNCH_R(G, V, M, Z, true);                                                                        \
+        } else {                                                                                               \
+            LAUNCH_R(G, V, M, Z, false);                                                                       \
+        }                                                                                                      \
+    }
+#define LAUNCH_R(G, V, M, Z, R)                                                                                \
+    {                                                                                                          \
         const int mult = reduce_tile_mult<G>(layout->outer, layout->channels, layout->inner);                 \
         if (!make_tiles<G>(layout->outer, layout->channels, layout->inner, &tiles, mult))                      \
             return VSIQ_ERR_INVALID_ARG;                                                                       \
         int grid = launch_grid(ctas_for_tiles<G>(tiles.n_tiles));                                              \
         if (grid < 0) return -grid;                                                                            \
         const int use_ticket = tiles.n_tiles <= kTicketMaxRecords ? 1 : 0;                                     \
-        lsq_bwd_kernel<G, V, M, Z><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd, workspace, lo,             \
+        lsq_bwd_kernel<G, V, M, Z, R><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd, workspace, lo,          \
                                                               layout->outer, use_ticket);                      \
         if (!use_ticket) {                                                                                     \
             const int64_t items = layout->outer * (int64_t)tiles.chunks;                                       \
@@ -516,6 +544,7 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
     VSIQ_DISPATCH_GROUP_VEC(warp_group, vec8, CALL);
 #undef CALL
 #undef LAUNCH
+#undef LAUNCH_R
     return (int)cudaGetLastError();
 }
 

@@ -271,7 +271,10 @@ __global__ void lsq_init_kernel(const double* __restrict__ state, int64_t C, int
     if (c >= C) return;
     const double* st = state + c * VSIQ_STATE_WIDTH;
     // quantization_manager.py:112: 2 * np.mean(mean_abs_x) / np.sqrt(2 ** (bits - 1) - 1)
-    const double s0 = 2.0 * (st[5] / st[4]) / sqrt((double)((1 << (bits - 1)) - 1));
+    double s0 = 2.0 * (st[5] / st[4]) / sqrt((double)((1 << (bits - 1)) - 1));
+    // a channel that only ever saw zeros (dead ReLU channel) would get step size 0 and turn 0/0 into NaN; torch's
+    // own observers floor the scale at fp32 epsilon, so do that (never binding for the reference's per-tensor case)
+    if (!(s0 >= 1.1920928955078125e-07)) s0 = (s0 != s0) ? s0 : 1.1920928955078125e-07;
     if (out_f64)
         ((double*)out)[c] = s0;
     else

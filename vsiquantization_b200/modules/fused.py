@@ -74,17 +74,35 @@ class ConvBnReLU(_ConvBase):
             self.bn = bn
         self._bn_reestimate = None  # set by utils.estimate_bn while re-estimating
 
+    fuse_relu_into_quant = True  # ReLU + output fake-quant as one kernel pass (same values, one read/write less)
+
     def _bn(self, x):
         if self._bn_reestimate is not None:
             return self._bn_reestimate(self, x)
         return self.bn(x)
 
-    def run_forward_core(self, x, weights, bias):
+    def _pre_activation(self, x, weights, bias):
         x = self._conv(x, weights, bias)
         if not self.is_fuse_bn:
             x = self._bn(x)
+        return x
+
+    def run_forward_core(self, x, weights, bias):
+        x = self._pre_activation(x, weights, bias)
         # the reference applies SiLU when relu is not an nn.ReLU -- including relu=None (ConvBn overrides this)
         return F.relu(x) if self.is_relu else F.silu(x)
+
+    def forward(self, x):
+        """fake_quantize.py:43-51 with the ReLU folded into the output quantiser when that is possible."""
+        if not (self.fuse_relu_into_quant and self.is_relu and self._has_act and self.quantize_out
+                and type(self).run_forward_core is ConvBnReLU.run_forward_core
+                and self.activation_quantizer.can_fuse_relu()):
+            return super().forward(x)
+        if self.quantize_inp:
+            x = self.quantize_activation(x)
+        weights, bias = self.get_weight_bias()
+        weights = self.quantize_weights(weights)
+        return self.activation_quantizer.quantize(self._pre_activation(x, weights, bias), pre_relu=True)
 
 
 class ConvBn(ConvBnReLU):

@@ -81,12 +81,14 @@ class QSpec:
     ch_axis: Optional[int] = None
     zp_learned: bool = False
     mask_mode: int = _lib.MASK_ROUNDED
+    pre_relu: bool = False  # quantise relu(x); the backward also applies relu's mask (one pass instead of two)
 
 
 def _make_qparams(spec: QSpec, scale, zero_point, channels: int, device: torch.device, keep: list) -> QParams:
     qp = QParams()
     qp.qmin, qp.qmax = int(spec.qmin), int(spec.qmax)
     qp.zp_learned = 1 if spec.zp_learned else 0
+    qp.pre_op = _lib.PRE_RELU if spec.pre_relu else _lib.PRE_NONE
     qp.scale_dtype = qp.zp_dtype = F32
     if isinstance(scale, torch.Tensor):
         s = scale.detach()

@@ -103,8 +103,22 @@ class QuantizationManager(nn.Module):
             self._calibrated = True
             self._invalidate()
 
-    def quantize(self, x):
-        """collect (if calibrating) then fake-quantise (if enabled) -- :73-90."""
+    def can_fuse_relu(self) -> bool:
+        """True when quantize(x, pre_relu=True) will run relu + fake-quant as ONE kernel pass."""
+        collecting = (not self.is_learning_scale) and self.is_observer_qparam
+        return bool(self.is_quantize and not collecting and getattr(self.quantizer, "supports_pre_relu", False))
+
+    def quantize(self, x, pre_relu: bool = False):
+        """collect (if calibrating) then fake-quantise (if enabled) -- :73-90.  ``pre_relu``: x is the pre-activation
+        and relu is applied here -- fused into the quantiser kernels when quantising, as a plain F.relu otherwise."""
+        if pre_relu:
+            if not self.can_fuse_relu():
+                return self.quantize(torch.nn.functional.relu(x))
+            if "scale" in self._parameters or "zero_point" in self._parameters or not self._calibrated \
+                    or "scale" in self.__dict__:
+                return self.quantizer.quantize(x, self.scale, self.zero_point, self.is_learning_scale, pre_relu=True)
+            s, z = self.observer.device_qparams()
+            return self.quantizer.quantize(x, s, z, self.is_learning_scale, pre_relu=True)
         self.collect_qparameter(x)
         if not self.is_quantize:
             return x

@@ -65,20 +65,24 @@ class UniformQuantizer(BaseQuantizer):
                 return axes[0]
         raise ValueError("per-channel scale: set quantizer.ch_axis or pass a broadcast-shaped scale")
 
-    def _spec(self, ch_axis, zp_learned=False) -> ops.QSpec:
+    supports_pre_relu = True  # quantize(..., pre_relu=True) fuses the preceding ReLU into the kernels
+
+    def _spec(self, ch_axis, zp_learned=False, pre_relu=False) -> ops.QSpec:
         mode = _lib.MASK_FUNLSQ if self.mask_mode == "funlsq" else _lib.MASK_ROUNDED
-        return ops.QSpec(self.qmin, self.qmax, ch_axis=ch_axis, zp_learned=zp_learned, mask_mode=mode)
+        return ops.QSpec(self.qmin, self.qmax, ch_axis=ch_axis, zp_learned=zp_learned, mask_mode=mode,
+                         pre_relu=pre_relu)
 
     # -- the plugin entry point ------------------------------------------------------------------------
-    def quantize(self, x, scale, zero_point, is_learning_scale=False):
-        """Fake-quantise x (uniform.py:34-56).
+    def quantize(self, x, scale, zero_point, is_learning_scale=False, pre_relu=False):
+        """Fake-quantise x (uniform.py:34-56); with ``pre_relu`` quantise relu(x) in the same pass (the fused layer's
+        F.relu, modules/fused.py:133, folded into the kernel; gradients include relu's mask).
 
         scale: Python int/float, np.float64, or a tensor / nn.Parameter with 1 or C entries (fp32 or the reference's
         0-dim fp64, on any device).  zero_point: Python int, or a float tensor / nn.Parameter (learnable: the forward
         uses clamp(round(z)), uniform.py:98-102).  The result is autograd-connected to x and to every qparam that
         requires grad."""
         if not x.is_cuda:
-            y = self.quantize(_as_cuda(x), scale, zero_point, is_learning_scale)
+            y = self.quantize(_as_cuda(x), scale, zero_point, is_learning_scale, pre_relu)
             return y.to(x.device)
         ch_axis = self._resolve_axis(x, scale)
         scale_learn = isinstance(scale, torch.Tensor) and scale.requires_grad and torch.is_grad_enabled()
@@ -89,7 +93,7 @@ class UniformQuantizer(BaseQuantizer):
         if not (scale_learn or zp_learn):
             s = scale.detach() if isinstance(scale, torch.Tensor) else scale
             z = zero_point.detach() if zp_tensor else zero_point
-            return ops.FakeQuantFixed.apply(x, s, z, self._spec(ch_axis, zp_learned=zp_round))
+            return ops.FakeQuantFixed.apply(x, s, z, self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu))
         if not isinstance(scale, torch.Tensor):
             raise TypeError("a learnable zero_point needs a tensor scale")
         C = scale.numel()
@@ -103,7 +107,8 @@ class UniformQuantizer(BaseQuantizer):
             else:
                 gs_host *= float(cgs)
         zp_arg = zero_point if zp_learn else (zero_point.detach() if zp_tensor else zero_point)
-        return ops.FakeQuantLearned.apply(x, scale, zp_arg, self._spec(ch_axis, zp_learned=zp_round), gs_host, gs_dev)
+        return ops.FakeQuantLearned.apply(x, scale, zp_arg, self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu),
+                                          gs_host, gs_dev)
 
     def quantize_codes(self, x, scale, zero_point):
         """(fake-quantised tensor, integer codes as int8/uint8) -- the reference keeps codes as floats (uniform.py:54)."""
