@@ -156,6 +156,8 @@ def run(args) -> dict:
     from vsiquantization_b200 import _lib
     model, n_fused, calib_s = build_model(args, device)
     model.train()
+    if args.channels_last:
+        model.to(memory_format=torch.channels_last)
     bucket = None
     net = model
     if world > 1:
@@ -170,8 +172,10 @@ def run(args) -> dict:
     host = [torch.randint(0, 256, (args.batch, 3, args.imgsz, args.imgsz), generator=g, dtype=torch.uint8).pin_memory()
             for _ in range(2)]
 
+    cl = (lambda t: t.contiguous(memory_format=torch.channels_last)) if args.channels_last else (lambda t: t)
+
     def step(i):
-        imgs = host[i % 2].to(device, non_blocking=True).float() / 255.0
+        imgs = cl(host[i % 2].to(device, non_blocking=True).float() / 255.0)
         outs = net(imgs)
         loss = sum((o.float() ** 2).mean() for o in outs)
         if world > 1:
@@ -195,10 +199,10 @@ def run(args) -> dict:
             raise SystemExit("--cuda-graph is single-GPU for now (DDP's bucketed all-reduce is not captured)")
         from vsiquantization_b200.graph import GraphedQATStep
         graphed = GraphedQATStep(model, opt, lambda outs: sum((o.float() ** 2).mean() for o in outs),
-                                 host[0].to(device).float() / 255.0)
+                                 cl(host[0].to(device).float() / 255.0))
 
         def step(i):  # noqa: F811
-            imgs = host[i % 2].to(device, non_blocking=True).float() / 255.0
+            imgs = cl(host[i % 2].to(device, non_blocking=True).float() / 255.0)
             return float(graphed(imgs).item())
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -225,7 +229,8 @@ def run(args) -> dict:
            "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps,
            "images_per_s": args.batch * world * args.steps / (ms * 1e-3), "quant_impl": args.quant_impl,
            "w_bits": args.w_bits, "a_bits": args.a_bits, "asymmetric": args.asym, "per_channel": args.per_channel,
-           "lsq": args.lsq, "mixed": args.mixed, "cuda_graph": args.cuda_graph, "loss": loss, "vsiq_launches_per_step": launches / args.steps,
+           "lsq": args.lsq, "mixed": args.mixed, "cuda_graph": args.cuda_graph, "channels_last": args.channels_last,
+           "loss": loss, "vsiq_launches_per_step": launches / args.steps,
            "calibration_s": calib_s, "calib_batches": args.calib_batches,
            "h2d_bytes_per_step": args.batch * 3 * args.imgsz * args.imgsz, "d2h_bytes_per_step": 4,
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
@@ -249,6 +254,7 @@ def parse(argv=None):
     ap.add_argument("--calib-batches", type=int, default=2)
     ap.add_argument("--calib-batch", type=int, default=2)
     ap.add_argument("--quant-impl", default="native", choices=["native", "eager"])
+    ap.add_argument("--channels-last", action="store_true", help="NHWC memory format (cuDNN's native layout on sm_100)")
     ap.add_argument("--cuda-graph", action="store_true", help="capture fwd+bwd+optimizer once, replay per step")
     return ap.parse_args(argv)
 

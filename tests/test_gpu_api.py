@@ -397,3 +397,40 @@ def test_fused_layer_relu_fusion_is_transparent():
     for u, w in zip(*res):
         assert torch.allclose(u, w, rtol=1e-6, atol=1e-7)
     assert torch.equal(res[0][0], res[1][0])
+
+
+def test_channels_last_runs_in_place_layout():
+    """Per-tensor quantisation and weight rows walk channels_last memory without a copy and give the same VALUES as NCHW."""
+    from vsiquantization_b200 import ops
+    from vsiquantization_b200.quantizers.uniform import UniformQuantizer
+    torch.manual_seed(1)
+    x = torch.randn(4, 16, 9, 7, device="cuda")
+    g = torch.randn(4, 16, 9, 7, device="cuda")
+    xc = x.contiguous(memory_format=torch.channels_last)
+    q = UniformQuantizer(8, True)
+    s = torch.nn.Parameter(torch.tensor(0.02, dtype=torch.float64, device="cuda"))
+    outs = []
+    for inp, grad in ((x, g), (xc, g), (xc, g.contiguous(memory_format=torch.channels_last))):
+        s.grad = None
+        inp = inp.clone(memory_format=torch.preserve_format).requires_grad_(True)
+        y = q.quantize(inp, s, 0, True, pre_relu=True)
+        assert y.stride() == inp.stride()  # output keeps the input's memory format
+        y.backward(grad)
+        outs.append((y.detach(), inp.grad, s.grad.clone()))
+    for y, dx, ds in outs[1:]:
+        assert torch.equal(y, outs[0][0]) and torch.equal(dx, outs[0][1])
+        assert ds.item() == pytest.approx(outs[0][2].item(), rel=1e-6)  # same terms, different summation order
+    # weights: ch_axis 0 on channels_last memory (the output channel is outermost in both formats)
+    w = torch.randn(8, 16, 3, 3, device="cuda")
+    wc = w.contiguous(memory_format=torch.channels_last)
+    sc = torch.linspace(0.01, 0.05, 8, device="cuda")
+    spec = ops.QSpec(-8, 7, ch_axis=0)
+    assert torch.equal(ops.fake_quant_forward(wc, sc, torch.zeros(8, device="cuda"), spec),
+                       ops.fake_quant_forward(w, sc, torch.zeros(8, device="cuda"), spec))
+    # per-channel activations need NCHW rows: converted, values still right
+    spa = ops.QSpec(0, 255, ch_axis=1)
+    sa = torch.linspace(0.01, 0.05, 16, device="cuda")
+    assert torch.equal(ops.fake_quant_forward(xc, sa, torch.zeros(16, device="cuda"), spa),
+                       ops.fake_quant_forward(x, sa, torch.zeros(16, device="cuda"), spa))
+    st = ops.observe(xc).cpu()
+    assert st[0, 0].item() == x.min().item() and st[0, 1].item() == x.max().item()

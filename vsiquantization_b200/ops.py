@@ -35,6 +35,42 @@ def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _dense_for(t: torch.Tensor, name: str, ch_axis: Optional[int]) -> torch.Tensor:
+    """CUDA fp32 tensor the kernels can walk WITHOUT a copy.
+
+    The kernels only need memory order, not logical order: per-tensor work (ch_axis None) and weight rows (ch_axis 0,
+    the output channel is outermost in both formats) run on channels_last memory as it is, so cuDNN's native NHWC layout
+    on sm_100 never has to be converted for the quantiser.  Per-channel ACTIVATION quantisation (ch_axis 1) needs the
+    channel to own contiguous rows, i.e. NCHW: anything else is converted."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} lives on {t.device}; vsiquantization_b200 runs on CUDA only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.is_contiguous():
+        return t
+    if ch_axis in (None, 0):
+        if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+            return t
+        if t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d):
+            return t
+    return t.contiguous()
+
+
+def _match_layout(g: torch.Tensor, x: torch.Tensor, name: str) -> torch.Tensor:
+    """grad_output walked in the same memory order as x (elementwise kernels pair elements by address)."""
+    if not g.is_cuda or g.dtype != torch.float32:
+        _dense_for(g, name, None)  # raises the right error
+    if g.shape != x.shape:
+        raise ValueError(f"{name} has shape {tuple(g.shape)}, expected {tuple(x.shape)}")
+    if g.stride() == x.stride():
+        return g
+    out = torch.empty_like(x)  # preserve_format: x's strides
+    out.copy_(g)
+    return out
+
+
 def layout_of(shape, ch_axis: Optional[int]) -> Tuple[int, int, int]:
     """(outer, channels, inner) of a contiguous tensor quantised along ch_axis (None = per tensor)."""
     n = 1
@@ -138,8 +174,8 @@ def _count_launch(n: int = 1) -> None:
 def _out_like(x: torch.Tensor, out: Optional[torch.Tensor], name: str) -> torch.Tensor:
     if out is None:
         return torch.empty_like(x)
-    if out.shape != x.shape or out.dtype != torch.float32 or out.device != x.device or not out.is_contiguous():
-        raise ValueError(f"{name} must be a contiguous float32 tensor shaped like the input, on the same device")
+    if out.shape != x.shape or out.dtype != torch.float32 or out.device != x.device or out.stride() != x.stride():
+        raise ValueError(f"{name} must be a float32 tensor with the input's shape and strides, on the same device")
     if out.data_ptr() == x.data_ptr():
         raise ValueError(f"{name} must not alias the input")
     return out
@@ -148,7 +184,7 @@ def _out_like(x: torch.Tensor, out: Optional[torch.Tensor], name: str) -> torch.
 def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_codes: bool = False,
                        out: Optional[torch.Tensor] = None):
     """y = (clamp(rint(x/s + z), qmin, qmax) - z) * s  [reference: quantizers/uniform.py:54-55,95]."""
-    x = _require_cuda_f32(x, "x")
+    x = _dense_for(x, "x", spec.ch_axis)
     outer, C, inner = layout_of(x.shape, spec.ch_axis)
     lay = Layout(outer, C, inner)
     keep: list = []
@@ -167,8 +203,8 @@ def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_cod
 def fake_quant_backward_ste(x: torch.Tensor, g: torch.Tensor, scale, zero_point, spec: QSpec,
                             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dx of the forward through the straight-through estimator [uniform.py:258-271 + clamp backward]."""
-    x = _require_cuda_f32(x, "x")
-    g = _require_cuda_f32(g, "grad_output")
+    x = _dense_for(x, "x", spec.ch_axis)
+    g = _match_layout(g, x, "grad_output")
     outer, C, inner = layout_of(x.shape, spec.ch_axis)
     lay = Layout(outer, C, inner)
     keep: list = []
@@ -183,8 +219,8 @@ def fake_quant_backward_ste(x: torch.Tensor, g: torch.Tensor, scale, zero_point,
 
 def fake_quant_forward_backward(x, g, scale, zero_point, spec: QSpec, y_out=None, dx_out=None):
     """Fused forward + STE backward sweep (16 B/element) -- used by the host pipeline and the bench."""
-    x = _require_cuda_f32(x, "x")
-    g = _require_cuda_f32(g, "grad_output")
+    x = _dense_for(x, "x", spec.ch_axis)
+    g = _match_layout(g, x, "grad_output")
     outer, C, inner = layout_of(x.shape, spec.ch_axis)
     lay = Layout(outer, C, inner)
     keep: list = []
@@ -204,8 +240,8 @@ def lsq_backward(x, g, scale, zero_point, spec: QSpec, grad_scale: float, grad_s
     """dx + per-channel dscale (+ dzero_point) in one pass [uniform.py:47-55,242-255; lsq_module.py:147-173,317-340].
 
     ds_out / dz_out let the caller point the kernel at slices of a flat gradient buffer (parallel.py)."""
-    x = _require_cuda_f32(x, "x")
-    g = _require_cuda_f32(g, "grad_output")
+    x = _dense_for(x, "x", spec.ch_axis)
+    g = _match_layout(g, x, "grad_output")
     outer, C, inner = layout_of(x.shape, spec.ch_axis)
     lay = Layout(outer, C, inner)
     keep: list = []
@@ -245,7 +281,7 @@ def observe(x: torch.Tensor, ch_axis: Optional[int] = None, state: Optional[torc
     """One pass: per-channel {min, max, sum|x|, sum x, sum x^2} (+ running observer state, scale, zero-point).
 
     Replaces observers/minmax.py:42-47,67-74 and quantization_manager.py:66-68.  No host sync."""
-    x = _require_cuda_f32(x, "x")
+    x = _dense_for(x, "x", ch_axis)
     outer, C, inner = layout_of(x.shape, ch_axis)
     lay = Layout(outer, C, inner)
     with torch.cuda.device(x.device):
@@ -295,7 +331,7 @@ def bn_fold(W, bias, gamma, beta, mean, var, eps: float, scale=None, zero_point=
 
     With `spec` also returns the fake-quantised W' from the same pass; with want_stats the per-tensor
     {min,max,sum|x|,sum x,sum x^2} of W'.  Returns (W', b', Wq or None, stats or None)."""
-    W = _require_cuda_f32(W, "weight")
+    W = _dense_for(W, "weight", 0)
     C = W.shape[0]
     inner = W.numel() // C
     dev = W.device
