@@ -204,6 +204,23 @@ int64_t vsiq_host_pipeline_last_launches(const vsiq_host_pipeline *p);
 int vsiq_fake_quant_fwd_bwd(const float *x, const float *g, float *y, float *dx, const vsiq_layout *layout,
                             const vsiq_qparams *qp, vsiq_stream_t stream);
 
+/* ---- channel-innermost tensors (NHWC / torch.channels_last: cuDNN's native layout on sm_100) ----------
+ * The tensor is [rows, channels] with the channel fastest (rows = N*H*W).  channels % 4 == 0 and <= 1024, 16-byte
+ * aligned pointers; anything else returns VSIQ_ERR_UNSUPPORTED (the caller converts to NCHW).
+ *   forward : y  = fq(act(x + bias[c]))     bias may be NULL; act from qp->pre_op; qp_channels = 1 or channels
+ *   backward: dx (act mask included), dscale / dzp (qp_channels entries; dscale NULL = plain STE),
+ *             dbias[c] = sum_rows dx (NULL allowed) -- the fused layer's conv-bias gradient (modules/fused.py:124-130;
+ *             ATen computes it with a separate full-tensor reduction) comes out of the same pass.
+ * Same arithmetic, bit-identical values, as vsiq_fake_quant_fwd / vsiq_lsq_bwd on the NCHW-permuted tensor. */
+size_t vsiq_ci_workspace_bytes(int64_t rows, int64_t channels);
+int vsiq_ci_fake_quant_fwd(const float *x, const float *bias, float *y, int64_t rows, int64_t channels,
+                           const vsiq_qparams *qp, int64_t qp_channels, void *workspace, size_t workspace_bytes,
+                           vsiq_stream_t stream);
+int vsiq_ci_lsq_bwd(const float *x, const float *bias, const float *g, float *dx, void *dscale, int dscale_dtype,
+                    void *dzp, int dzp_dtype, float *dbias, int64_t rows, int64_t channels, const vsiq_qparams *qp,
+                    int64_t qp_channels, double grad_scale_host, const float *grad_scale_dev, void *workspace,
+                    size_t workspace_bytes, vsiq_stream_t stream);
+
 /* ---- self-test ---------------------------------------------------------------------------
  * The kernels divide by the (tile-uniform) scale through a hoisted correctly-rounded reciprocal and
  * exact-residual FMA corrections instead of the per-element IEEE division sequence.  This entry

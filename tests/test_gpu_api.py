@@ -434,3 +434,45 @@ def test_channels_last_runs_in_place_layout():
                        ops.fake_quant_forward(x, sa, torch.zeros(16, device="cuda"), spa))
     st = ops.observe(xc).cpu()
     assert st[0, 0].item() == x.min().item() and st[0, 1].item() == x.max().item()
+
+
+def test_fused_layer_channels_last_bias_epilogue():
+    """channels_last ConvBnReLU: bias add + ReLU + output quantiser in one pass, conv-bias gradient from the backward
+    kernel -- same output and gradients as the plain NCHW path."""
+    from vsiquantization_b200.modules.fused import ConvBnReLU
+    torch.manual_seed(0)
+    args = ("MinMaxObserver", "UniformQuantizer", "MinMaxObserver", "UniformQuantizer", True, True, True, 8, 8)
+    cv, bn = torch.nn.Conv2d(8, 16, 3, 1, 1, bias=False), torch.nn.BatchNorm2d(16)
+    with torch.no_grad():
+        bn.bias.normal_()
+        bn.running_mean.normal_()
+    layer = ConvBnReLU(cv, bn, torch.nn.ReLU(), *args).cuda()
+    x = torch.randn(2, 8, 12, 10, device="cuda")
+    for qm in (layer.weight_quantizer, layer.activation_quantizer):
+        qm.is_learning_scale, qm.is_quantize = False, False
+    layer.eval()(x)
+    for qm in (layer.weight_quantizer, layer.activation_quantizer):
+        qm.is_learning_scale, qm.is_quantize = True, True
+        qm.init_scaling_factor_for_learning()
+        qm.make_learn_qparameter()
+    res = []
+    for cl in (False, True):
+        layer.zero_grad(set_to_none=True)
+        if cl:
+            layer.to(memory_format=torch.channels_last)
+        xin = (x.contiguous(memory_format=torch.channels_last) if cl else x.clone()).requires_grad_(True)
+        y = layer(xin)
+        assert (not cl) or y.is_contiguous(memory_format=torch.channels_last)
+        (y ** 2).sum().backward()
+        res.append([y.detach(), xin.grad, layer.conv_fuse.weight.grad.clone(), layer.conv_fuse.bias.grad.clone(),
+                    layer.activation_quantizer.scale.grad.clone().float()])
+    # cuDNN picks different conv kernels per layout, so a few pre-activations differ in the last bits and may flip a code
+    # (one quantisation step); everything else must agree
+    for name, u, w in zip(("y", "dx", "dW", "db"), *res):
+        close = torch.isclose(u, w, rtol=2e-3, atol=2e-3 * float(w.abs().max()))
+        assert close.float().mean().item() > 0.98, (name, close.float().mean().item())
+    # dscale is a cancelling sum of rounding residuals: judge it against the mass of its terms (|g| * 0.5 per element)
+    y = res[0][0]
+    gs = (127 * y.numel()) ** -0.5
+    mass = gs * float((2 * y).abs().sum()) * 0.5
+    assert abs(float(res[0][4]) - float(res[1][4])) <= 0.02 * mass

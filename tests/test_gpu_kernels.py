@@ -381,3 +381,85 @@ def test_full_size_properties(ops, log2n):
     assert st[0] == float(x.min()) and st[1] == float(x.max())
     assert abs(st[3] - float(x.double().sum())) <= 1e-6 * st[2]
     assert st[4] == pytest.approx(float((x.double() ** 2).sum()), rel=1e-6)
+
+
+# ---------------------------------------------------------- channel-innermost (NHWC / channels_last) kernels
+@pytest.mark.parametrize("shape", [(2, 16, 9, 7), (3, 64, 20, 20), (1, 48, 33, 5), (2, 512, 6, 5), (2, 1024, 3, 3), (5, 4, 40, 40),
+                                   (64, 32, 64, 64)])
+@pytest.mark.parametrize("pcq,bias,relu", [(False, False, False), (True, False, True), (False, True, True), (True, True, True),
+                                           (True, True, False)])
+def test_channels_inner_matches_oracle(ops, shape, pcq, bias, relu):
+    """NHWC kernels == the oracle applied to the NCHW tensor (after bias add / relu in fp32), bit for bit for y and dx;
+    dscale / dzp / dbias to the fp64 oracle within summation tolerance."""
+    rng = np.random.default_rng(sum(shape) + 7 * pcq + 3 * bias + relu)
+    N, C, H, W = shape
+    x = (rng.standard_normal(shape) * 2).astype(np.float32)
+    g = rng.standard_normal(shape).astype(np.float32)
+    b = (rng.standard_normal(C) * 0.5).astype(np.float32) if bias else None
+    if pcq:
+        s = (0.02 * rng.uniform(0.5, 2.0, C)).astype(np.float32)
+        zf = rng.uniform(-3, 40, C).astype(np.float32)
+    else:
+        s = np.float32(0.023)
+        zf = np.float32(3.3)
+    spec = ops.QSpec(0, 255, ch_axis=1 if pcq else None, zp_learned=True, pre_relu=relu)
+    xt = dev(x).contiguous(memory_format=torch.channels_last)
+    gt = dev(g).contiguous(memory_format=torch.channels_last)
+    assert ops.ci_supported(xt)
+    s_t = dev(s).view(1, C, 1, 1) if pcq else torch.tensor(float(s), device="cuda")
+    z_t = dev(zf).view(1, C, 1, 1) if pcq else torch.tensor(float(zf), device="cuda")
+    bt = dev(b) if bias else None
+    y = ops.ci_forward(xt, bt, s_t, z_t, spec)
+    assert y.stride() == xt.stride()
+    # oracle on the pre-activation computed op by op in fp32
+    pre = x + b.reshape(1, C, 1, 1) if bias else x
+    act = np.where(np.isnan(pre), pre, np.maximum(pre, 0)).astype(np.float32) if relu else pre
+    y_o = oracle.fake_quant_fwd(act, s, zf, 0, 255, ch_axis=1 if pcq else None, zp_learned=True)
+    assert bits_equal(y.cpu().numpy(), y_o), first_mismatch(y.cpu().numpy(), y_o)
+    gs = ops.lsq_grad_scale(255, x.size, C if pcq else 1)
+    dx, ds, dz, db = ops.ci_backward(xt, bt, gt, s_t, z_t, spec, gs, None, True, True, True)
+    dx_o, ds_o, dz_o = oracle.fake_quant_bwd(act, g, s, zf, 0, 255, ch_axis=1 if pcq else None, zp_learned=True,
+                                             grad_scale=gs, want_dz=True)
+    if relu:
+        dx_o = np.where(pre > 0, dx_o, np.float32(0)).astype(np.float32)
+    assert bits_equal(dx.cpu().numpy(), dx_o), first_mismatch(dx.cpu().numpy(), dx_o)
+    am = np.moveaxis(act, 1, 0).reshape(C, -1) if pcq else act.reshape(1, -1)
+    gm = np.moveaxis(g, 1, 0).reshape(C, -1) if pcq else g.reshape(1, -1)
+    sv = np.atleast_1d(s).astype(np.float64)
+    zv = np.atleast_1d(zf)
+    ds, dz = ds.cpu().numpy().astype(np.float64), dz.cpu().numpy().astype(np.float64)
+    for c in range(am.shape[0]):
+        zeff = float(np.clip(np.rint(zv[c]), 0, 255))
+        mass = gs * sum_mass(am[c], gm[c], sv[c], zeff, 0, 255)
+        assert abs(ds[c] - ds_o[c]) <= 2e-6 * mass + 1e-30, (c, ds[c], ds_o[c])
+        zmass = gs * float(np.sum(np.abs(gm[c].astype(np.float64) * sv[c])))
+        assert abs(dz[c] - dz_o[c]) <= 2e-6 * zmass + 1e-30, (c, dz[c], dz_o[c])
+    if bias:
+        db_o = np.moveaxis(dx_o.astype(np.float64), 1, 0).reshape(C, -1).sum(1)
+        db_mass = np.moveaxis(np.abs(dx_o.astype(np.float64)), 1, 0).reshape(C, -1).sum(1)
+        assert np.all(np.abs(db.cpu().numpy() - db_o) <= 2e-6 * db_mass + 1e-30)
+    # STE-only form (no dscale) gives the same dx and dbias
+    dx2, ds2, _, db2 = ops.ci_backward(xt, bt, gt, s_t, z_t, spec, want_ds=False, want_dbias=True)
+    assert ds2 is None and bits_equal(dx2.cpu().numpy(), dx_o)
+    if bias:
+        assert torch.equal(db2, db)
+
+
+def test_channels_inner_special_values_and_determinism(ops):
+    x = torch.randn(4, 32, 17, 13, device="cuda")
+    x.view(-1)[:9] = torch.tensor([0.0, -0.0, float("nan"), 1e-40, -1e-40, float("inf"), -float("inf"), 3e38, 1e-30], device="cuda")
+    x = x.contiguous(memory_format=torch.channels_last)
+    g = torch.randn_like(x)
+    b = torch.randn(32, device="cuda")
+    s = torch.full((1, 32, 1, 1), 0.02, device="cuda")
+    z = torch.full((1, 32, 1, 1), 7.6, device="cuda")
+    spec = ops.QSpec(0, 255, ch_axis=1, zp_learned=True, pre_relu=True)
+    y = ops.ci_forward(x, b, s, z, spec)
+    xn = x.cpu().numpy() + b.cpu().numpy().reshape(1, 32, 1, 1)
+    act = np.where(np.isnan(xn), xn, np.maximum(xn, 0)).astype(np.float32)
+    y_o = oracle.fake_quant_fwd(act, s.cpu().numpy().reshape(-1), z.cpu().numpy().reshape(-1), 0, 255, ch_axis=1, zp_learned=True)
+    assert bits_equal(y.cpu().numpy(), y_o), first_mismatch(y.cpu().numpy(), y_o)
+    a = ops.ci_backward(x, b, g, s, z, spec, 0.01, None, True, True, True)
+    c = ops.ci_backward(x, b, g, s, z, spec, 0.01, None, True, True, True)
+    for u, w in zip(a, c):  # dynamic tile scheduling, yet bit-reproducible: fixed-order combination
+        assert torch.equal(torch.nan_to_num(u), torch.nan_to_num(w))

@@ -10,5 +10,5 @@ HOSTCXX="${VSIQ_HOSTCXX:-/usr/bin/g++}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo \
     -ccbin "$HOSTCXX" -Xcompiler -fPIC,-O2,-Wall -shared -cudart static \
     ${VSIQ_NVCC_EXTRA:-} \
-    -o "$OUT" "$HERE/abi.cu" "$HERE/fake_quant.cu" "$HERE/observer.cu" "$HERE/bn_fold.cu" "$HERE/host_pipeline.cu"
+    -o "$OUT" "$HERE/abi.cu" "$HERE/fake_quant.cu" "$HERE/observer.cu" "$HERE/bn_fold.cu" "$HERE/channels_inner.cu" "$HERE/host_pipeline.cu"
 echo "built $OUT"

@@ -1,0 +1,459 @@
+// channels_inner.cu -- the fake-quant epilogue for CHANNEL-INNERMOST tensors (NHWC / torch.channels_last, cuDNN's
+// native layout on sm_100): [rows = N*H*W][C] with the channel fastest.
+//
+//   forward : y  = fq(act(x + bias[c]))                       act = relu or identity, qparams per tensor or per channel
+//   backward: dx = STE/LSQ gradient w.r.t. x (act mask included), dscale / dzero_point (per tensor or per channel),
+//             dbias[c] = sum over rows of dx                  -- the conv's bias gradient, for free in the same pass
+//
+// Same arithmetic as fake_quant.cu (reference: quantizers/uniform.py:47-55,95,242-271; lsq_module.py:147-173,254-274,
+// 317-358); the bias add is the fused layer's conv bias (modules/fused.py:124-130) moved into this epilogue so that its
+// gradient (ATen: a separate full-tensor reduction per layer) rides along with dx.
+//
+// Mapping: C % 4 == 0 and C <= 1024.  A 128-bit vector holds 4 consecutive channels; with G = C/4 vector groups per row
+// only T = (256 / G) * G threads of a CTA are active, so thread t ALWAYS owns channel group t % G: its four channels'
+// qparams, bias and gradient accumulators live in registers for the whole kernel.  Tiles are handed out dynamically
+// (atomic counter: hardware-like balancing without a CTA launch per tile), accumulators are carried across tiles in fp64
+// and flushed ONCE per CTA; records are combined in a fixed order (deterministic) by the last CTA or a finalize launch.
+//
+// Roofline: HBM; 8 B/element forward, 12 B/element backward, as for the NCHW kernels.
+#include "common.cuh"
+
+namespace vsiq {
+
+constexpr int kCiVec = 4;
+constexpr int kCiUnroll = 4;       // 128-bit loads in flight per thread per input
+constexpr int kCiBatches = 4;      // batches per tile
+constexpr int kCiMaxChannels = 1024;
+
+struct CiGeom {
+    int64_t n_vec;       // total vectors = rows * C / 4
+    int channels;
+    int groups;          // G = C / 4
+    int threads;         // T: active threads per CTA (multiple of G)
+    int tile_vecs;       // T * unroll * batches
+    uint32_t n_tiles;
+};
+
+inline bool make_ci_geom(int64_t rows, int64_t channels, CiGeom* g) {
+    if (channels < kCiVec || channels % kCiVec != 0 || channels > kCiMaxChannels || rows <= 0) return false;
+    g->channels = (int)channels;
+    g->groups = (int)(channels / kCiVec);
+    g->threads = (kThreads / g->groups) * g->groups;
+    g->tile_vecs = g->threads * kCiUnroll * kCiBatches;
+    g->n_vec = rows * (int64_t)g->groups;
+    const int64_t nt = (g->n_vec + g->tile_vecs - 1) / g->tile_vecs;
+    if (nt <= 0 || nt >= (int64_t(1) << 31)) return false;
+    g->n_tiles = (uint32_t)nt;
+    return true;
+}
+
+struct Vec4 {
+    float v[4];
+};
+__device__ __forceinline__ Vec4 ld4(const float* p) {
+    Vec4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st4(float* p, const Vec4& r) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
+}
+
+// workspace header: [0] ticket, [1] tile counter (both left zero), records after kWsHeader
+__device__ __forceinline__ bool next_tile(unsigned int* counter, uint32_t n_tiles, uint32_t* tile) {
+    __shared__ uint32_t s_tile;
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    *tile = s_tile;
+    return s_tile < n_tiles;
+}
+
+struct CiOut {
+    void* dscale;
+    void* dzp;
+    float* dbias;
+    int ds_f64, dz_f64;
+    double gs_host;
+    const float* gs_dev;
+};
+
+// Record layout per CTA (doubles): [E: nq][B: nq][DB: C]   with nq = C (per-channel qparams) or 1 (per tensor)
+__device__ __forceinline__ int ci_record_width(int C, bool pcq, bool bias) { return 2 * (pcq ? C : 1) + (bias ? C : 0); }
+
+__device__ __forceinline__ void ci_store(const CiOut& o, const QPDev& qpd, bool pcq, bool bias, int C, int idx, double v) {
+    // idx addresses the record: [0,nq) E, [nq,2nq) B, [2nq, 2nq+C) DB
+    const int nq = pcq ? C : 1;
+    const double gs = o.gs_host * (o.gs_dev ? (double)__ldg(o.gs_dev) : 1.0);
+    if (idx < nq) {
+        if (o.dscale) {
+            const double ds = gs * v;
+            if (o.ds_f64) ((double*)o.dscale)[idx] = ds; else ((float*)o.dscale)[idx] = (float)ds;
+        }
+    } else if (idx < 2 * nq) {
+        if (o.dzp) {
+            const int c = idx - nq;
+            const QP p = load_qp(qpd, c);
+            const float zr = rintf(p.zf);
+            const bool cz = qpd.zp_learned ? ((zr >= p.lo) && (zr <= p.hi)) : true;
+            const double dz = cz ? -gs * (double)p.s * v : 0.0;
+            if (o.dz_f64) ((double*)o.dzp)[c] = dz; else ((float*)o.dzp)[c] = (float)dz;
+        }
+    } else if (bias && o.dbias) {
+        o.dbias[idx - 2 * nq] = (float)v;
+    }
+}
+
+// combine record entry `idx` over n_rec records (fixed order), one thread per entry
+__device__ __forceinline__ double ci_combine_entry(const double* records, int width, uint32_t n_rec, int idx) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    uint32_t r = 0;
+    for (; r + 4 <= n_rec; r += 4) {
+        a0 += __ldcg(records + (size_t)(r + 0) * width + idx);
+        a1 += __ldcg(records + (size_t)(r + 1) * width + idx);
+        a2 += __ldcg(records + (size_t)(r + 2) * width + idx);
+        a3 += __ldcg(records + (size_t)(r + 3) * width + idx);
+    }
+    for (; r < n_rec; ++r) a0 += __ldcg(records + (size_t)r * width + idx);
+    return (a0 + a1) + (a2 + a3);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    ci_finalize_kernel(const void* ws, int width, uint32_t n_rec, CiOut o, QPDev qpd, int pcq, int bias, int C) {
+    const double* records = (const double*)((const char*)ws + kWsHeader);
+    for (int idx = blockIdx.x * kThreads + threadIdx.x; idx < width; idx += gridDim.x * kThreads)
+        ci_store(o, qpd, pcq, bias, C, idx, ci_combine_entry(records, width, n_rec, idx));
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+template <bool PCQ, bool BIAS, bool RELU>
+__global__ void __launch_bounds__(kThreads, 2)
+    ci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y, CiGeom geo,
+                  QPDev qpd, void* ws) {
+    unsigned int* counter = (unsigned int*)ws + 1;
+    const int t = threadIdx.x;
+    const bool active = t < geo.threads;
+    const int c0 = (t % geo.groups) * kCiVec;
+    QP p[kCiVec];
+    float bv[kCiVec];
+    bool all_fast = true;
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        p[e] = load_qp(qpd, PCQ ? c0 + e : 0);
+        all_fast = all_fast && p[e].fast;
+        bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
+    }
+    uint32_t tile;
+    while (next_tile(counter, geo.n_tiles, &tile)) {
+        if (!active) continue;
+        const int64_t vb = (int64_t)tile * geo.tile_vecs;
+#pragma unroll 1
+        for (int b = 0; b < kCiBatches; ++b) {
+            Vec4 vin[kCiUnroll];
+            bool ok[kCiUnroll];
+#pragma unroll
+            for (int j = 0; j < kCiUnroll; ++j) {
+                const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
+                ok[j] = v < geo.n_vec;
+                if (ok[j]) vin[j] = ld4(x + v * kCiVec);
+            }
+#pragma unroll
+            for (int j = 0; j < kCiUnroll; ++j) {
+                if (!ok[j]) continue;
+                const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
+                Vec4 out;
+                bool bad = !all_fast;
+#pragma unroll
+                for (int e = 0; e < kCiVec; ++e) {
+                    float xe = BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e];
+                    if (RELU) xe = max_nan(xe, 0.0f);
+                    out.v[e] = dequant(elem_fast(xe, p[e], bad).q, p[e]);
+                }
+                if (bad) {
+#pragma unroll
+                    for (int e = 0; e < kCiVec; ++e) {
+                        float xe = BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e];
+                        if (RELU) xe = max_nan(xe, 0.0f);
+                        out.v[e] = dequant(elem_slow(xe, p[e]).q, p[e]);
+                    }
+                }
+                st4(y + v * kCiVec, out);
+            }
+        }
+    }
+    // the last CTA to leave resets the tile counter for the next launch
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
+        s_last = (tk == gridDim.x - 1);
+        if (s_last) {
+            *(unsigned int*)ws = 0;
+            *counter = 0;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------- backward
+template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
+__global__ void __launch_bounds__(kThreads, 2)
+    ci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ g,
+                  float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket) {
+    __shared__ double s_acc[kThreads][3 * kCiVec];  // per thread: e[4], b[4], db[4]
+    unsigned int* counter = (unsigned int*)ws + 1;
+    double* records = ws_partials(ws);
+    const int t = threadIdx.x;
+    const bool active = t < geo.threads;
+    const int C = geo.channels;
+    const int c0 = (t % geo.groups) * kCiVec;
+    QP p[kCiVec];
+    float bv[kCiVec];
+    bool all_fast = true;
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        p[e] = load_qp(qpd, PCQ ? c0 + e : 0);
+        all_fast = all_fast && p[e].fast;
+        bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
+    }
+    double acc_e[kCiVec], acc_b[kCiVec], acc_db[kCiVec];
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) acc_e[e] = acc_b[e] = acc_db[e] = 0.0;
+
+    uint32_t tile;
+    while (next_tile(counter, geo.n_tiles, &tile)) {
+        if (!active) continue;
+        const int64_t vb = (int64_t)tile * geo.tile_vecs;
+        float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials of this tile
+#pragma unroll
+        for (int e = 0; e < kCiVec; ++e) te[e] = tb[e] = tdb[e] = 0.0f;
+#pragma unroll 1
+        for (int b = 0; b < kCiBatches; ++b) {
+            Vec4 vx[kCiUnroll], vg[kCiUnroll];
+            bool ok[kCiUnroll];
+#pragma unroll
+            for (int j = 0; j < kCiUnroll; ++j) {
+                const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
+                ok[j] = v < geo.n_vec;
+                if (ok[j]) {
+                    vx[j] = ld4(x + v * kCiVec);
+                    vg[j] = ld4(g + v * kCiVec);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kCiUnroll; ++j) {
+                if (!ok[j]) continue;
+                const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
+                Vec4 out;
+                float ve[kCiVec], vbz[kCiVec];
+                bool bad = !all_fast;
+#pragma unroll
+                for (int e = 0; e < kCiVec; ++e) {
+                    const float xb = BIAS ? __fadd_rn(vx[j].v[e], bv[e]) : vx[j].v[e];
+                    const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+                    const float ge = vg[j].v[e];
+                    const Elem el = elem_fast(xe, p[e], bad);
+                    float d = dx_fast(ge, el.m, p[e], bad);
+                    if (RELU) d = xb > 0.0f ? d : 0.0f;
+                    out.v[e] = d;
+                    if (WANT_DS) {
+                        const float dd = __fsub_rn(el.q, p[e].z);
+                        const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
+                        ve[e] = ge * (dd - mv);
+                        vbz[e] = el.m ? 0.0f : ge;
+                    }
+                }
+                if (bad) {  // rare: IEEE sequences for the whole vector
+#pragma unroll
+                    for (int e = 0; e < kCiVec; ++e) {
+                        const float xb = BIAS ? __fadd_rn(vx[j].v[e], bv[e]) : vx[j].v[e];
+                        const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+                        const float ge = vg[j].v[e];
+                        const Elem el = elem_slow(xe, p[e]);
+                        float d = dx_slow(ge, el.m, p[e]);
+                        if (RELU) d = xb > 0.0f ? d : 0.0f;
+                        out.v[e] = d;
+                        if (WANT_DS) {
+                            const float dd = __fsub_rn(el.q, p[e].z);
+                            const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
+                            ve[e] = ge * (dd - mv);
+                            vbz[e] = el.m ? 0.0f : ge;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < kCiVec; ++e) {
+                    if (WANT_DS) {
+                        te[e] += ve[e];
+                        tb[e] += vbz[e];
+                    }
+                    if (BIAS) tdb[e] += out.v[e];
+                }
+                st4(dx + v * kCiVec, out);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < kCiVec; ++e) {
+            if (WANT_DS) {
+                acc_e[e] += (double)te[e];
+                acc_b[e] += (double)tb[e];
+            }
+            if (BIAS) acc_db[e] += (double)tdb[e];
+        }
+    }
+
+    // ---- one flush per CTA: fixed-order reduction over the threads that share a channel group ----
+    if (!WANT_DS && !BIAS) {
+        __shared__ int s_last0;
+        if (threadIdx.x == 0) {
+            unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
+            s_last0 = (tk == gridDim.x - 1);
+            if (s_last0) {
+                *(unsigned int*)ws = 0;
+                *counter = 0;
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        s_acc[t][e] = active ? acc_e[e] : 0.0;
+        s_acc[t][kCiVec + e] = active ? acc_b[e] : 0.0;
+        s_acc[t][2 * kCiVec + e] = active ? acc_db[e] : 0.0;
+    }
+    __syncthreads();
+    const int nq = PCQ ? C : 1;
+    const int width = 2 * nq + (BIAS ? C : 0);
+    double* rec = records + (size_t)blockIdx.x * width;
+    const int reps = geo.threads / geo.groups;
+    for (int idx = t; idx < width; idx += kThreads) {
+        double s = 0.0;
+        if (idx < 2 * nq) {
+            const int which = idx < nq ? 0 : 1;
+            if (WANT_DS) {
+                if (PCQ) {
+                    const int c = idx - which * nq;
+                    for (int k = 0; k < reps; ++k) s += s_acc[k * geo.groups + c / kCiVec][which * kCiVec + (c % kCiVec)];
+                } else {
+                    for (int k = 0; k < geo.threads; ++k)
+                        s += (s_acc[k][which * kCiVec + 0] + s_acc[k][which * kCiVec + 1]) +
+                             (s_acc[k][which * kCiVec + 2] + s_acc[k][which * kCiVec + 3]);
+                }
+            }
+        } else {
+            const int c = idx - 2 * nq;
+            for (int k = 0; k < reps; ++k) s += s_acc[k * geo.groups + c / kCiVec][2 * kCiVec + (c % kCiVec)];
+        }
+        rec[idx] = s;
+    }
+    // ticket; the last CTA also resets the tile counter
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
+        s_last = (tk == gridDim.x - 1);
+        if (s_last) {
+            *(unsigned int*)ws = 0;
+            *counter = 0;
+        }
+    }
+    __syncthreads();
+    if (!s_last || !use_ticket) return;
+    __threadfence();
+    for (int idx = t; idx < width; idx += kThreads)
+        ci_store(o, qpd, PCQ, BIAS, C, idx, ci_combine_entry(records, width, gridDim.x, idx));
+}
+
+static int ci_grid(uint32_t n_tiles) {
+    DeviceProps dp;
+    if (int e = get_device_props(&dp)) return -e;
+    const uint32_t cap = (uint32_t)dp.sm_count * 2u;  // __launch_bounds__(256, 2): every CTA resident, tiles stolen dynamically
+    return (int)(n_tiles < cap ? n_tiles : cap);
+}
+
+}  // namespace vsiq
+
+using namespace vsiq;
+
+extern "C" size_t vsiq_ci_workspace_bytes(int64_t rows, int64_t channels) {
+    CiGeom g;
+    if (!make_ci_geom(rows, channels, &g)) return 0;
+    DeviceProps dp;
+    int sms = get_device_props(&dp) ? 256 : dp.sm_count;
+    return kWsHeader + (size_t)sms * 2 * (size_t)(3 * channels) * sizeof(double);
+}
+
+extern "C" int vsiq_ci_fake_quant_fwd(const float* x, const float* bias, float* y, int64_t rows, int64_t channels,
+                                      const vsiq_qparams* qp, int64_t qp_channels, void* workspace,
+                                      size_t workspace_bytes, vsiq_stream_t stream) {
+    QPDev qpd;
+    if (int e = fill_qp(qp, &qpd)) return e;
+    if (rows == 0) return VSIQ_OK;
+    if (!x || !y) return VSIQ_ERR_INVALID_ARG;
+    if (qp_channels != 1 && qp_channels != channels) return VSIQ_ERR_INVALID_ARG;
+    CiGeom geo;
+    if (!make_ci_geom(rows, channels, &geo)) return VSIQ_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return VSIQ_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < kWsHeader) return VSIQ_ERR_WORKSPACE;
+    const int grid = ci_grid(geo.n_tiles);
+    if (grid < 0) return -grid;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool pcq = qp_channels == channels && channels > 1, relu = qp->pre_op == VSIQ_PRE_RELU, hb = bias != nullptr;
+#define F(P, B, R) ci_fwd_kernel<P, B, R><<<grid, kThreads, 0, st>>>(x, bias, y, geo, qpd, workspace)
+    if (pcq) { if (hb) { if (relu) F(true, true, true); else F(true, true, false); } else { if (relu) F(true, false, true); else F(true, false, false); } }
+    else     { if (hb) { if (relu) F(false, true, true); else F(false, true, false); } else { if (relu) F(false, false, true); else F(false, false, false); } }
+#undef F
+    return (int)cudaGetLastError();
+}
+
+extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g, float* dx, void* dscale,
+                               int dscale_dtype, void* dzp, int dzp_dtype, float* dbias, int64_t rows, int64_t channels,
+                               const vsiq_qparams* qp, int64_t qp_channels, double grad_scale_host,
+                               const float* grad_scale_dev, void* workspace, size_t workspace_bytes,
+                               vsiq_stream_t stream) {
+    QPDev qpd;
+    if (int e = fill_qp(qp, &qpd)) return e;
+    if (qp_channels != 1 && qp_channels != channels) return VSIQ_ERR_INVALID_ARG;
+    if (dzp && !dscale) return VSIQ_ERR_INVALID_ARG;
+    if (dbias && !bias) return VSIQ_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) {
+        cudaError_t ce = cudaSuccess;
+        if (dscale) ce = cudaMemsetAsync(dscale, 0, (size_t)qp_channels * (dscale_dtype ? 8 : 4), st);
+        if (ce == cudaSuccess && dzp) ce = cudaMemsetAsync(dzp, 0, (size_t)qp_channels * (dzp_dtype ? 8 : 4), st);
+        if (ce == cudaSuccess && dbias) ce = cudaMemsetAsync(dbias, 0, (size_t)channels * 4, st);
+        return (int)ce;
+    }
+    if (!x || !g || !dx) return VSIQ_ERR_INVALID_ARG;
+    CiGeom geo;
+    if (!make_ci_geom(rows, channels, &geo)) return VSIQ_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15u)
+        return VSIQ_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < vsiq_ci_workspace_bytes(rows, channels)) return VSIQ_ERR_WORKSPACE;
+    const int grid = ci_grid(geo.n_tiles);
+    if (grid < 0) return -grid;
+    const bool pcq = qp_channels == channels && channels > 1, relu = qp->pre_op == VSIQ_PRE_RELU, hb = bias != nullptr;
+    const bool want_ds = dscale != nullptr;
+    CiOut o;
+    o.dscale = dscale;
+    o.dzp = dzp;
+    o.dbias = dbias;
+    o.ds_f64 = dscale_dtype == VSIQ_F64;
+    o.dz_f64 = dzp_dtype == VSIQ_F64;
+    o.gs_host = grad_scale_host;
+    o.gs_dev = grad_scale_dev;
+    const int width = 2 * (pcq ? (int)channels : 1) + (hb ? (int)channels : 0);
+    const int use_ticket = ((int64_t)grid * width <= 65536) ? 1 : 0;  // else: multi-CTA finalize launch
+#define B(P, H, R, D) ci_bwd_kernel<P, H, R, D><<<grid, kThreads, 0, st>>>(x, bias, g, dx, geo, qpd, workspace, o, use_ticket)
+#define B3(P, H, R) { if (want_ds) B(P, H, R, true); else B(P, H, R, false); }
+#define B2(P, H) { if (relu) B3(P, H, true) else B3(P, H, false) }
+    if (pcq) { if (hb) B2(true, true) else B2(true, false) } else { if (hb) B2(false, true) else B2(false, false) }
+#undef B2
+#undef B3
+#undef B
+    if ((want_ds || hb) && !use_ticket) {
+        const int fgrid = (width + kThreads - 1) / kThreads;
+        ci_finalize_kernel<<<fgrid, kThreads, 0, st>>>(workspace, width, (uint32_t)grid, o, qpd, pcq ? 1 : 0, hb ? 1 : 0,
+                                                      (int)channels);
+    }
+    return (int)cudaGetLastError();
+}

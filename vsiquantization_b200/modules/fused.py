@@ -75,6 +75,7 @@ class ConvBnReLU(_ConvBase):
         self._bn_reestimate = None  # set by utils.estimate_bn while re-estimating
 
     fuse_relu_into_quant = True  # ReLU + output fake-quant as one kernel pass (same values, one read/write less)
+    fuse_bias_into_quant = True  # channels_last only: conv bias add + its gradient ride in the quantiser kernels
 
     def _bn(self, x):
         if self._bn_reestimate is not None:
@@ -102,6 +103,12 @@ class ConvBnReLU(_ConvBase):
             x = self.quantize_activation(x)
         weights, bias = self.get_weight_bias()
         weights = self.quantize_weights(weights)
+        if (self.fuse_bias_into_quant and bias is not None and self.is_fuse_bn and x.dim() == 4 and not x.is_contiguous()
+                and x.is_contiguous(memory_format=torch.channels_last)):
+            pre = self._conv(x, weights, None)  # bias-free conv; the epilogue adds the bias and returns its gradient
+            if ops.ci_supported(pre):
+                return self.activation_quantizer.quantize(pre, pre_relu=True, bias=bias)
+            return self.activation_quantizer.quantize(pre + bias.view(1, -1, 1, 1), pre_relu=True)
         return self.activation_quantizer.quantize(self._pre_activation(x, weights, bias), pre_relu=True)
 
 

@@ -184,6 +184,8 @@ def _out_like(x: torch.Tensor, out: Optional[torch.Tensor], name: str) -> torch.
 def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_codes: bool = False,
                        out: Optional[torch.Tensor] = None):
     """y = (clamp(rint(x/s + z), qmin, qmax) - z) * s  [reference: quantizers/uniform.py:54-55,95]."""
+    if spec.ch_axis == 1 and not want_codes and ci_supported(x):
+        return ci_forward(x, None, scale, zero_point, spec, out=out)  # per-channel qparams on NHWC memory, no conversion
     x = _dense_for(x, "x", spec.ch_axis)
     outer, C, inner = layout_of(x.shape, spec.ch_axis)
     lay = Layout(outer, C, inner)
@@ -203,6 +205,8 @@ def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_cod
 def fake_quant_backward_ste(x: torch.Tensor, g: torch.Tensor, scale, zero_point, spec: QSpec,
                             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dx of the forward through the straight-through estimator [uniform.py:258-271 + clamp backward]."""
+    if spec.ch_axis == 1 and out is None and ci_supported(x):
+        return ci_backward(x, None, g, scale, zero_point, spec, want_ds=False, want_dbias=False)[0]
     x = _dense_for(x, "x", spec.ch_axis)
     g = _match_layout(g, x, "grad_output")
     outer, C, inner = layout_of(x.shape, spec.ch_axis)
@@ -240,6 +244,11 @@ def lsq_backward(x, g, scale, zero_point, spec: QSpec, grad_scale: float, grad_s
     """dx + per-channel dscale (+ dzero_point) in one pass [uniform.py:47-55,242-255; lsq_module.py:147-173,317-340].
 
     ds_out / dz_out let the caller point the kernel at slices of a flat gradient buffer (parallel.py)."""
+    if (spec.ch_axis == 1 and ds_out is None and dz_out is None and dx_out is None and ci_supported(x)
+            and spec.mask_mode == _lib.MASK_ROUNDED):
+        dx, ds, dz, _ = ci_backward(x, None, g, scale, zero_point, spec, grad_scale, grad_scale_dev, True, want_dz,
+                                    False, ds_dtype, dz_dtype)
+        return dx, ds, dz
     x = _dense_for(x, "x", spec.ch_axis)
     g = _match_layout(g, x, "grad_output")
     outer, C, inner = layout_of(x.shape, spec.ch_axis)
@@ -265,6 +274,78 @@ def lsq_backward(x, g, scale, zero_point, spec: QSpec, grad_scale: float, grad_s
                                ws.numel(), _stream_ptr()), "vsiq_lsq_bwd")
         _count_launch()
     return dx, ds, dz
+
+
+def ci_supported(x: torch.Tensor) -> bool:
+    """True when x is a channels_last (NHWC-in-memory) activation the channel-innermost kernels can walk in place."""
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+            and x.shape[1] % 4 == 0 and x.shape[1] <= 1024 and x.data_ptr() % 16 == 0)
+
+
+def _ci_qparams(spec: QSpec, scale, zero_point, C: int, device, keep: list):
+    qpc = C if spec.ch_axis == 1 else 1
+    if spec.ch_axis not in (None, 1):
+        raise ValueError("channel-innermost activations are quantised per tensor or along dim 1")
+    return _make_qparams(spec, scale, zero_point, qpc, device, keep), qpc
+
+
+def ci_forward(x: torch.Tensor, bias: Optional[torch.Tensor], scale, zero_point, spec: QSpec,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = fq(act(x + bias[c])) on a channels_last tensor, in place of layout conversions (vsiq_ci_fake_quant_fwd)."""
+    if not ci_supported(x):
+        raise ValueError("ci_forward needs a float32 CUDA channels_last tensor with C % 4 == 0 and C <= 1024")
+    N, C, H, W = x.shape
+    rows = N * H * W
+    keep: list = []
+    with torch.cuda.device(x.device):
+        qp, qpc = _ci_qparams(spec, scale, zero_point, C, x.device, keep)
+        b = None
+        if bias is not None:
+            b = bias.detach().to(device=x.device, dtype=torch.float32).contiguous()
+            if b.numel() != C:
+                raise ValueError("bias must have one entry per channel")
+        y = _out_like(x, out, "out")
+        ws = _workspace(lib.vsiq_ci_workspace_bytes(rows, C), x.device)
+        check(lib.vsiq_ci_fake_quant_fwd(x.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(), rows, C,
+                                         ctypes.byref(qp), qpc, ws.data_ptr(), ws.numel(), _stream_ptr()),
+              "vsiq_ci_fake_quant_fwd")
+        _count_launch()
+    return y
+
+
+def ci_backward(x: torch.Tensor, bias: Optional[torch.Tensor], g: torch.Tensor, scale, zero_point, spec: QSpec,
+                grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None, want_ds: bool = True,
+                want_dz: bool = False, want_dbias: bool = True, ds_dtype=torch.float32, dz_dtype=torch.float32):
+    """dx, dscale, dzero_point, dbias of ci_forward in one pass (vsiq_ci_lsq_bwd); dscale None = plain STE."""
+    if not ci_supported(x):
+        raise ValueError("ci_backward needs a float32 CUDA channels_last tensor with C % 4 == 0 and C <= 1024")
+    g = _match_layout(g, x, "grad_output")
+    N, C, H, W = x.shape
+    rows = N * H * W
+    keep: list = []
+    with torch.cuda.device(x.device):
+        qp, qpc = _ci_qparams(spec, scale, zero_point, C, x.device, keep)
+        b = None
+        if bias is not None:
+            b = bias.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        ds = torch.empty(qpc, dtype=ds_dtype, device=x.device) if want_ds else None
+        dz = torch.empty(qpc, dtype=dz_dtype, device=x.device) if (want_ds and want_dz) else None
+        db = torch.empty(C, dtype=torch.float32, device=x.device) if (b is not None and want_dbias) else None
+        gsd = None
+        if grad_scale_dev is not None:
+            gsd = grad_scale_dev.detach().to(device=x.device, dtype=torch.float32).contiguous()
+            keep.append(gsd)
+        ws = _workspace(lib.vsiq_ci_workspace_bytes(rows, C), x.device)
+        check(lib.vsiq_ci_lsq_bwd(x.data_ptr(), b.data_ptr() if b is not None else None, g.data_ptr(), dx.data_ptr(),
+                                  ds.data_ptr() if ds is not None else None, _dtype_code(ds) if ds is not None else F32,
+                                  dz.data_ptr() if dz is not None else None, _dtype_code(dz) if dz is not None else F32,
+                                  db.data_ptr() if db is not None else None, rows, C, ctypes.byref(qp), qpc,
+                                  float(grad_scale), gsd.data_ptr() if gsd is not None else None, ws.data_ptr(),
+                                  ws.numel(), _stream_ptr()), "vsiq_ci_lsq_bwd")
+        _count_launch()
+    return dx, ds, dz, db
 
 
 def new_observer_state(channels: int = 1, device=None) -> torch.Tensor:
@@ -499,6 +580,40 @@ class FakeQuantLearned(torch.autograd.Function):
         ds = ds.view(scale.shape).to(scale.device) if ctx.needs_input_grad[1] else None
         dz = dz.view(zp.shape).to(zp.device) if want_dz else None
         return (dx if ctx.needs_input_grad[0] else None), ds, dz, None, None, None
+
+
+class FakeQuantEpilogue(torch.autograd.Function):
+    """y = fq(act(x + bias[c])) on a channels_last conv output: the fused layer's bias add, activation and output
+    quantiser as one forward pass, and dx, dbias (the conv's bias gradient), dscale, dzero_point as one backward pass."""
+
+    @staticmethod
+    def forward(ctx, x, bias, scale, zero_point, spec: QSpec, grad_scale: float, grad_scale_dev):
+        ctx.spec, ctx.grad_scale, ctx.grad_scale_dev = spec, grad_scale, grad_scale_dev
+        ctx.scale_is_tensor = isinstance(scale, torch.Tensor)
+        ctx.zp_is_tensor = isinstance(zero_point, torch.Tensor)
+        ctx.scale_const = None if ctx.scale_is_tensor else scale
+        ctx.zp_const = None if ctx.zp_is_tensor else zero_point
+        saved = [x, bias] + ([scale] if ctx.scale_is_tensor else []) + ([zero_point] if ctx.zp_is_tensor else [])
+        ctx.save_for_backward(*saved)
+        return ci_forward(x, bias, scale, zero_point, spec)
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        x, bias = saved[0], saved[1]
+        k = 2
+        scale = saved[k] if ctx.scale_is_tensor else ctx.scale_const
+        k += 1 if ctx.scale_is_tensor else 0
+        zp = saved[k] if ctx.zp_is_tensor else ctx.zp_const
+        want_ds = ctx.scale_is_tensor and ctx.needs_input_grad[2]
+        want_dz = want_ds and ctx.zp_is_tensor and ctx.needs_input_grad[3]
+        dx, ds, dz, db = ci_backward(x, bias, g, scale, zp, ctx.spec, ctx.grad_scale, ctx.grad_scale_dev, want_ds, want_dz,
+                                     ctx.needs_input_grad[1], scale.dtype if ctx.scale_is_tensor else torch.float32,
+                                     zp.dtype if ctx.zp_is_tensor else torch.float32)
+        ds = ds.view(scale.shape).to(scale.device) if want_ds else None
+        dz = dz.view(zp.shape).to(zp.device) if want_dz else None
+        db = db.view(bias.shape) if db is not None else None
+        return (dx if ctx.needs_input_grad[0] else None), db, ds, dz, None, None, None
 
 
 def lsq_grad_scale(qmax: int, numel: int, channels: int = 1) -> float:

@@ -108,17 +108,24 @@ class QuantizationManager(nn.Module):
         collecting = (not self.is_learning_scale) and self.is_observer_qparam
         return bool(self.is_quantize and not collecting and getattr(self.quantizer, "supports_pre_relu", False))
 
-    def quantize(self, x, pre_relu: bool = False):
+    def quantize(self, x, pre_relu: bool = False, bias=None):
         """collect (if calibrating) then fake-quantise (if enabled) -- :73-90.  ``pre_relu``: x is the pre-activation
-        and relu is applied here -- fused into the quantiser kernels when quantising, as a plain F.relu otherwise."""
+        and relu is applied here -- fused into the quantiser kernels when quantising, as a plain F.relu otherwise.
+        ``bias`` (with pre_relu, channels_last x): the conv bias is added in the same pass and its gradient comes out of
+        the backward kernel."""
         if pre_relu:
             if not self.can_fuse_relu():
+                if bias is not None:
+                    x = x + bias.view(1, -1, 1, 1)
                 return self.quantize(torch.nn.functional.relu(x))
+            kw = {"pre_relu": True}
+            if bias is not None:
+                kw["bias"] = bias
             if "scale" in self._parameters or "zero_point" in self._parameters or not self._calibrated \
                     or "scale" in self.__dict__:
-                return self.quantizer.quantize(x, self.scale, self.zero_point, self.is_learning_scale, pre_relu=True)
+                return self.quantizer.quantize(x, self.scale, self.zero_point, self.is_learning_scale, **kw)
             s, z = self.observer.device_qparams()
-            return self.quantizer.quantize(x, s, z, self.is_learning_scale, pre_relu=True)
+            return self.quantizer.quantize(x, s, z, self.is_learning_scale, **kw)
         self.collect_qparameter(x)
         if not self.is_quantize:
             return x

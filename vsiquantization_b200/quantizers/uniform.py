@@ -73,7 +73,7 @@ class UniformQuantizer(BaseQuantizer):
                          pre_relu=pre_relu)
 
     # -- the plugin entry point ------------------------------------------------------------------------
-    def quantize(self, x, scale, zero_point, is_learning_scale=False, pre_relu=False):
+    def quantize(self, x, scale, zero_point, is_learning_scale=False, pre_relu=False, bias=None):
         """Fake-quantise x (uniform.py:34-56); with ``pre_relu`` quantise relu(x) in the same pass (the fused layer's
         F.relu, modules/fused.py:133, folded into the kernel; gradients include relu's mask).
 
@@ -82,9 +82,11 @@ class UniformQuantizer(BaseQuantizer):
         uses clamp(round(z)), uniform.py:98-102).  The result is autograd-connected to x and to every qparam that
         requires grad."""
         if not x.is_cuda:
-            y = self.quantize(_as_cuda(x), scale, zero_point, is_learning_scale, pre_relu)
+            y = self.quantize(_as_cuda(x), scale, zero_point, is_learning_scale, pre_relu, bias)
             return y.to(x.device)
         ch_axis = self._resolve_axis(x, scale)
+        if bias is not None:
+            return self._quantize_epilogue(x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis)
         scale_learn = isinstance(scale, torch.Tensor) and scale.requires_grad and torch.is_grad_enabled()
         zp_tensor = isinstance(zero_point, torch.Tensor)
         # the reference rounds / clamps a tensor zero-point only on the asymmetric learning path (uniform.py:50-52)
@@ -109,6 +111,30 @@ class UniformQuantizer(BaseQuantizer):
         zp_arg = zero_point if zp_learn else (zero_point.detach() if zp_tensor else zero_point)
         return ops.FakeQuantLearned.apply(x, scale, zp_arg, self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu),
                                           gs_host, gs_dev)
+
+    def _quantize_epilogue(self, x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis):
+        """fq(act(x + bias)) on a channels_last conv output (ops.FakeQuantEpilogue); bias gradient from the same pass."""
+        if not ops.ci_supported(x):
+            raise ValueError("bias fusion needs a channels_last float32 CUDA tensor with C % 4 == 0 and C <= 1024")
+        if self.mask_mode == "funlsq":
+            raise ValueError("mask_mode='funlsq' has no fused-bias form")
+        zp_tensor = isinstance(zero_point, torch.Tensor)
+        zp_round = zp_tensor and is_learning_scale and not self.symmetric and zero_point.is_floating_point()
+        grad_on = torch.is_grad_enabled()
+        scale_learn = isinstance(scale, torch.Tensor) and scale.requires_grad and grad_on
+        zp_learn = zp_round and zero_point.requires_grad and grad_on
+        gs_host, gs_dev = 1.0, None
+        if is_learning_scale and isinstance(scale, torch.Tensor):
+            gs_host = self.calculate_grad_scale(x, scale.numel()) * float(self.grad_boost)
+            cgs = self.calib_grad_scale
+            if isinstance(cgs, torch.Tensor):
+                gs_dev = cgs.detach().to(device=x.device, dtype=torch.float32).sum().reshape(1)
+            else:
+                gs_host *= float(cgs)
+        s_arg = scale if scale_learn else (scale.detach() if isinstance(scale, torch.Tensor) else scale)
+        z_arg = zero_point if zp_learn else (zero_point.detach() if zp_tensor else zero_point)
+        spec = self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu)
+        return ops.FakeQuantEpilogue.apply(x, bias, s_arg, z_arg, spec, gs_host, gs_dev)
 
     def quantize_codes(self, x, scale, zero_point):
         """(fake-quantised tensor, integer codes as int8/uint8) -- the reference keeps codes as floats (uniform.py:54)."""

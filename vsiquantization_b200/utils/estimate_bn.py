@@ -39,7 +39,9 @@ def _make_hook(sync: bool):
         stats = ops.observe(x, ch_axis=1)                      # [C,5]: .., sum x, sum x^2  -- one read of x
         count = float(x.numel() // x.shape[1])
         if sync and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(stats[:, 2:], op=torch.distributed.ReduceOp.SUM)
+            sums = stats[:, 2:].contiguous()  # NCCL wants a dense buffer
+            torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM)
+            stats[:, 2:] = sums
             count *= torch.distributed.get_world_size()
         mean, var_b, _ = ops.bn_moments_finalize(stats, count, module.running_mean_sum, module.running_var_sum)
         if bn.num_batches_tracked is not None:
