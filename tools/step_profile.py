@@ -8,8 +8,12 @@ torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda")
 model, n_fused, _ = yolo_qat.build_model(args, dev)
 model.train()
+if args.channels_last:
+    model.to(memory_format=torch.channels_last)
 opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.9, nesterov=True)
 x = torch.rand(64, 3, 640, 640, device=dev)
+if args.channels_last:
+    x = x.contiguous(memory_format=torch.channels_last)
 def step():
     outs = model(x); loss = sum((o.float() ** 2).mean() for o in outs); loss.backward(); opt.step(); opt.zero_grad(set_to_none=True)
 for _ in range(4): step()

@@ -59,14 +59,34 @@ __device__ __forceinline__ void st4(float* p, const Vec4& r) {
     asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
 }
 
-// workspace header: [0] ticket, [1] tile counter (both left zero), records after kWsHeader
-__device__ __forceinline__ bool next_tile(unsigned int* counter, uint32_t n_tiles, uint32_t* tile) {
-    __shared__ uint32_t s_tile;
+// workspace header: [0] ticket, [1] tile counter (both left zero), records after kWsHeader.
+// Dynamic tile scheduler with a one-tile look-ahead: thread 0 claims tile i+1 (atomicAdd) BEFORE the CTA works on
+// tile i and publishes it afterwards, so the ~1 us round trip of the atomic hides behind a tile's worth of traffic
+// and the CTA pays one __syncthreads per tile.
+struct TileQueue {
+    unsigned int* counter;
+    uint32_t n_tiles;
+    uint32_t ahead;  // thread 0 only: the tile claimed for the next iteration
+    int buf;
+};
+__device__ __forceinline__ void tq_init(TileQueue& q, unsigned int* counter, uint32_t n_tiles, uint32_t* s_tile) {
+    q.counter = counter;
+    q.n_tiles = n_tiles;
+    q.buf = 0;
+    q.ahead = 0;
+    if (threadIdx.x == 0) s_tile[0] = atomicAdd(counter, 1u);
     __syncthreads();
-    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
+}
+// returns the current tile (>= n_tiles: done) and starts claiming the next one
+__device__ __forceinline__ uint32_t tq_current(TileQueue& q, const uint32_t* s_tile) {
+    const uint32_t tile = s_tile[q.buf];
+    if (threadIdx.x == 0 && tile < q.n_tiles) q.ahead = atomicAdd(q.counter, 1u);
+    return tile;
+}
+__device__ __forceinline__ void tq_advance(TileQueue& q, uint32_t* s_tile) {
+    if (threadIdx.x == 0) s_tile[q.buf ^ 1] = q.ahead;
     __syncthreads();
-    *tile = s_tile;
-    return s_tile < n_tiles;
+    q.buf ^= 1;
 }
 
 struct CiOut {
@@ -104,25 +124,42 @@ __device__ __forceinline__ void ci_store(const CiOut& o, const QPDev& qpd, bool 
     }
 }
 
-// combine record entry `idx` over n_rec records (fixed order), one thread per entry
-__device__ __forceinline__ double ci_combine_entry(const double* records, int width, uint32_t n_rec, int idx) {
+// Combine 32 consecutive record entries [base, base+32) over n_rec per-CTA records: warp w sums records w, w+8, ...
+// (each read is one coalesced 256-byte row segment, four independent chains per thread), then the eight slices are
+// added in a fixed order.  Deterministic.  s_part: [kWarps][32] doubles of shared memory.
+__device__ __forceinline__ void ci_combine_chunk(const double* records, int width, uint32_t n_rec, int base,
+                                                 double (*s_part)[32], const CiOut& o, const QPDev& qpd, bool pcq,
+                                                 bool bias, int C) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = base + lane;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    uint32_t r = 0;
-    for (; r + 4 <= n_rec; r += 4) {
-        a0 += __ldcg(records + (size_t)(r + 0) * width + idx);
-        a1 += __ldcg(records + (size_t)(r + 1) * width + idx);
-        a2 += __ldcg(records + (size_t)(r + 2) * width + idx);
-        a3 += __ldcg(records + (size_t)(r + 3) * width + idx);
+    if (idx < width) {
+        uint32_t r = warp;
+        for (; r + 3 * kWarps < n_rec; r += 4 * kWarps) {
+            a0 += __ldcg(records + (size_t)r * width + idx);
+            a1 += __ldcg(records + (size_t)(r + kWarps) * width + idx);
+            a2 += __ldcg(records + (size_t)(r + 2 * kWarps) * width + idx);
+            a3 += __ldcg(records + (size_t)(r + 3 * kWarps) * width + idx);
+        }
+        for (; r < n_rec; r += kWarps) a0 += __ldcg(records + (size_t)r * width + idx);
     }
-    for (; r < n_rec; ++r) a0 += __ldcg(records + (size_t)r * width + idx);
-    return (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    s_part[warp][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (warp == 0 && idx < width) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) v += s_part[w][lane];
+        ci_store(o, qpd, pcq, bias, C, idx, v);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
     ci_finalize_kernel(const void* ws, int width, uint32_t n_rec, CiOut o, QPDev qpd, int pcq, int bias, int C) {
+    __shared__ double s_part[kWarps][32];
     const double* records = (const double*)((const char*)ws + kWsHeader);
-    for (int idx = blockIdx.x * kThreads + threadIdx.x; idx < width; idx += gridDim.x * kThreads)
-        ci_store(o, qpd, pcq, bias, C, idx, ci_combine_entry(records, width, n_rec, idx));
+    for (int base = blockIdx.x * 32; base < width; base += gridDim.x * 32)
+        ci_combine_chunk(records, width, n_rec, base, s_part, o, qpd, pcq, bias, C);
 }
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -143,24 +180,27 @@ __global__ void __launch_bounds__(kThreads, 2)
         all_fast = all_fast && p[e].fast;
         bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
     }
-    uint32_t tile;
-    while (next_tile(counter, geo.n_tiles, &tile)) {
+    __shared__ uint32_t s_tile[2];
+    TileQueue tq;
+    tq_init(tq, counter, geo.n_tiles, s_tile);
+    constexpr int kU = 2 * kCiUnroll, kB = kCiBatches / 2;  // forward: one input, so twice the loads in flight
+    for (uint32_t tile = tq_current(tq, s_tile); tile < geo.n_tiles; tq_advance(tq, s_tile), tile = tq_current(tq, s_tile)) {
         if (!active) continue;
         const int64_t vb = (int64_t)tile * geo.tile_vecs;
 #pragma unroll 1
-        for (int b = 0; b < kCiBatches; ++b) {
-            Vec4 vin[kCiUnroll];
-            bool ok[kCiUnroll];
+        for (int b = 0; b < kB; ++b) {
+            Vec4 vin[kU];
+            bool ok[kU];
 #pragma unroll
-            for (int j = 0; j < kCiUnroll; ++j) {
-                const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
+            for (int j = 0; j < kU; ++j) {
+                const int64_t v = vb + (int64_t)(b * kU + j) * geo.threads + t;
                 ok[j] = v < geo.n_vec;
                 if (ok[j]) vin[j] = ld4(x + v * kCiVec);
             }
 #pragma unroll
-            for (int j = 0; j < kCiUnroll; ++j) {
+            for (int j = 0; j < kU; ++j) {
                 if (!ok[j]) continue;
-                const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
+                const int64_t v = vb + (int64_t)(b * kU + j) * geo.threads + t;
                 Vec4 out;
                 bool bad = !all_fast;
 #pragma unroll
@@ -218,8 +258,10 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) acc_e[e] = acc_b[e] = acc_db[e] = 0.0;
 
-    uint32_t tile;
-    while (next_tile(counter, geo.n_tiles, &tile)) {
+    __shared__ uint32_t s_tile[2];
+    TileQueue tq;
+    tq_init(tq, counter, geo.n_tiles, s_tile);
+    for (uint32_t tile = tq_current(tq, s_tile); tile < geo.n_tiles; tq_advance(tq, s_tile), tile = tq_current(tq, s_tile)) {
         if (!active) continue;
         const int64_t vb = (int64_t)tile * geo.tile_vecs;
         float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials of this tile
@@ -319,6 +361,32 @@ __global__ void __launch_bounds__(kThreads, 2)
         s_acc[t][kCiVec + e] = active ? acc_b[e] : 0.0;
         s_acc[t][2 * kCiVec + e] = active ? acc_db[e] : 0.0;
     }
+    __shared__ double s_pt[2];
+    if (WANT_DS && !PCQ) {  // per-tensor sums: warp shuffle, then the eight warps in order
+        __shared__ double s_w[kWarps][2];
+        double e = 0.0, b = 0.0;
+        if (active) {
+            e = (acc_e[0] + acc_e[1]) + (acc_e[2] + acc_e[3]);
+            b = (acc_b[0] + acc_b[1]) + (acc_b[2] + acc_b[3]);
+        }
+        e = warp_sum(e);
+        b = warp_sum(b);
+        if ((t & 31) == 0) {
+            s_w[t >> 5][0] = e;
+            s_w[t >> 5][1] = b;
+        }
+        __syncthreads();
+        if (t == 0) {
+            double es = 0.0, bs = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                es += s_w[w][0];
+                bs += s_w[w][1];
+            }
+            s_pt[0] = es;
+            s_pt[1] = bs;
+        }
+    }
     __syncthreads();
     const int nq = PCQ ? C : 1;
     const int width = 2 * nq + (BIAS ? C : 0);
@@ -333,9 +401,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                     const int c = idx - which * nq;
                     for (int k = 0; k < reps; ++k) s += s_acc[k * geo.groups + c / kCiVec][which * kCiVec + (c % kCiVec)];
                 } else {
-                    for (int k = 0; k < geo.threads; ++k)
-                        s += (s_acc[k][which * kCiVec + 0] + s_acc[k][which * kCiVec + 1]) +
-                             (s_acc[k][which * kCiVec + 2] + s_acc[k][which * kCiVec + 3]);
+                    s = s_pt[which];  // block-reduced below
                 }
             }
         } else {
@@ -359,8 +425,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     __syncthreads();
     if (!s_last || !use_ticket) return;
     __threadfence();
-    for (int idx = t; idx < width; idx += kThreads)
-        ci_store(o, qpd, PCQ, BIAS, C, idx, ci_combine_entry(records, width, gridDim.x, idx));
+    double(*s_part)[32] = reinterpret_cast<double(*)[32]>(&s_acc[0][0]);  // s_acc is free again
+    for (int base = 0; base < width; base += 32)
+        ci_combine_chunk(records, width, gridDim.x, base, s_part, o, qpd, PCQ, BIAS, C);
 }
 
 static int ci_grid(uint32_t n_tiles) {
@@ -442,7 +509,7 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
     o.gs_host = grad_scale_host;
     o.gs_dev = grad_scale_dev;
     const int width = 2 * (pcq ? (int)channels : 1) + (hb ? (int)channels : 0);
-    const int use_ticket = ((int64_t)grid * width <= 65536) ? 1 : 0;  // else: multi-CTA finalize launch
+    const int use_ticket = width <= 64 ? 1 : 0;  // wider records: one finalize CTA per 32 entries instead
 #define B(P, H, R, D) ci_bwd_kernel<P, H, R, D><<<grid, kThreads, 0, st>>>(x, bias, g, dx, geo, qpd, workspace, o, use_ticket)
 #define B3(P, H, R) { if (want_ds) B(P, H, R, true); else B(P, H, R, false); }
 #define B2(P, H) { if (relu) B3(P, H, true) else B3(P, H, false) }
@@ -451,7 +518,7 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
 #undef B3
 #undef B
     if ((want_ds || hb) && !use_ticket) {
-        const int fgrid = (width + kThreads - 1) / kThreads;
+        const int fgrid = (width + 31) / 32;
         ci_finalize_kernel<<<fgrid, kThreads, 0, st>>>(workspace, width, (uint32_t)grid, o, qpd, pcq ? 1 : 0, hb ? 1 : 0,
                                                       (int)channels);
     }
