@@ -59,36 +59,6 @@ __device__ __forceinline__ void st4(float* p, const Vec4& r) {
     asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
 }
 
-// workspace header: [0] ticket, [1] tile counter (both left zero), records after kWsHeader.
-// Dynamic tile scheduler with a one-tile look-ahead: thread 0 claims tile i+1 (atomicAdd) BEFORE the CTA works on
-// tile i and publishes it afterwards, so the ~1 us round trip of the atomic hides behind a tile's worth of traffic
-// and the CTA pays one __syncthreads per tile.
-struct TileQueue {
-    unsigned int* counter;
-    uint32_t n_tiles;
-    uint32_t ahead;  // thread 0 only: the tile claimed for the next iteration
-    int buf;
-};
-__device__ __forceinline__ void tq_init(TileQueue& q, unsigned int* counter, uint32_t n_tiles, uint32_t* s_tile) {
-    q.counter = counter;
-    q.n_tiles = n_tiles;
-    q.buf = 0;
-    q.ahead = 0;
-    if (threadIdx.x == 0) s_tile[0] = atomicAdd(counter, 1u);
-    __syncthreads();
-}
-// returns the current tile (>= n_tiles: done) and starts claiming the next one
-__device__ __forceinline__ uint32_t tq_current(TileQueue& q, const uint32_t* s_tile) {
-    const uint32_t tile = s_tile[q.buf];
-    if (threadIdx.x == 0 && tile < q.n_tiles) q.ahead = atomicAdd(q.counter, 1u);
-    return tile;
-}
-__device__ __forceinline__ void tq_advance(TileQueue& q, uint32_t* s_tile) {
-    if (threadIdx.x == 0) s_tile[q.buf ^ 1] = q.ahead;
-    __syncthreads();
-    q.buf ^= 1;
-}
-
 struct CiOut {
     void* dscale;
     void* dzp;

@@ -460,6 +460,36 @@ __device__ __forceinline__ bool last_cta_ticket(unsigned int* counter, bool wrot
 constexpr size_t kWsHeader = 256;
 __device__ __forceinline__ double* ws_partials(void* ws) { return (double*)((char*)ws + kWsHeader); }
 
+// workspace header: [0] ticket, [1] tile counter (both left zero), records after kWsHeader.
+// Dynamic tile scheduler with a one-tile look-ahead: thread 0 claims tile i+1 (atomicAdd) BEFORE the CTA works on
+// tile i and publishes it afterwards, so the ~1 us round trip of the atomic hides behind a tile's worth of traffic
+// and the CTA pays one __syncthreads per tile.
+struct TileQueue {
+    unsigned int* counter;
+    uint32_t n_tiles;
+    uint32_t ahead;  // thread 0 only: the tile claimed for the next iteration
+    int buf;
+};
+__device__ __forceinline__ void tq_init(TileQueue& q, unsigned int* counter, uint32_t n_tiles, uint32_t* s_tile) {
+    q.counter = counter;
+    q.n_tiles = n_tiles;
+    q.buf = 0;
+    q.ahead = 0;
+    if (threadIdx.x == 0) s_tile[0] = atomicAdd(counter, 1u);
+    __syncthreads();
+}
+// returns the current tile (>= n_tiles: done) and starts claiming the next one
+__device__ __forceinline__ uint32_t tq_current(TileQueue& q, const uint32_t* s_tile) {
+    const uint32_t tile = s_tile[q.buf];
+    if (threadIdx.x == 0 && tile < q.n_tiles) q.ahead = atomicAdd(q.counter, 1u);
+    return tile;
+}
+__device__ __forceinline__ void tq_advance(TileQueue& q, uint32_t* s_tile) {
+    if (threadIdx.x == 0) s_tile[q.buf ^ 1] = q.ahead;
+    __syncthreads();
+    q.buf ^= 1;
+}
+
 // Record index of (channel c, item i) where a channel owns outer * chunks records: tile index is
 // (o * C + c) * chunks + k.  32-bit math (n_tiles < 2^31); outer == 1 needs no division.
 __device__ __forceinline__ uint32_t record_slot(const Tiles& t, uint32_t outer, uint32_t c, uint32_t i) {

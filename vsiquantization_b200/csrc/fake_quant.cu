@@ -318,6 +318,59 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// Per-tensor LSQ backward (rows == 1): no tile ever needs its own record, so CTAs are persistent, steal 8192-element
+// tiles from the look-ahead queue, carry the two sums in registers (fp32 per tile, fp64 across tiles) and flush ONCE.
+// Keeps the hardware-like balance of the per-tile grid without a block reduction per tile: mid-size activations
+// (2^22..2^26 elements) no longer pay for the reduction epilogue.
+template <int V, int MASK_MODE, bool WANT_DZ, bool RELU>
+__global__ void __launch_bounds__(kThreads)
+    lsq_bwd_pt_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, Tiles tiles,
+                      QPDev qpd, void* ws, LsqOut o) {
+    __shared__ double s_red[kWarps][2];
+    __shared__ uint32_t s_tile[2];
+    const float* const in[2] = {x, g};
+    float* const out[1] = {dx};
+    double* partials = ws_partials(ws);
+    unsigned int* counter = (unsigned int*)ws + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    LsqBwdOp<MASK_MODE, WANT_DZ, RELU> op;
+    op.p = load_qp(qpd, 0);
+    double e_run = 0.0, b_run = 0.0;
+    TileQueue tq;
+    tq_init(tq, counter, tiles.n_tiles, s_tile);
+    for (uint32_t t = tq_current(tq, s_tile); t < tiles.n_tiles; tq_advance(tq, s_tile), t = tq_current(tq, s_tile)) {
+        const TileCursor<kThreads> c = tile_at<kThreads>(tiles, t);
+        op.e_acc = 0.0f;
+        op.b_acc = 0.0f;
+        span_apply<kThreads, V, 2, 1>(in, out, c.offset, c.len, op);
+        e_run += (double)op.e_acc;
+        if (WANT_DZ) b_run += (double)op.b_acc;
+    }
+    const double e = warp_sum(e_run);
+    const double b = WANT_DZ ? warp_sum(b_run) : 0.0;
+    if (lane == 0) {
+        s_red[warp][0] = e;
+        s_red[warp][1] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double es = 0.0, bs = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            es += s_red[w][0];
+            bs += s_red[w][1];
+        }
+        partials[2 * (size_t)blockIdx.x] = es;
+        partials[2 * (size_t)blockIdx.x + 1] = bs;
+    }
+    if (!last_cta_ticket((unsigned int*)ws, threadIdx.x == 0)) return;
+    if (threadIdx.x == 0) *counter = 0;  // every other CTA has left its tile loop
+    Tiles rec = tiles;  // one record per CTA
+    rec.channels = 1;
+    rec.chunks = gridDim.x;
+    lsq_combine_cta(partials, rec, 1, 0, o, qpd, s_red);
+}
+
 // MODE 0: thread per channel, 1: warp per channel, 2: CTA per channel
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
@@ -490,6 +543,7 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
     const bool vec8 = aligned32(x) && aligned32(g) && aligned32(dx);
     Tiles tiles;
     LsqOut lo;
+    const bool per_tensor_dyn = layout->outer == 1 && layout->channels == 1 && !warp_group;
     lo.dscale = dscale;
     lo.dzp = dzp;
     lo.ds_f64 = dscale_dtype == VSIQ_F64;
@@ -530,6 +584,22 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
                                                                                           layout->outer);      \
             }                                                                                                  \
         }                                                                                                      \
+    }
+    if (per_tensor_dyn) {
+        if (!make_tiles<kThreads>(1, 1, layout->inner, &tiles)) return VSIQ_ERR_INVALID_ARG;
+        DeviceProps dp;
+        if (int e = get_device_props(&dp)) return e;
+        const uint32_t cap = (uint32_t)dp.sm_count * 3u;
+        const int grid = (int)(tiles.n_tiles < cap ? tiles.n_tiles : cap);
+        const bool relu = qp->pre_op == VSIQ_PRE_RELU;
+#define PT(V, M, Z, R) lsq_bwd_pt_kernel<V, M, Z, R><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd, workspace, lo)
+#define PT2(V, M, Z) { if (relu) PT(V, M, Z, true); else PT(V, M, Z, false); }
+#define PT1(V) { if (mask_mode == VSIQ_MASK_FUNLSQ) PT(V, VSIQ_MASK_FUNLSQ, false, false); else if (dzp) PT2(V, VSIQ_MASK_ROUNDED, true) else PT2(V, VSIQ_MASK_ROUNDED, false) }
+        if (vec8) PT1(8) else PT1(1)
+#undef PT1
+#undef PT2
+#undef PT
+        return (int)cudaGetLastError();
     }
 #define CALL(G, V)                                   \
     {                                                \

@@ -236,6 +236,39 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// Per-tensor observer (rows == 1): persistent CTAs on the look-ahead tile queue, statistics carried in registers,
+// one record per CTA (see lsq_bwd_pt_kernel).
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+    observe_pt_kernel(const float* __restrict__ x, Tiles tiles, void* ws, ObserveOut o) {
+    __shared__ double s_red[kWarps][kPartialWidth];
+    __shared__ uint32_t s_tile[2];
+    const float* const in[1] = {x};
+    float* const out[1] = {nullptr};
+    double* partials = ws_partials(ws);
+    unsigned int* counter = (unsigned int*)ws + 1;
+    StatsOp op;
+    op.reset();
+    TileQueue tq;
+    tq_init(tq, counter, tiles.n_tiles, s_tile);
+    for (uint32_t t = tq_current(tq, s_tile); t < tiles.n_tiles; tq_advance(tq, s_tile), t = tq_current(tq, s_tile)) {
+        const TileCursor<kThreads> c = tile_at<kThreads>(tiles, t);
+        span_apply<kThreads, V, 1, 0>(in, out, c.offset, c.len, op);
+    }
+    double rec[kPartialWidth];
+    stats_group_reduce<kThreads>(op, rec, s_red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < kPartialWidth; ++k) partials[(size_t)blockIdx.x * kPartialWidth + k] = rec[k];
+    }
+    if (!last_cta_ticket((unsigned int*)ws, threadIdx.x == 0)) return;
+    if (threadIdx.x == 0) *counter = 0;
+    Tiles recs = tiles;
+    recs.channels = 1;
+    recs.chunks = gridDim.x;
+    observe_combine<kThreads>(partials, recs, 1, 0, o, s_red);
+}
+
 // MODE 0: thread per channel, 1: warp per channel, 2: CTA per channel
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
@@ -335,11 +368,28 @@ extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* s
     Tiles tiles;
     ObserveOut oo;
     oo.stats = stats;
+    const bool per_tensor_dyn = layout->outer == 1 && layout->channels == 1 && !warp_group;
     oo.state = state;
     oo.bits = bits;
     oo.symmetric = symmetric;
     oo.eps = eps;
     oo.count = (double)layout->outer * (double)layout->inner;
+    if (per_tensor_dyn) {
+        oo.bits = bits;
+        oo.symmetric = symmetric;
+        oo.eps = eps;
+        oo.count = (double)layout->inner;
+        if (!make_tiles<kThreads>(1, 1, layout->inner, &tiles)) return VSIQ_ERR_INVALID_ARG;
+        DeviceProps dp;
+        if (int e = get_device_props(&dp)) return e;
+        const uint32_t cap = (uint32_t)dp.sm_count * 4u;
+        const int grid = (int)(tiles.n_tiles < cap ? tiles.n_tiles : cap);
+        if (vec8)
+            observe_pt_kernel<8><<<grid, kThreads, 0, st>>>(x, tiles, workspace, oo);
+        else
+            observe_pt_kernel<1><<<grid, kThreads, 0, st>>>(x, tiles, workspace, oo);
+        return (int)cudaGetLastError();
+    }
 #define CALL(G, V)                                                                                              \
     {                                                                                                           \
         const int mult = reduce_tile_mult<G>(layout->outer, layout->channels, layout->inner);                  \
