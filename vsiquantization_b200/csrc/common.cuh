@@ -490,6 +490,40 @@ __device__ __forceinline__ void tq_advance(TileQueue& q, uint32_t* s_tile) {
     q.buf ^= 1;
 }
 
+// Per-channel reductions over NCHW-like [outer, C, inner] tensors: "channel items".  All (row n, chunk) units of channel
+// c are dealt round-robin to k CTAs, so a CTA only ever sees ONE channel: qparams are loaded once, the sums stay in
+// registers across units and are flushed once (k records per channel) instead of once per tile.  GROUP = 256: the CTA
+// cooperates on each unit (rows >= 2048 elements, 16384-element chunks); GROUP = 32: every warp takes its own units
+// (short rows, one unit per row).
+struct PcGeom {
+    int64_t outer, channels, inner;
+    uint32_t chunks;  // units per row
+    uint32_t units;   // outer * chunks: units per channel
+    uint32_t k;       // CTAs per channel
+    int chunk;        // elements per unit
+};
+inline bool make_pc_geom(int64_t outer, int64_t channels, int64_t inner, bool warp_group, int sm_count, PcGeom* g) {
+    if (outer <= 0 || channels <= 1 || inner <= 0) return false;
+    g->outer = outer;
+    g->channels = channels;
+    g->inner = inner;
+    const int64_t chunk = warp_group ? inner : 16384;
+    const int64_t chunks = (inner + chunk - 1) / chunk;
+    const int64_t units = outer * chunks;
+    if (units >= (int64_t(1) << 31) || chunk >= (int64_t(1) << 31)) return false;
+    g->chunk = (int)chunk;
+    g->chunks = (uint32_t)chunks;
+    g->units = (uint32_t)units;
+    const int64_t per_cta = warp_group ? kWarps : 1;  // units a CTA works on concurrently
+    int64_t k = ((int64_t)sm_count * 8 + channels - 1) / channels;
+    const int64_t kmax = (units + per_cta - 1) / per_cta;
+    if (k > kmax) k = kmax;
+    if (k < 1) k = 1;
+    g->k = (uint32_t)k;
+    if (channels * k >= (int64_t(1) << 31)) return false;
+    return channels * k >= (int64_t)sm_count * 2;  // else too few CTAs: the per-tile schedule is the better one
+}
+
 // Record index of (channel c, item i) where a channel owns outer * chunks records: tile index is
 // (o * C + c) * chunks + k.  32-bit math (n_tiles < 2^31); outer == 1 needs no division.
 __device__ __forceinline__ uint32_t record_slot(const Tiles& t, uint32_t outer, uint32_t c, uint32_t i) {

@@ -371,6 +371,71 @@ __global__ void __launch_bounds__(kThreads)
     lsq_combine_cta(partials, rec, 1, 0, o, qpd, s_red);
 }
 
+// Per-channel LSQ backward on [outer, C, inner] with the channel-item schedule (see PcGeom): one flush per CTA.
+template <int GROUP, int V, bool WANT_DZ, bool RELU>
+__global__ void __launch_bounds__(kThreads)
+    lsq_bwd_pc_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, PcGeom geo,
+                      QPDev qpd, void* ws, LsqOut o, int use_ticket) {
+    __shared__ double s_red[kWarps][2];
+    const float* const in[2] = {x, g};
+    float* const out[1] = {dx};
+    double* partials = ws_partials(ws);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t C = (uint32_t)geo.channels;
+    const uint32_t c = blockIdx.x % C, j = blockIdx.x / C;
+    LsqBwdOp<VSIQ_MASK_ROUNDED, WANT_DZ, RELU> op;
+    op.p = load_qp(qpd, c);
+    double e_run = 0.0, b_run = 0.0;
+    const uint32_t first = GROUP == 32 ? j + (uint32_t)warp * geo.k : j;
+    const uint32_t step = GROUP == 32 ? geo.k * kWarps : geo.k;
+    for (uint32_t u = first; u < geo.units; u += step) {
+        const uint32_t n = u / geo.chunks, ch = u - n * geo.chunks;
+        const int64_t start = (int64_t)ch * geo.chunk;
+        const int64_t rem = geo.inner - start;
+        const int len = rem < geo.chunk ? (int)rem : geo.chunk;
+        const int64_t off = ((int64_t)n * C + c) * geo.inner + start;
+        op.e_acc = 0.0f;
+        op.b_acc = 0.0f;
+        span_apply<GROUP, V, 2, 1>(in, out, off, len, op);
+        e_run += (double)op.e_acc;
+        if (WANT_DZ) b_run += (double)op.b_acc;
+    }
+    const double e = warp_sum(e_run);
+    const double b = WANT_DZ ? warp_sum(b_run) : 0.0;
+    if (lane == 0) {
+        s_red[warp][0] = e;
+        s_red[warp][1] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double es = 0.0, bs = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            es += s_red[w][0];
+            bs += s_red[w][1];
+        }
+        const size_t slot = (size_t)c * geo.k + j;
+        partials[2 * slot] = es;
+        partials[2 * slot + 1] = bs;
+    }
+    if (!use_ticket) return;
+    if (!last_cta_ticket((unsigned int*)ws, threadIdx.x == 0)) return;
+    Tiles rec;  // k records per channel, contiguous
+    rec.rows = geo.channels;
+    rec.channels = geo.channels;
+    rec.inner = 0;
+    rec.chunks = geo.k;
+    rec.n_tiles = C * geo.k;
+    rec.tile = 0;
+    if (geo.k <= kThreadCombineMaxItems) {
+        for (int64_t cc = threadIdx.x; cc < geo.channels; cc += kThreads) lsq_combine_thread(partials, rec, 1, cc, o, qpd);
+    } else if (geo.channels < kWarps) {
+        for (int64_t cc = 0; cc < geo.channels; ++cc) lsq_combine_cta(partials, rec, 1, cc, o, qpd, s_red);
+    } else {
+        for (int64_t cc = warp; cc < geo.channels; cc += kWarps) lsq_combine_warp(partials, rec, 1, cc, o, qpd);
+    }
+}
+
 // MODE 0: thread per channel, 1: warp per channel, 2: CTA per channel
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
@@ -584,6 +649,40 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
                                                                                           layout->outer);      \
             }                                                                                                  \
         }                                                                                                      \
+    }
+    PcGeom pc;
+    DeviceProps dprops;
+    if (int e = get_device_props(&dprops)) return e;
+    if (mask_mode == VSIQ_MASK_ROUNDED && layout->channels > 1 &&
+        make_pc_geom(layout->outer, layout->channels, layout->inner, warp_group, dprops.sm_count, &pc) &&
+        (size_t)pc.channels * pc.k * 2 * sizeof(double) + kWsHeader <= workspace_bytes) {
+        const int grid = (int)(pc.channels * pc.k);
+        const int use_ticket = (uint32_t)grid <= kTicketMaxRecords ? 1 : 0;
+        const bool relu = qp->pre_op == VSIQ_PRE_RELU;
+#define PC(G, V, Z, R) lsq_bwd_pc_kernel<G, V, Z, R><<<grid, kThreads, 0, st>>>(x, g, dx, pc, qpd, workspace, lo, use_ticket)
+#define PC2(G, V, Z) { if (relu) PC(G, V, Z, true); else PC(G, V, Z, false); }
+#define PC1(G, V) { if (dzp) PC2(G, V, true) else PC2(G, V, false) }
+        if (warp_group) { if (vec8) PC1(32, 8) else PC1(32, 1) } else { if (vec8) PC1(kThreads, 8) else PC1(kThreads, 1) }
+#undef PC1
+#undef PC2
+#undef PC
+        if (!use_ticket) {
+            Tiles rec;
+            rec.rows = pc.channels;
+            rec.channels = pc.channels;
+            rec.inner = 0;
+            rec.chunks = pc.k;
+            rec.n_tiles = (uint32_t)grid;
+            rec.tile = 0;
+            if (pc.k <= kThreadCombineMaxItems) {
+                int64_t fg = (pc.channels + kThreads - 1) / kThreads;
+                lsq_finalize_kernel<0><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(rec, qpd, workspace, lo, 1);
+            } else {
+                int64_t fg = (pc.channels + kWarps - 1) / kWarps;
+                lsq_finalize_kernel<1><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(rec, qpd, workspace, lo, 1);
+            }
+        }
+        return (int)cudaGetLastError();
     }
     if (per_tensor_dyn) {
         if (!make_tiles<kThreads>(1, 1, layout->inner, &tiles)) return VSIQ_ERR_INVALID_ARG;

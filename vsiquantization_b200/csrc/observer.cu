@@ -269,6 +269,54 @@ __global__ void __launch_bounds__(kThreads)
     observe_combine<kThreads>(partials, recs, 1, 0, o, s_red);
 }
 
+// Per-channel observer on [outer, C, inner] with the channel-item schedule (PcGeom): one record per CTA.  This is the
+// kernel behind BN re-estimation's per-batch moments (utils/estimate_bn.py:82) and per-channel calibration.
+template <int GROUP, int V>
+__global__ void __launch_bounds__(kThreads)
+    observe_pc_kernel(const float* __restrict__ x, PcGeom geo, void* ws, ObserveOut o, int use_ticket) {
+    __shared__ double s_red[kWarps][kPartialWidth];
+    const float* const in[1] = {x};
+    float* const out[1] = {nullptr};
+    double* partials = ws_partials(ws);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t C = (uint32_t)geo.channels;
+    const uint32_t c = blockIdx.x % C, j = blockIdx.x / C;
+    StatsOp op;
+    op.reset();
+    const uint32_t first = GROUP == 32 ? j + (uint32_t)warp * geo.k : j;
+    const uint32_t step = GROUP == 32 ? geo.k * kWarps : geo.k;
+    for (uint32_t u = first; u < geo.units; u += step) {
+        const uint32_t n = u / geo.chunks, ch = u - n * geo.chunks;
+        const int64_t start = (int64_t)ch * geo.chunk;
+        const int64_t rem = geo.inner - start;
+        const int len = rem < geo.chunk ? (int)rem : geo.chunk;
+        span_apply<GROUP, V, 1, 0>(in, out, ((int64_t)n * C + c) * geo.inner + start, len, op);
+    }
+    double rec[kPartialWidth];
+    stats_group_reduce<kThreads>(op, rec, s_red);  // whole CTA -> one record (warps hold different units of channel c)
+    if (threadIdx.x == 0) {
+        const size_t slot = (size_t)c * geo.k + j;
+#pragma unroll
+        for (int q = 0; q < kPartialWidth; ++q) partials[slot * kPartialWidth + q] = rec[q];
+    }
+    if (!use_ticket) return;
+    if (!last_cta_ticket((unsigned int*)ws, threadIdx.x == 0)) return;
+    Tiles recs;
+    recs.rows = geo.channels;
+    recs.channels = geo.channels;
+    recs.inner = 0;
+    recs.chunks = geo.k;
+    recs.n_tiles = C * geo.k;
+    recs.tile = 0;
+    if (geo.k <= kThreadCombineMaxItems) {
+        for (int64_t cc = threadIdx.x; cc < geo.channels; cc += kThreads) observe_combine<1>(partials, recs, 1, cc, o, s_red);
+    } else if (geo.channels < kWarps) {
+        for (int64_t cc = 0; cc < geo.channels; ++cc) observe_combine<kThreads>(partials, recs, 1, cc, o, s_red);
+    } else {
+        for (int64_t cc = warp; cc < geo.channels; cc += kWarps) observe_combine<32>(partials, recs, 1, cc, o, s_red);
+    }
+}
+
 // MODE 0: thread per channel, 1: warp per channel, 2: CTA per channel
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
@@ -374,6 +422,43 @@ extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* s
     oo.symmetric = symmetric;
     oo.eps = eps;
     oo.count = (double)layout->outer * (double)layout->inner;
+    oo.bits = bits;
+    oo.symmetric = symmetric;
+    oo.eps = eps;
+    oo.count = (double)layout->outer * (double)layout->inner;
+    PcGeom pc;
+    DeviceProps dprops;
+    if (int e = get_device_props(&dprops)) return e;
+    if (layout->channels > 1 &&
+        make_pc_geom(layout->outer, layout->channels, layout->inner, warp_group, dprops.sm_count, &pc) &&
+        (size_t)pc.channels * pc.k * kPartialWidth * sizeof(double) + kWsHeader <= workspace_bytes) {
+        const int grid = (int)(pc.channels * pc.k);
+        const int use_ticket = (uint32_t)grid <= kTicketMaxRecords ? 1 : 0;
+        if (warp_group) {
+            if (vec8) observe_pc_kernel<32, 8><<<grid, kThreads, 0, st>>>(x, pc, workspace, oo, use_ticket);
+            else observe_pc_kernel<32, 1><<<grid, kThreads, 0, st>>>(x, pc, workspace, oo, use_ticket);
+        } else {
+            if (vec8) observe_pc_kernel<kThreads, 8><<<grid, kThreads, 0, st>>>(x, pc, workspace, oo, use_ticket);
+            else observe_pc_kernel<kThreads, 1><<<grid, kThreads, 0, st>>>(x, pc, workspace, oo, use_ticket);
+        }
+        if (!use_ticket) {
+            Tiles recs;
+            recs.rows = pc.channels;
+            recs.channels = pc.channels;
+            recs.inner = 0;
+            recs.chunks = pc.k;
+            recs.n_tiles = (uint32_t)grid;
+            recs.tile = 0;
+            if (pc.k <= kThreadCombineMaxItems) {
+                int64_t fg = (pc.channels + kThreads - 1) / kThreads;
+                observe_finalize_kernel<0><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(recs, 1, workspace, oo);
+            } else {
+                int64_t fg = (pc.channels + kWarps - 1) / kWarps;
+                observe_finalize_kernel<1><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(recs, 1, workspace, oo);
+            }
+        }
+        return (int)cudaGetLastError();
+    }
     if (per_tensor_dyn) {
         oo.bits = bits;
         oo.symmetric = symmetric;
