@@ -211,6 +211,8 @@ int vsiq_fake_quant_fwd_bwd(const float *x, const float *g, float *y, float *dx,
  *   backward: dx (act mask included), dscale / dzp (qp_channels entries; dscale NULL = plain STE),
  *             dbias[c] = sum_rows dx (NULL allowed) -- the fused layer's conv-bias gradient (modules/fused.py:124-130;
  *             ATen computes it with a separate full-tensor reduction) comes out of the same pass.
+ *             g_row_pitch: elements between consecutive rows of g (0 or `channels` = dense; larger when g is a channel
+ *             slice of a wider NHWC tensor, which is what the backward of torch.cat produces; multiple of 4).
  * Same arithmetic, bit-identical values, as vsiq_fake_quant_fwd / vsiq_lsq_bwd on the NCHW-permuted tensor. */
 size_t vsiq_ci_workspace_bytes(int64_t rows, int64_t channels);
 int vsiq_ci_fake_quant_fwd(const float *x, const float *bias, float *y, int64_t rows, int64_t channels,
@@ -218,8 +220,8 @@ int vsiq_ci_fake_quant_fwd(const float *x, const float *bias, float *y, int64_t 
                            vsiq_stream_t stream);
 int vsiq_ci_lsq_bwd(const float *x, const float *bias, const float *g, float *dx, void *dscale, int dscale_dtype,
                     void *dzp, int dzp_dtype, float *dbias, int64_t rows, int64_t channels, const vsiq_qparams *qp,
-                    int64_t qp_channels, double grad_scale_host, const float *grad_scale_dev, void *workspace,
-                    size_t workspace_bytes, vsiq_stream_t stream);
+                    int64_t qp_channels, double grad_scale_host, const float *grad_scale_dev, int64_t g_row_pitch,
+                    void *workspace, size_t workspace_bytes, vsiq_stream_t stream);
 
 /* ---- self-test ---------------------------------------------------------------------------
  * The kernels divide by the (tile-uniform) scale through a hoisted correctly-rounded reciprocal and

@@ -463,3 +463,20 @@ def test_channels_inner_special_values_and_determinism(ops):
     c = ops.ci_backward(x, b, g, s, z, spec, 0.01, None, True, True, True)
     for u, w in zip(a, c):  # dynamic tile scheduling, yet bit-reproducible: fixed-order combination
         assert torch.equal(torch.nan_to_num(u), torch.nan_to_num(w))
+
+
+def test_channels_inner_strided_grad_output(ops):
+    """grad_output that is a channel slice of a wider NHWC tensor (what torch.cat's backward hands out) is read in place."""
+    torch.manual_seed(2)
+    x = torch.randn(3, 32, 11, 9, device="cuda").contiguous(memory_format=torch.channels_last)
+    wide = torch.randn(3, 96, 11, 9, device="cuda").contiguous(memory_format=torch.channels_last)
+    g_view = wide[:, 32:64]
+    assert g_view.stride() != x.stride() and g_view.stride(1) == 1
+    b = torch.randn(32, device="cuda")
+    s = torch.full((1, 32, 1, 1), 0.02, device="cuda")
+    z = torch.full((1, 32, 1, 1), 3.3, device="cuda")
+    spec = ops.QSpec(0, 255, ch_axis=1, zp_learned=True, pre_relu=True)
+    a = ops.ci_backward(x, b, g_view, s, z, spec, 0.01, None, True, True, True)
+    c = ops.ci_backward(x, b, g_view.contiguous(memory_format=torch.channels_last), s, z, spec, 0.01, None, True, True, True)
+    for u, w in zip(a, c):
+        assert torch.equal(u, w)

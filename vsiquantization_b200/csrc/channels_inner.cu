@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
 __global__ void __launch_bounds__(kThreads, 2)
     ci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ g,
-                  float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket) {
+                  float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket, int64_t g_pitch) {
     __shared__ double s_acc[kThreads][3 * kCiVec];  // per thread: e[4], b[4], db[4]
     unsigned int* counter = (unsigned int*)ws + 1;
     double* records = ws_partials(ws);
@@ -227,6 +227,11 @@ __global__ void __launch_bounds__(kThreads, 2)
     double acc_e[kCiVec], acc_b[kCiVec], acc_db[kCiVec];
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) acc_e[e] = acc_b[e] = acc_db[e] = 0.0;
+    // grad_output may be a channel slice of a wider NHWC tensor (the backward of torch.cat hands out such views): row r
+    // of g starts at g + r * g_pitch.  Thread t's vectors sit in rows tile*tile_rows + step*rows_per_step + t/G.
+    const int rows_per_step = geo.threads / geo.groups;
+    const int64_t tile_rows = geo.tile_vecs / geo.groups;
+    const int t_row = t / geo.groups;
 
     __shared__ uint32_t s_tile[2];
     TileQueue tq;
@@ -247,7 +252,8 @@ __global__ void __launch_bounds__(kThreads, 2)
                 ok[j] = v < geo.n_vec;
                 if (ok[j]) {
                     vx[j] = ld4(x + v * kCiVec);
-                    vg[j] = ld4(g + v * kCiVec);
+                    const int64_t row = (int64_t)tile * tile_rows + (int64_t)(b * kCiUnroll + j) * rows_per_step + t_row;
+                    vg[j] = ld4(g + row * g_pitch + c0);
                 }
             }
 #pragma unroll
@@ -445,12 +451,14 @@ extern "C" int vsiq_ci_fake_quant_fwd(const float* x, const float* bias, float* 
 extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g, float* dx, void* dscale,
                                int dscale_dtype, void* dzp, int dzp_dtype, float* dbias, int64_t rows, int64_t channels,
                                const vsiq_qparams* qp, int64_t qp_channels, double grad_scale_host,
-                               const float* grad_scale_dev, void* workspace, size_t workspace_bytes,
-                               vsiq_stream_t stream) {
+                               const float* grad_scale_dev, int64_t g_row_pitch, void* workspace,
+                               size_t workspace_bytes, vsiq_stream_t stream) {
     QPDev qpd;
     if (int e = fill_qp(qp, &qpd)) return e;
     if (qp_channels != 1 && qp_channels != channels) return VSIQ_ERR_INVALID_ARG;
     if (dzp && !dscale) return VSIQ_ERR_INVALID_ARG;
+    if (g_row_pitch == 0) g_row_pitch = channels;
+    if (g_row_pitch < channels || (g_row_pitch & 3)) return VSIQ_ERR_UNSUPPORTED;
     if (dbias && !bias) return VSIQ_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (rows == 0) {
@@ -480,7 +488,8 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
     o.gs_dev = grad_scale_dev;
     const int width = 2 * (pcq ? (int)channels : 1) + (hb ? (int)channels : 0);
     const int use_ticket = width <= 64 ? 1 : 0;  // wider records: one finalize CTA per 32 entries instead
-#define B(P, H, R, D) ci_bwd_kernel<P, H, R, D><<<grid, kThreads, 0, st>>>(x, bias, g, dx, geo, qpd, workspace, o, use_ticket)
+#define B(P, H, R, D) \
+    ci_bwd_kernel<P, H, R, D><<<grid, kThreads, 0, st>>>(x, bias, g, dx, geo, qpd, workspace, o, use_ticket, g_row_pitch)
 #define B3(P, H, R) { if (want_ds) B(P, H, R, true); else B(P, H, R, false); }
 #define B2(P, H) { if (relu) B3(P, H, true) else B3(P, H, false) }
     if (pcq) { if (hb) B2(true, true) else B2(true, false) } else { if (hb) B2(false, true) else B2(false, false) }

@@ -320,9 +320,16 @@ def ci_backward(x: torch.Tensor, bias: Optional[torch.Tensor], g: torch.Tensor, 
     """dx, dscale, dzero_point, dbias of ci_forward in one pass (vsiq_ci_lsq_bwd); dscale None = plain STE."""
     if not ci_supported(x):
         raise ValueError("ci_backward needs a float32 CUDA channels_last tensor with C % 4 == 0 and C <= 1024")
-    g = _match_layout(g, x, "grad_output")
     N, C, H, W = x.shape
     rows = N * H * W
+    # grad_output as a channel slice of a wider NHWC tensor (torch.cat's backward): read it in place through a row pitch
+    pitch = 0
+    if (g.is_cuda and g.dtype == torch.float32 and g.shape == x.shape and g.stride() != x.stride() and g.stride(1) == 1
+            and g.stride(3) % 4 == 0 and g.stride(3) >= C and g.stride(2) == W * g.stride(3)
+            and g.stride(0) == H * W * g.stride(3) and g.data_ptr() % 16 == 0):
+        pitch = g.stride(3)
+    else:
+        g = _match_layout(g, x, "grad_output")
     keep: list = []
     with torch.cuda.device(x.device):
         qp, qpc = _ci_qparams(spec, scale, zero_point, C, x.device, keep)
@@ -342,7 +349,7 @@ def ci_backward(x: torch.Tensor, bias: Optional[torch.Tensor], g: torch.Tensor, 
                                   ds.data_ptr() if ds is not None else None, _dtype_code(ds) if ds is not None else F32,
                                   dz.data_ptr() if dz is not None else None, _dtype_code(dz) if dz is not None else F32,
                                   db.data_ptr() if db is not None else None, rows, C, ctypes.byref(qp), qpc,
-                                  float(grad_scale), gsd.data_ptr() if gsd is not None else None, ws.data_ptr(),
+                                  float(grad_scale), gsd.data_ptr() if gsd is not None else None, pitch, ws.data_ptr(),
                                   ws.numel(), _stream_ptr()), "vsiq_ci_lsq_bwd")
         _count_launch()
     return dx, ds, dz, db
