@@ -16,11 +16,25 @@ g = torch.randn(n, device="cuda")
 s_t = torch.tensor(3.0 / 127, dtype=torch.float64, device="cuda")
 spec = ops.QSpec(-128, 127)
 gs = ops.lsq_grad_scale(127, n)
+# channels_last activation [64, 32, 320, 320] (209.7 M elements) for the channel-innermost kernels
+B = max(1, n // (32 * 320 * 320))
+xa = torch.randn(B, 32, 320, 320, device="cuda").contiguous(memory_format=torch.channels_last)
+ga = torch.randn(B, 32, 320, 320, device="cuda").contiguous(memory_format=torch.channels_last)
+sc = torch.full((1, 32, 1, 1), 0.02, device="cuda")
+zc = torch.full((1, 32, 1, 1), 3.3, device="cuda")
+bias = torch.randn(32, device="cuda")
+pc = ops.QSpec(0, 255, ch_axis=1, zp_learned=True, pre_relu=True)
+xn = xa.contiguous()
+gn = ga.contiguous()
 for _ in range(reps):
     ops.fake_quant_forward(x, 3.0 / 127, 0, spec)
     ops.fake_quant_backward_ste(x, g, 3.0 / 127, 0, spec)
     ops.lsq_backward(x, g, s_t, 0, spec, gs, ds_dtype=torch.float64)
     ops.fake_quant_forward_backward(x, g, 3.0 / 127, 0, spec)
     ops.observe(x)
+    ops.ci_forward(xa, bias, sc, zc, pc)
+    ops.ci_backward(xa, bias, ga, sc, zc, pc, 1e-3, None, True, True, True)
+    ops.lsq_backward(xn, gn, sc, zc, pc, 1e-3, want_dz=True)
+    ops.observe(xn, ch_axis=1)
 torch.cuda.synchronize()
 print("ok")
