@@ -419,7 +419,28 @@ def main():
     gen_bn_fold(gen)
     gen_bn_reestimate(gen)
     gen_tiny_e2e(gen)
+    gen_compute_scale(torch.Generator().manual_seed(4321))
+
+
+def gen_compute_scale(gen):
+    """compute_scale (utils/estimate_bn.py:104-139): per-channel calib_grad_scale from BN affine params and weight moments."""
+    from utils.estimate_bn import compute_scale
+    cv = torch.nn.Conv2d(4, 6, 3, 1, 1, bias=False)
+    bn = torch.nn.BatchNorm2d(6, eps=0.001)
+    with torch.no_grad():
+        cv.weight.copy_(torch.randn(cv.weight.shape, generator=gen) * 0.3)
+        bn.weight.copy_(torch.rand(6, generator=gen) + 0.5)
+        bn.bias.copy_(torch.randn(6, generator=gen) * 0.2)
+    layer = ConvBnReLU(cv, bn, torch.nn.ReLU(), "MinMaxObserver", "UniformQuantizer", "MinMaxObserver",
+                       "UniformQuantizer", True, True, False, 8, 8)
+    model = torch.nn.Sequential(layer)
+    compute_scale(model, None)
+    save("compute_scale", W=cv.weight.detach().numpy(), gamma=bn.weight.detach().numpy(), beta=bn.bias.detach().numpy(),
+         calib_grad_scale=layer.activation_quantizer.quantizer.calib_grad_scale.numpy())
 
 
 if __name__ == "__main__":
-    main()
+    if os.environ.get("VSIQ_GOLDEN_ONLY") == "compute_scale":
+        gen_compute_scale(torch.Generator().manual_seed(4321))
+    else:
+        main()

@@ -141,3 +141,18 @@ def test_dropin_maps_reference_module_paths():
     assert sorted(reg) == ["LSQObserver", "LSQQuantizer", "MinMaxObserver", "UniformQuantizer"]
     assert set(dropin._TIER2) >= {"modules.fuse", "modules.fuse_config", "utils.quantize_manager", "utils.estimate_bn",
                                   "quantizers.uniform", "observers.minmax"}
+
+
+def test_dropin_install_modules_in_a_fresh_interpreter():
+    """Tier 2: after install_modules() the reference's import lines resolve to this package."""
+    import subprocess
+    import sys
+    code = ("import vsiquantization_b200.dropin as d; d.install_modules();"
+            "from modules.fuse import fuse_modules_unified; from modules.fuse_config import load_fuse_config_from_yaml, FuseConfig;"
+            "from utils.quantize_manager import calibrate_qat_model, activate_learning_qparam, activate_quantizer;"
+            "from utils.estimate_bn import reestimate_BN_stats, compute_scale; from utils.registry import CLASS_REGISTRY;"
+            "from quantizers.quantization_manager import QuantizationManager;"
+            "print(fuse_modules_unified.__module__, sorted(CLASS_REGISTRY))")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-500:]
+    assert "vsiquantization_b200.modules.fuse" in out.stdout and "LSQQuantizer" in out.stdout

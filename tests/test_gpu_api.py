@@ -476,3 +476,63 @@ def test_fused_layer_channels_last_bias_epilogue():
     gs = (127 * y.numel()) ** -0.5
     mass = gs * float((2 * y).abs().sum()) * 0.5
     assert abs(float(res[0][4]) - float(res[1][4])) <= 0.02 * mass
+
+
+def test_compute_scale_matches_reference_golden():
+    """utils.estimate_bn.compute_scale: per-channel calib_grad_scale (estimate_bn.py:104-139)."""
+    from vsiquantization_b200.modules.fused import ConvBnReLU
+    from vsiquantization_b200.utils.estimate_bn import compute_scale
+    G = load_golden("compute_scale")
+    cv = torch.nn.Conv2d(4, 6, 3, 1, 1, bias=False)
+    bn = torch.nn.BatchNorm2d(6, eps=0.001)
+    with torch.no_grad():
+        cv.weight.copy_(torch.as_tensor(G["W"]))
+        bn.weight.copy_(torch.as_tensor(G["gamma"]))
+        bn.bias.copy_(torch.as_tensor(G["beta"]))
+    layer = ConvBnReLU(cv, bn, torch.nn.ReLU(), "MinMaxObserver", "UniformQuantizer", "MinMaxObserver", "UniformQuantizer",
+                       True, True, False, 8, 8).cuda()
+    compute_scale(torch.nn.Sequential(layer), None)
+    cgs = layer.activation_quantizer.quantizer.calib_grad_scale
+    np.testing.assert_allclose(cgs.cpu().numpy(), G["calib_grad_scale"], rtol=2e-5)
+    # and the [C] vector is usable by the learnable path (its sum scales dscale)
+    x = torch.randn(2, 6, 5, 5, device="cuda").requires_grad_(True)
+    s = torch.nn.Parameter(torch.tensor(0.05, dtype=torch.float64, device="cuda"))
+    layer.activation_quantizer.quantizer.quantize(x, s, 0, True).sum().backward()
+    assert torch.isfinite(s.grad)
+
+
+def test_graphed_step_matches_eager_steps():
+    """Whole-step CUDA-graph capture (graph.py): same losses as the eager-launched steps, bit for bit."""
+    from tiny_model import make_tiny
+    from vsiquantization_b200.graph import GraphedQATStep
+    from vsiquantization_b200.modules.fuse import fuse_modules_unified
+    from vsiquantization_b200.utils.quantize_manager import activate_learning_qparam, activate_quantizer, calibrate_qat_model
+
+    def build():
+        torch.manual_seed(0)
+        m = fuse_modules_unified(make_tiny(0), [["conv", "bn", "relu"]]).cuda()
+        calib = [(torch.randint(0, 256, (2, 3, 32, 32), generator=torch.Generator().manual_seed(5), dtype=torch.uint8), None)]
+        calibrate_qat_model(m, calib, _data_calib, "cuda")
+        activate_learning_qparam(m, use_init=True)
+        activate_quantizer(m)
+        m.train()
+        return m, torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9)
+
+    loss_fn = lambda y: (y ** 2).mean()  # noqa: E731
+    batches = [torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(10 + i)).cuda() for i in range(4)]
+    m1, o1 = build()
+    eager = []
+    for _ in range(3):  # the same warm-up steps GraphedQATStep runs on its example input
+        o1.zero_grad(set_to_none=True)
+        loss_fn(m1(batches[0])).backward()
+        o1.step()
+    for b in batches:
+        o1.zero_grad(set_to_none=True)
+        loss = loss_fn(m1(b))
+        loss.backward()
+        o1.step()
+        eager.append(loss.item())
+    m2, o2 = build()
+    step = GraphedQATStep(m2, o2, loss_fn, batches[0], warmup=3)
+    graphed = [step(b).item() for b in batches]
+    assert graphed == eager
