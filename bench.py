@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 2^20..2^30 x quantiser-kind sweep (N=1 only)")
+    ap.add_argument("--sweep-log2n", type=int, nargs="+", default=[20, 22, 24, 26, 28, 30])
     return ap.parse_args()
 
 
@@ -160,6 +162,76 @@ def cpu_baseline(log2n: int, iters: int = 5, warm: int = 2):
         out["c_port_fused_gbs"] = None
         out["c_port_note"] = str(e)[:80]
     return out
+
+
+def size_sweep(dev, log2ns, peak, iters: int = 10):
+    """BASELINE configs[1] in full: per-tensor and per-channel W8 / W4 quantisers over 2^20 .. 2^30 fp32 elements,
+    forward + backward timed separately with CUDA events (median of `iters`); tensors that fit the 126 MB L2 get a
+    1 GiB flush write before every timed launch.  Extra information beside the contract keys, N = 1 only."""
+    import torch
+    from vsiquantization_b200 import ops
+
+    def timed(fn, flush):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(iters):
+            if flush is not None:
+                flush.fill_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        return ts[len(ts) // 2]
+
+    rows = []
+    flush = torch.empty(256 << 20, dtype=torch.float32, device=dev)
+    C = 512
+    for lg in log2ns:
+        n = 1 << lg
+        try:
+            torch.manual_seed(0)
+            x, g = torch.randn(n, device=dev), torch.randn(n, device=dev)
+            y, dx = torch.empty_like(x), torch.empty_like(x)
+        except torch.OutOfMemoryError:
+            rows.append({"log2n": lg, "skipped": "out of memory"})
+            continue
+        fl = flush if 4 * n <= (256 << 20) else None
+        xc, gc, yc, dxc = x.view(C, n // C), g.view(C, n // C), y.view(C, n // C), dx.view(C, n // C)
+        s8 = (torch.rand(C, device=dev) * 1.5 + 0.5) * (3.0 / 127)
+        s4 = (torch.rand(C, device=dev) * 1.5 + 0.5) * (3.0 / 7)
+        z0, z8 = torch.zeros(C, device=dev), torch.full((C,), 8.3, device=dev)
+        ds, dz = torch.empty(C, device=dev), torch.empty(C, device=dev)
+        pt8, pt4 = ops.QSpec(-128, 127), ops.QSpec(0, 15)
+        pc8, pc4 = ops.QSpec(-128, 127, ch_axis=0), ops.QSpec(0, 15, ch_axis=0, zp_learned=True)
+        gs4 = ops.lsq_grad_scale(15, n, C)
+        kinds = [
+            ("per-tensor W8 symmetric UniformQuantizer, fwd + STE bwd",
+             lambda: ops.fake_quant_forward(x, SCALE, ZP, pt8, out=y),
+             lambda: ops.fake_quant_backward_ste(x, g, SCALE, ZP, pt8, out=dx)),
+            ("per-tensor W4 asymmetric UniformQuantizer (z=8), fwd + STE bwd",
+             lambda: ops.fake_quant_forward(x, 3.0 / 7, 8, pt4, out=y),
+             lambda: ops.fake_quant_backward_ste(x, g, 3.0 / 7, 8, pt4, out=dx)),
+            (f"per-channel (C={C}, ch_axis 0) W8 symmetric UniformQuantizer, fwd + STE bwd",
+             lambda: ops.fake_quant_forward(xc, s8, z0, pc8, out=yc),
+             lambda: ops.fake_quant_backward_ste(xc, gc, s8, z0, pc8, out=dxc)),
+            (f"per-channel (C={C}, ch_axis 0) W4 asymmetric LSQQuantizer, fwd + LSQ bwd (dx, dscale[C], dzp[C])",
+             lambda: ops.fake_quant_forward(xc, s4, z8, pc4, out=yc),
+             lambda: ops.lsq_backward(xc, gc, s4, z8, pc4, gs4, ds_out=ds, dz_out=dz, want_dz=True, dx_out=dxc)),
+        ]
+        for name, f, b in kinds:
+            tf, tb = timed(f, fl), timed(b, fl)
+            gbs = 20.0 * n / ((tf + tb) * 1e-3) / 1e9
+            rows.append({"log2n": lg, "quantizer": name, "fwd_ms": round(tf, 5), "bwd_ms": round(tb, 5),
+                         "fwd_bwd_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4),
+                         "l2_flushed": fl is not None})
+        del x, g, y, dx, xc, gc, yc, dxc
+        torch.cuda.empty_cache()
+    return rows
 
 
 # ---------------------------------------------------------------------------------- reference arm
@@ -338,6 +410,8 @@ def run_native(args):
                                     "frac": 8.0 * n / (fwd_ms * 1e-3) / 1e9 / peak}},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "oracle_spot_check_bit_exact": check,
     }
+    if world == 1 and not args.no_sweep:
+        line["sweep"] = size_sweep(dev, args.sweep_log2n, peak)
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.cpu_log2n)
     print(json.dumps(line), flush=True)

@@ -158,6 +158,10 @@ def run(args) -> dict:
     model.train()
     if args.channels_last:
         model.to(memory_format=torch.channels_last)
+    bank = None
+    if args.weight_bank and args.quant_impl == "native":
+        from vsiquantization_b200.bank import WeightBank
+        bank = WeightBank(model).install()
     bucket = None
     net = model
     if world > 1:
@@ -230,6 +234,7 @@ def run(args) -> dict:
            "images_per_s": args.batch * world * args.steps / (ms * 1e-3), "quant_impl": args.quant_impl,
            "w_bits": args.w_bits, "a_bits": args.a_bits, "asymmetric": args.asym, "per_channel": args.per_channel,
            "lsq": args.lsq, "mixed": args.mixed, "cuda_graph": args.cuda_graph, "channels_last": args.channels_last,
+           "weight_bank": bool(bank is not None and bank.last_used),
            "loss": loss, "vsiq_launches_per_step": launches / args.steps,
            "calibration_s": calib_s, "calib_batches": args.calib_batches,
            "h2d_bytes_per_step": args.batch * 3 * args.imgsz * args.imgsz, "d2h_bytes_per_step": 4,
@@ -256,6 +261,7 @@ def parse(argv=None):
     ap.add_argument("--quant-impl", default="native", choices=["native", "eager"])
     ap.add_argument("--channels-last", action="store_true", help="NHWC memory format (cuDNN's native layout on sm_100)")
     ap.add_argument("--cuda-graph", action="store_true", help="capture fwd+bwd+optimizer once, replay per step")
+    ap.add_argument("--weight-bank", action="store_true", help="all weight quantisers in one multi-tensor launch each way")
     return ap.parse_args(argv)
 
 

@@ -223,6 +223,52 @@ int vsiq_ci_lsq_bwd(const float *x, const float *bias, const float *g, float *dx
                     int64_t qp_channels, double grad_scale_host, const float *grad_scale_dev, int64_t g_row_pitch,
                     void *workspace, size_t workspace_bytes, vsiq_stream_t stream);
 
+/* ---- multi-tensor weight path ("weight bank") ---------------------------------------------
+ * Every fused layer fake-quantises its (small) weight tensor each step: FakeQuantize.quantize_weights
+ * (quantizers/fake_quantize.py:62-63) -> QuantizationManager.quantize (quantization_manager.py:73-90) ->
+ * UniformQuantizer.quantize (uniform.py:34-56), i.e. L forward launches and L backward launches per step for
+ * L = 57..97 YOLOv8 layers.  These entry points do all L tensors in ONE launch each way (plus one tiny combine
+ * launch for the LSQ sums): a table of vsiq_mt_entry describes the tensors, warps take 1024-element tiles across the
+ * whole table.  Same arithmetic, bit-identical values, as L calls of vsiq_fake_quant_fwd / vsiq_lsq_bwd.
+ *
+ * The caller fills one vsiq_mt_entry per tensor, calls vsiq_mt_plan on the HOST array (it fills the fields below the
+ * marker), copies the array to the device as plain bytes and passes both copies to the launchers (the host copy gives
+ * the launch geometry, the kernels read the device copy).  Pointers inside the table (x, qparams) must stay valid;
+ * per-step buffers (y, g, dx, gradient outputs) are launch arguments.  pre_op must be VSIQ_PRE_NONE. */
+typedef struct vsiq_mt_entry {
+    const float *x;              /* weight [rows, inner] fp32 (any alignment; 32-byte aligned is the fast path) */
+    int64_t rows;                /* output channels */
+    int64_t inner;               /* elements per output channel */
+    int64_t out_offset;          /* element offset of this tensor inside the flat y (fwd) / dx (bwd) buffer; multiple of 8 */
+    int64_t qp_offset;           /* first entry of this tensor inside the flat dscale / dzp outputs */
+    int64_t qp_channels;         /* 1 = per tensor, rows = per channel (ch_axis 0) */
+    vsiq_qparams qp;
+    double grad_scale;           /* LSQ gradient scale, host factor ((qmax * numel / qp_channels) ** -0.5 [* ...]) */
+    const float *grad_scale_dev; /* optional device factor (calib_grad_scale), may be NULL */
+    int32_t learn;               /* backward: 0 = STE only, 1 = dscale, 2 = dscale and dzero_point */
+    /* ---- filled by vsiq_mt_plan ---- */
+    uint32_t first_tile;
+    uint32_t n_tiles;
+    uint32_t chunks;             /* tiles per row */
+    int32_t tile;                /* elements per tile */
+    float tlo, thi;              /* pre-rounding clamp thresholds derived from qmin / qmax */
+} vsiq_mt_entry;
+
+#define VSIQ_MT_MAX_TENSORS 4096
+/* Validates the entries and fills their plan fields; *total_tiles receives the tile count of the whole table. */
+int vsiq_mt_plan(vsiq_mt_entry *table_host, int n, uint32_t *total_tiles);
+/* y_flat[out_offset + i] = fq(x[i]) for every tensor of the table: one launch. */
+int vsiq_mt_fake_quant_fwd(const vsiq_mt_entry *table_host, const vsiq_mt_entry *table_dev, int n, float *y_flat,
+                           vsiq_stream_t stream);
+/* dx_flat[out_offset + i], dscale_flat[qp_offset + c] (fp64), dzp_flat[qp_offset + c] (fp32) for every tensor:
+ * one streaming launch per 120 tensors plus one combine launch.  g: HOST array of n DEVICE pointers (the upstream
+ * gradient of each tensor, same shape as x).  dscale_flat / dzp_flat may be NULL when no entry learns.  The
+ * workspace needs no initialisation.  Deterministic (fixed-order fp64 combination). */
+size_t vsiq_mt_workspace_bytes(uint32_t total_tiles);
+int vsiq_mt_lsq_bwd(const vsiq_mt_entry *table_host, const vsiq_mt_entry *table_dev, int n, const float *const *g,
+                    float *dx_flat, double *dscale_flat, float *dzp_flat, void *workspace, size_t workspace_bytes,
+                    vsiq_stream_t stream);
+
 /* ---- self-test ---------------------------------------------------------------------------
  * The kernels divide by the (tile-uniform) scale through a hoisted correctly-rounded reciprocal and
  * exact-residual FMA corrections instead of the per-element IEEE division sequence.  This entry

@@ -156,3 +156,61 @@ def test_dropin_install_modules_in_a_fresh_interpreter():
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr[-500:]
     assert "vsiquantization_b200.modules.fuse" in out.stdout and "LSQQuantizer" in out.stdout
+
+
+def test_checkpoint_keeps_calibration_and_learned_qparams():
+    """state_dict round trip: the reference loses fixed scale / zero-point and observer extrema
+    (plain attributes, yolov8_qat.py:299); here they travel in `_extra_state`, learned qparams keep the reference's
+    key names, and a reference-style checkpoint (no extra state) still loads strictly."""
+    import torch
+    from vsiquantization_b200.quantizers.quantization_manager import QuantizationManager as M
+
+    class Layer(torch.nn.Module):
+        def __init__(self, sym=True):
+            super().__init__()
+            self.weight_quantizer = M("UniformQuantizer", "MinMaxObserver", 8, sym)
+            self.activation_quantizer = M("LSQQuantizer", "LSQObserver", 4, sym)
+
+    def calibrated(sym=True):
+        layer = Layer(sym)
+        for k, q in enumerate((layer.weight_quantizer, layer.activation_quantizer)):
+            st = torch.zeros(1, 8, dtype=torch.float64)
+            st[0, :5] = torch.tensor([-1.5 - k, 2.0 + k, (2.0 + k) / 127, 3.0 * (not sym), 2.0], dtype=torch.float64)
+            st[0, 5] = 1.25
+            q.observer.load_state(st)
+            q._calibrated = True
+            q._invalidate()
+            q.is_learning_scale, q.is_quantize = False, True
+        return layer
+
+    a = calibrated()
+    sd = a.state_dict()
+    assert set(sd) == {"weight_quantizer._extra_state", "activation_quantizer._extra_state"}
+    b = Layer()
+    assert not b.load_state_dict(sd, strict=True).missing_keys
+    for qa, qb in ((a.weight_quantizer, b.weight_quantizer), (a.activation_quantizer, b.activation_quantizer)):
+        assert (qb.scale, qb.zero_point) == (qa.scale, qa.zero_point) and isinstance(qb.scale, float)
+        assert (qb.observer.min_val, qb.observer.max_val) == (qa.observer.min_val, qa.observer.max_val)
+        assert (qb.is_learning_scale, qb.is_quantize, qb.is_observer_qparam) == (False, True, True)
+    # learned qparams: reference key names, re-created on a freshly fused model
+    c = calibrated(sym=False)
+    for q in (c.weight_quantizer, c.activation_quantizer):
+        q.is_learning_scale = True
+        q.init_scaling_factor_for_learning()
+        q.make_learn_qparameter()
+    with torch.no_grad():
+        c.weight_quantizer.scale.fill_(0.0123)
+    sd = c.state_dict()
+    assert {"weight_quantizer.scale", "weight_quantizer.zero_point", "activation_quantizer.scale"} <= set(sd)
+    assert sd["weight_quantizer.scale"].dtype == torch.float64 and sd["weight_quantizer.scale"].shape == ()
+    d = Layer(sym=False)
+    res = d.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert isinstance(d.weight_quantizer.scale, torch.nn.Parameter) and d.weight_quantizer.scale.item() == 0.0123
+    assert torch.equal(d.weight_quantizer.zero_point.detach(), c.weight_quantizer.zero_point.detach())
+    assert d.weight_quantizer.is_learning_scale and d.activation_quantizer.is_learning_scale
+    # a checkpoint written by the reference: learned scales only, no extra state
+    ref_sd = {k: v for k, v in sd.items() if not k.endswith("_extra_state")}
+    e = Layer(sym=False)
+    res = e.load_state_dict(ref_sd, strict=True)
+    assert not res.missing_keys and e.weight_quantizer.scale.item() == 0.0123

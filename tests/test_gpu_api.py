@@ -536,3 +536,144 @@ def test_graphed_step_matches_eager_steps():
     step = GraphedQATStep(m2, o2, loss_fn, batches[0], warmup=3)
     graphed = [step(b).item() for b in batches]
     assert graphed == eager
+
+
+def _bank_model(per_channel, asym, w_bits, channels_last):
+    from tiny_model import make_tiny
+    from vsiquantization_b200.modules.fuse import fuse_modules_unified
+    from vsiquantization_b200.modules.fuse_config import FuseConfig, create_fuse_config_manager
+    from vsiquantization_b200.utils.quantize_manager import activate_learning_qparam, activate_quantizer, calibrate_qat_model
+    name = "LSQQuantizer" if per_channel else "UniformQuantizer"
+    cfg = FuseConfig(observer_w_name="LSQObserver", quantizer_w_name=name, observer_a_name="LSQObserver", quantizer_a_name=name,
+                     w_symmetric=not asym, a_symmetric=not asym, bits_w=w_bits, bits_a=8,
+                     w_ch_axis=0 if per_channel else None, a_ch_axis=1 if per_channel else None)
+    m = fuse_modules_unified(make_tiny(0), [["conv", "bn", "relu"]], config_manager=create_fuse_config_manager(cfg, {})).cuda()
+    calib = [(torch.randint(0, 256, (2, 3, 32, 32), generator=torch.Generator().manual_seed(5), dtype=torch.uint8), None)]
+    calibrate_qat_model(m, calib, _data_calib, "cuda")
+    activate_learning_qparam(m, use_init=True)
+    activate_quantizer(m)
+    m.train()
+    if channels_last:
+        m.to(memory_format=torch.channels_last)
+    return m
+
+
+@pytest.mark.parametrize("per_channel,asym,w_bits,channels_last", [(False, False, 8, False), (True, True, 4, False),
+                                                                   (True, True, 4, True), (False, True, 8, True)])
+def test_weight_bank_matches_per_layer_path(per_channel, asym, w_bits, channels_last):
+    """bank.WeightBank (one multi-tensor launch each way) against the per-layer launches: same loss, same weight
+    gradients bit for bit; dscale / dzero_point agree to summation order."""
+    from vsiquantization_b200 import _lib
+    from vsiquantization_b200.bank import WeightBank
+    m = _bank_model(per_channel, asym, w_bits, channels_last)
+    n_layers = sum(1 for x in m.modules() if hasattr(x, "weight_quantizer"))
+    assert n_layers >= 3
+    x = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    bank = WeightBank(m)
+    res = []
+    for use in (False, True):
+        if use:
+            bank.install()
+        m.zero_grad(set_to_none=True)
+        l0 = _lib.launch_count
+        loss = (m(x) ** 2).mean()
+        loss.backward()
+        launches = _lib.launch_count - l0
+        assert bank.last_used == use
+        res.append((loss.item(), launches, {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    bank.remove()
+    (la, na, ga), (lb, nb, gb) = res
+    assert la == lb
+    assert nb == na - 2 * n_layers + 3  # L forward + L backward launches became 1 + 1 (+ 1 combine)
+    assert ga.keys() == gb.keys()
+    for n in ga:
+        if n.endswith(("quantizer.scale", "quantizer.zero_point")):
+            a, b = ga[n].double(), gb[n].double()
+            assert a.shape == b.shape and ga[n].dtype == gb[n].dtype
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(a.abs().max() + 1e-30)), n
+        else:
+            assert torch.equal(ga[n], gb[n]), n
+    # eval / no-grad forward also goes through the bank and agrees
+    m.eval()
+    with torch.no_grad():
+        bank.install()
+        yb = m(x)
+        assert bank.last_used
+        bank.remove()
+        ya = m(x)
+    assert torch.equal(ya, yb)
+
+
+def test_weight_bank_falls_back_while_calibrating_and_works_under_graph_capture():
+    from vsiquantization_b200.bank import WeightBank
+    from vsiquantization_b200.graph import GraphedQATStep
+    from vsiquantization_b200.utils.quantize_manager import calibrate_qat_model
+    m = _bank_model(False, False, 8, False)
+    bank = WeightBank(m).install()
+    calib = [(torch.randint(0, 256, (2, 3, 32, 32), generator=torch.Generator().manual_seed(6), dtype=torch.uint8), None)]
+    calibrate_qat_model(m, calib, _data_calib, "cuda")  # observers collect: per-layer path
+    assert not bank.last_used
+    m2 = _bank_model(False, False, 8, False)
+    m3 = _bank_model(False, False, 8, False)
+    WeightBank(m3).install()
+    loss_fn = lambda y: (y ** 2).mean()  # noqa: E731
+    batches = [torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(20 + i)).cuda() for i in range(3)]
+    out = []
+    for mod in (m2, m3):
+        opt = torch.optim.SGD(mod.parameters(), lr=1e-3, momentum=0.9)
+        step = GraphedQATStep(mod, opt, loss_fn, batches[0], warmup=3)
+        out.append([step(b).item() for b in batches])
+    assert out[0] == out[1]
+
+
+def test_multi_tensor_abi_against_single_tensor_kernels():
+    """vsiq_mt_* on ragged / unaligned / empty-ish tensors against vsiq_fake_quant_fwd and vsiq_lsq_bwd."""
+    import ctypes
+    from vsiquantization_b200 import _lib, ops
+    from vsiquantization_b200.bank import _Plan
+    torch.manual_seed(7)
+    shapes = [(16, 3, 3, 3), (1, 5), (7, 333), (64, 32, 3, 3), (3, 4100), (256, 1, 1, 1), (130, 1029)]
+    items, ref = [], []
+    big = torch.randn(sum(int(np.prod(s)) for s in shapes) + 64, device="cuda")
+    off = 3  # deliberately unaligned views for some tensors
+    for i, shp in enumerate(shapes):
+        n = int(np.prod(shp))
+        w = big[off:off + n].view(shp) if i % 3 == 1 else torch.randn(shp, device="cuda")
+        off += n
+        pc = i % 2 == 0 and shp[0] > 1
+        C = shp[0] if pc else 1
+        scale = (torch.rand(C, device="cuda", dtype=torch.float64) * 0.05 + 0.01) if pc else \
+            torch.tensor(0.03 + 0.01 * i, device="cuda", dtype=torch.float64)
+        asym = i % 3 == 0
+        zp = (torch.rand(C, device="cuda") * 10 + 2.3).reshape(scale.shape) if asym else 0
+        spec = ops.QSpec(0, 15, ch_axis=0 if pc else None, zp_learned=asym) if asym else \
+            ops.QSpec(-128, 127, ch_axis=0 if pc else None)
+        learn = 2 if asym else (1 if i != 5 else 0)
+        gs = ops.lsq_grad_scale(spec.qmax, n, C)
+        items.append((None, w, scale, zp, spec, learn, gs, None))
+    plan = _Plan(items, torch.device("cuda"))
+    y_flat = torch.full((plan.total_out,), float("nan"), device="cuda")
+    _lib.check(_lib.lib.vsiq_mt_fake_quant_fwd(plan.host, plan.dev.data_ptr(), len(items), y_flat.data_ptr(),
+                                               ops._stream_ptr()), "mt fwd")
+    gs_list = [torch.randn(it[1].shape, device="cuda") for it in items]
+    gptrs = (ctypes.c_void_p * len(items))(*[g.data_ptr() for g in gs_list])
+    dx_flat = torch.full((plan.total_out,), float("nan"), device="cuda")
+    ds_flat = torch.zeros(plan.total_q, dtype=torch.float64, device="cuda")
+    dz_flat = torch.zeros(plan.total_q, dtype=torch.float32, device="cuda")
+    ws = torch.empty(plan.ws_bytes, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib.vsiq_mt_lsq_bwd(plan.host, plan.dev.data_ptr(), len(items), gptrs, dx_flat.data_ptr(),
+                                        ds_flat.data_ptr(), dz_flat.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        ops._stream_ptr()), "mt bwd")
+    for i, (_, w, scale, zp, spec, learn, gs, _) in enumerate(items):
+        y = ops.fake_quant_forward(w, scale, zp, spec)
+        assert torch.equal(plan.view(y_flat, i), y), i
+        dx, ds, dz = ops.lsq_backward(w, gs_list[i], scale, zp, spec, gs, want_dz=learn == 2, ds_dtype=torch.float64)
+        assert torch.equal(plan.view(dx_flat, i), dx), i
+        q0, C = plan.q_offsets[i], scale.numel()
+        if learn:
+            tol = 1e-6 * float((gs_list[i].abs().sum() * 128 * gs))
+            assert torch.allclose(ds_flat[q0:q0 + C], ds.double().reshape(-1), rtol=1e-6, atol=tol), i
+        if learn == 2:
+            assert torch.allclose(dz_flat[q0:q0 + C], dz.reshape(-1), rtol=1e-5, atol=1e-6 * float(dz.abs().max())), i

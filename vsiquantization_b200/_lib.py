@@ -32,6 +32,17 @@ class QParams(ctypes.Structure):
                 ("pre_op", ctypes.c_int32)]
 
 
+class MtEntry(ctypes.Structure):
+    """vsiq_mt_entry (include/vsiq.h): one weight tensor of a multi-tensor launch."""
+    _fields_ = [("x", c_void_p), ("rows", c_int64), ("inner", c_int64), ("out_offset", c_int64), ("qp_offset", c_int64),
+                ("qp_channels", c_int64), ("qp", QParams), ("grad_scale", c_double), ("grad_scale_dev", c_void_p),
+                ("learn", ctypes.c_int32), ("first_tile", ctypes.c_uint32), ("n_tiles", ctypes.c_uint32),
+                ("chunks", ctypes.c_uint32), ("tile", ctypes.c_int32), ("tlo", c_float), ("thi", c_float)]
+
+
+MT_PACK = 120  # upstream-gradient pointers per backward launch (multi_tensor.cu kMtPack)
+
+
 class VsiqError(RuntimeError):
     pass
 
@@ -78,6 +89,11 @@ _SIGNATURES = {
                                 c_int64, c_int64, ctypes.POINTER(QParams), c_int64, c_double, c_void_p, c_int64, c_void_p,
                                 c_size_t, c_void_p]),
     "vsiq_selftest_division": (c_int, [c_float, c_int, c_void_p, c_void_p]),
+    "vsiq_mt_plan": (c_int, [ctypes.POINTER(MtEntry), c_int, ctypes.POINTER(ctypes.c_uint32)]),
+    "vsiq_mt_fake_quant_fwd": (c_int, [ctypes.POINTER(MtEntry), c_void_p, c_int, c_void_p, c_void_p]),
+    "vsiq_mt_workspace_bytes": (c_size_t, [ctypes.c_uint32]),
+    "vsiq_mt_lsq_bwd": (c_int, [ctypes.POINTER(MtEntry), c_void_p, c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 EXPORTED = tuple(_SIGNATURES)

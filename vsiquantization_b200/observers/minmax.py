@@ -49,6 +49,20 @@ class MinMaxObserver(BaseObserver):
         self._state = state
         self._host = None
 
+    def load_state(self, state: torch.Tensor) -> None:
+        """Restore a saved [C, 8] fp64 state (checkpoints; QuantizationManager.set_extra_state).  It goes to the GPU
+        when there is one; without one it stays on the host and the first kernel call fails loudly."""
+        if state.dim() != 2 or state.shape[1] != 8:
+            raise ValueError("observer state must be [channels, 8]")
+        state = state.detach().to(torch.float64)
+        dev = self._state.device if self._state is not None else (torch.device("cuda") if torch.cuda.is_available()
+                                                                   else state.device)
+        if self._state is not None and self._state.shape == state.shape:
+            self._state.copy_(state)  # keeps arena bindings (parallel.py) intact
+        else:
+            self._state = state.to(dev).contiguous().clone()
+        self._host = None
+
     def _ensure_state(self, x: torch.Tensor) -> torch.Tensor:
         C = 1 if self.ch_axis is None else x.shape[self.ch_axis]
         if self._state is None:

@@ -13,6 +13,13 @@ SURVEY.md 0.4).  What differs is WHERE the numbers live:
   * with fixed qparams the kernels read scale / zero-point straight from the observer state on the device;
   * init_scaling_factor_for_learning + make_learn_qparameter build the learnable Parameter on the device.
 
+Checkpoints: the reference's calibrated scale / zero-point are plain Python attributes and its
+observer extrema live outside any nn.Module, so ``state_dict()`` loses them and only the learned ``scale`` Parameters
+survive (yolov8_qat.py:299,309).  Here the same keys are kept (``...weight_quantizer.scale`` / ``.zero_point`` for
+learned qparams) and everything else -- observer state, fixed qparams, the mode flags -- travels in the module's
+``_extra_state`` entry; loading a checkpoint that has learned qparams into a freshly fused model re-creates the
+Parameters, and a reference checkpoint without ``_extra_state`` still loads.
+
 Deliberate fixes where the reference cannot run: the constructor's ``is_symmetric`` is stored
 (the reference hard-codes True, :50, so an asymmetric learnable zero-point is unreachable and crashes, uniform.py:50-52);
 asymmetric managers therefore get the learnable zero-point the code at :100-101 intends.  Symmetric flows -- every
@@ -94,6 +101,62 @@ class QuantizationManager(nn.Module):
             out.append(max(var, 0.0) ** 0.5)
         return out
 
+    # ---- checkpointing --------------------------------------------------------------------------------------
+    def get_extra_state(self):
+        """Everything state_dict() would otherwise lose: mode flags, the observer's running state, fixed qparams."""
+        def host(v):
+            if isinstance(v, nn.Parameter):
+                return None  # learned qparams are ordinary state_dict entries
+            if isinstance(v, torch.Tensor):
+                return v.detach().cpu()
+            return v
+        st = getattr(self.observer, "state", None)
+        return {"version": 1,
+                "flags": {"is_observer_qparam": bool(self.is_observer_qparam), "is_learning_scale": bool(self.is_learning_scale),
+                          "is_quantize": bool(self.is_quantize)},
+                "calibrated": bool(self._calibrated),
+                "observer_state": st.detach().cpu() if isinstance(st, torch.Tensor) else None,
+                "scale": host(self.__dict__.get("scale")), "zero_point": host(self.__dict__.get("zero_point")),
+                "calib_grad_scale": host(getattr(self.quantizer, "calib_grad_scale", 1))}
+
+    def set_extra_state(self, state) -> None:
+        if not state:
+            return
+        for k, v in state.get("flags", {}).items():
+            setattr(self, k, v)
+        st = state.get("observer_state")
+        if st is not None and hasattr(self.observer, "load_state"):
+            self.observer.load_state(st)
+        self._calibrated = bool(state.get("calibrated", False)) and st is not None
+        self._invalidate()
+        for name in _LAZY:
+            v = state.get(name)
+            if v is not None and name not in self._parameters:
+                if isinstance(v, torch.Tensor) and st is not None:
+                    v = v.to(self.observer.state.device)
+                self.__dict__[name] = v
+        if self._calibrated and (state.get("scale") is not None):
+            self._calibrated = "scale" in self._parameters  # explicit host values win over the observer state
+        cgs = state.get("calib_grad_scale")
+        if cgs is not None and hasattr(self.quantizer, "calib_grad_scale"):
+            self.quantizer.calib_grad_scale = cgs
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # a checkpoint with learned qparams loaded into a freshly fused model: create the Parameters first
+        for name in _LAZY:
+            t = state_dict.get(prefix + name)
+            if isinstance(t, torch.Tensor) and name not in self._parameters:
+                self.__dict__.pop(name, None)
+                st = getattr(self.observer, "state", None)
+                dev = st.device if isinstance(st, torch.Tensor) else t.device
+                self.register_parameter(name, nn.Parameter(torch.empty_like(t, device=dev), requires_grad=True))
+                self._calibrated = False
+        n_missing = len(missing_keys)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        extra = prefix + "_extra_state"
+        if extra in missing_keys[n_missing:]:  # checkpoints written by the reference have no extra state
+            missing_keys.remove(extra)
+
     # ---- reference interface -----------------------------------------------------------------------------
     def collect_qparameter(self, x):
         """Observe x while calibrating (:55-71): one launch, no synchronisation."""
@@ -113,6 +176,11 @@ class QuantizationManager(nn.Module):
         and relu is applied here -- fused into the quantiser kernels when quantising, as a plain F.relu otherwise.
         ``bias`` (with pre_relu, channels_last x): the conv bias is added in the same pass and its gradient comes out of
         the backward kernel."""
+        banked = self.__dict__.get("_banked")
+        if banked is not None:  # bank.WeightBank already fake-quantised this weight in its multi-tensor launch
+            self.__dict__["_banked"] = None
+            if banked[0] is x and not pre_relu:
+                return banked[1]
         if pre_relu:
             if not self.can_fuse_relu():
                 if bias is not None:
@@ -161,6 +229,8 @@ class QuantizationManager(nn.Module):
         """scale -> nn.Parameter; asymmetric: zero_point -> float nn.Parameter initialised at zp + 1e-9 (:92-103);
         symmetric: zero_point = 0."""
         scale = self.scale
+        zp_now = self.zero_point
+        self._calibrated = False  # from here on the Parameters (not the observer state) are the source of truth
         if isinstance(scale, nn.Parameter):
             pass
         elif isinstance(scale, torch.Tensor):
@@ -173,7 +243,7 @@ class QuantizationManager(nn.Module):
             # after init_scaling_factor_for_learning and fp32 otherwise (:99); param_dtype decides here.
             self.scale = nn.Parameter(torch.tensor(float(scale), dtype=self.param_dtype, device=dev), requires_grad=True)
         if not self.is_symmetric:
-            zp = self.zero_point
+            zp = zp_now
             if not isinstance(zp, nn.Parameter):
                 self.__dict__.pop("zero_point", None)
                 if isinstance(zp, torch.Tensor):
