@@ -161,7 +161,8 @@ def run(args) -> dict:
     bank = None
     if args.weight_bank and args.quant_impl == "native":
         from vsiquantization_b200.bank import WeightBank
-        bank = WeightBank(model).install()
+        # under DDP every layer keeps its own backward node so the gradient all-reduce still overlaps the backward pass
+        bank = WeightBank(model, backward="per_layer" if world > 1 else "bank").install()
     bucket = None
     net = model
     if world > 1:

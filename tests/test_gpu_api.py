@@ -560,41 +560,47 @@ def _bank_model(per_channel, asym, w_bits, channels_last):
 
 @pytest.mark.parametrize("per_channel,asym,w_bits,channels_last", [(False, False, 8, False), (True, True, 4, False),
                                                                    (True, True, 4, True), (False, True, 8, True)])
-def test_weight_bank_matches_per_layer_path(per_channel, asym, w_bits, channels_last):
+def test_weight_bank_matches_per_layer_path(per_channel, asym, w_bits, channels_last, monkeypatch):
     """bank.WeightBank (one multi-tensor launch each way) against the per-layer launches: same loss, same weight
     gradients bit for bit; dscale / dzero_point agree to summation order."""
     from vsiquantization_b200 import _lib
     from vsiquantization_b200.bank import WeightBank
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)  # bit-for-bit comparisons across three backward runs
     m = _bank_model(per_channel, asym, w_bits, channels_last)
     n_layers = sum(1 for x in m.modules() if hasattr(x, "weight_quantizer"))
     assert n_layers >= 3
     x = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
     if channels_last:
         x = x.contiguous(memory_format=torch.channels_last)
-    bank = WeightBank(m)
     res = []
-    for use in (False, True):
-        if use:
+    for mode in (None, "bank", "per_layer"):
+        bank = WeightBank(m, backward=mode or "bank")
+        if mode:
             bank.install()
         m.zero_grad(set_to_none=True)
         l0 = _lib.launch_count
         loss = (m(x) ** 2).mean()
         loss.backward()
         launches = _lib.launch_count - l0
-        assert bank.last_used == use
+        assert bank.last_used == bool(mode)
+        bank.remove()
         res.append((loss.item(), launches, {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
-    bank.remove()
-    (la, na, ga), (lb, nb, gb) = res
-    assert la == lb
+    (la, na, ga), (lb, nb, gb), (lc, nc, gc) = res
+    assert la == lb == lc
     assert nb == na - 2 * n_layers + 3  # L forward + L backward launches became 1 + 1 (+ 1 combine)
-    assert ga.keys() == gb.keys()
+    assert nc == na - n_layers + 1      # per_layer: one forward launch, every layer keeps its own backward launch
+    assert ga.keys() == gb.keys() == gc.keys()
     for n in ga:
+        assert torch.equal(ga[n], gc[n]), n  # same backward kernels as the plain per-layer path
         if n.endswith(("quantizer.scale", "quantizer.zero_point")):
             a, b = ga[n].double(), gb[n].double()
             assert a.shape == b.shape and ga[n].dtype == gb[n].dtype
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(a.abs().max() + 1e-30)), n
         else:
-            assert torch.equal(ga[n], gb[n]), n
+            bad = (ga[n] != gb[n])
+            assert torch.equal(ga[n], gb[n]), (n, int(bad.sum()), ga[n].numel(), float((ga[n] - gb[n]).abs().max()),
+                                               ga[n][bad][:4].tolist(), gb[n][bad][:4].tolist())
+    bank = WeightBank(m)
     # eval / no-grad forward also goes through the bank and agrees
     m.eval()
     with torch.no_grad():

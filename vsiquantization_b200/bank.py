@@ -12,6 +12,11 @@ a bankable state (calibrating, quantisation switched off, CPU tensors, exotic st
     bank = WeightBank(model).install()      # forward pre-hook on `model`
     ...train as usual...
     bank.remove()
+
+``backward="per_layer"`` keeps the single forward launch but gives every layer its own backward node (one LSQ / STE
+launch per layer, as without the bank).  That is the right mode under DistributedDataParallel: a weight's gradient is
+then ready as soon as its layer's backward has run, so DDP's bucketed all-reduce still overlaps the rest of the
+backward pass; the one-launch backward can only run after the LAST weight gradient exists.
 """
 from __future__ import annotations
 
@@ -136,8 +141,38 @@ class _BankFunction(torch.autograd.Function):
         return tuple(out)
 
 
+class _BankedLayer(torch.autograd.Function):
+    """backward="per_layer": the forward value comes from the bank's launch, the backward is this layer's own."""
+
+    @staticmethod
+    def forward(ctx, w, scale, zero_point, wq, spec, learn, gs_host, gs_dev):
+        ctx.spec, ctx.learn, ctx.gs_host, ctx.gs_dev = spec, learn, gs_host, gs_dev
+        ctx.s_t, ctx.z_t = isinstance(scale, torch.Tensor), isinstance(zero_point, torch.Tensor)
+        ctx.consts = (None if ctx.s_t else scale, None if ctx.z_t else zero_point)
+        ctx.save_for_backward(w, *([scale] if ctx.s_t else []), *([zero_point] if ctx.z_t else []))
+        return wq.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        w = saved.pop(0)
+        scale = saved.pop(0) if ctx.s_t else ctx.consts[0]
+        zp = saved.pop(0) if ctx.z_t else ctx.consts[1]
+        if ctx.learn == 0:
+            dw = ops.fake_quant_backward_ste(w, g, scale, zp, ctx.spec) if ctx.needs_input_grad[0] else None
+            return dw, None, None, None, None, None, None, None
+        dw, ds, dz = ops.lsq_backward(w, g, scale, zp, ctx.spec, ctx.gs_host, ctx.gs_dev, want_dz=ctx.learn == 2,
+                                      ds_dtype=scale.dtype, dz_dtype=zp.dtype if ctx.z_t else torch.float32)
+        ds = ds.view(scale.shape) if ctx.needs_input_grad[1] else None
+        dz = dz.view(zp.shape) if (ctx.learn == 2 and ctx.needs_input_grad[2]) else None
+        return (dw if ctx.needs_input_grad[0] else None), ds, dz, None, None, None, None, None
+
+
 class WeightBank:
-    def __init__(self, model: torch.nn.Module):
+    def __init__(self, model: torch.nn.Module, backward: str = "bank"):
+        if backward not in ("bank", "per_layer"):
+            raise ValueError("backward must be 'bank' or 'per_layer'")
+        self.backward = backward
         self.model = model
         self.layers = [m for m in model.modules() if hasattr(m, "weight_quantizer") and hasattr(m, "get_weight_bias")]
         self._plans: dict = {}  # signature -> _Plan (train / eval states alternate; a handful at most)
@@ -235,9 +270,15 @@ class WeightBank:
                 self._plans.clear()
             plan = self._plans[sig] = _Plan(items, items[0][1].device)
         weights = [it[1] for it in plan.items]
-        scales = [it[2] for it in plan.items if it[5] >= 1]
-        zps = [it[3] for it in plan.items if it[5] >= 2]
-        outs = _BankFunction.apply(plan, len(weights), *weights, *scales, *zps)
+        if self.backward == "per_layer" and torch.is_grad_enabled():
+            with torch.no_grad():
+                flat = _BankFunction.apply(plan, len(weights), *weights)
+            outs = [_BankedLayer.apply(w, scale, zp, wq, spec, learn, gs_host, gs_dev)
+                    for (_, w, scale, zp, spec, learn, gs_host, gs_dev), wq in zip(plan.items, flat)]
+        else:
+            scales = [it[2] for it in plan.items if it[5] >= 1]
+            zps = [it[3] for it in plan.items if it[5] >= 2]
+            outs = _BankFunction.apply(plan, len(weights), *weights, *scales, *zps)
         for (mgr, w, *_), wq in zip(plan.items, outs):
             mgr.__dict__["_banked"] = (w, wq)
         self.last_used = True

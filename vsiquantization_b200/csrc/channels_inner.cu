@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads)
 
 // ---------------------------------------------------------------------------------------------- forward
 template <bool PCQ, bool BIAS, bool RELU>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: measured 5.84 -> 6.39 TB/s on [64,32,320,320]
     ci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y, CiGeom geo,
                   QPDev qpd, void* ws) {
     unsigned int* counter = (unsigned int*)ws + 1;
@@ -204,6 +204,81 @@ __global__ void __launch_bounds__(kThreads, 2)
 }
 
 // --------------------------------------------------------------------------------------------- backward
+// One tile of the backward: kCiBatches x kCiUnroll vectors per thread.  FULL = every vector of the tile is in bounds.
+template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS, bool FULL>
+__device__ __forceinline__ void ci_bwd_tile(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx,
+                                            const CiGeom& geo, int64_t vb, uint32_t tile, int t, int c0, int t_row,
+                                            int rows_per_step, int64_t tile_rows, int64_t g_pitch, const QP (&p)[kCiVec],
+                                            const float (&bv)[kCiVec], bool all_fast, float (&te)[kCiVec],
+                                            float (&tb)[kCiVec], float (&tdb)[kCiVec]) {
+#pragma unroll 1
+    for (int b = 0; b < kCiBatches; ++b) {
+        Vec4 vx[kCiUnroll], vg[kCiUnroll];
+        bool ok[kCiUnroll];
+#pragma unroll
+        for (int j = 0; j < kCiUnroll; ++j) {
+            const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
+            ok[j] = FULL || v < geo.n_vec;
+            if (ok[j]) {
+                vx[j] = ld4(x + v * kCiVec);
+                const int64_t row = (int64_t)tile * tile_rows + (int64_t)(b * kCiUnroll + j) * rows_per_step + t_row;
+                vg[j] = ld4(g + row * g_pitch + c0);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kCiUnroll; ++j) {
+            if (!ok[j]) continue;
+            const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
+            Vec4 out;
+            float ve[kCiVec], vbz[kCiVec];
+            bool bad = !all_fast;
+#pragma unroll
+            for (int e = 0; e < kCiVec; ++e) {
+                const float xb = BIAS ? __fadd_rn(vx[j].v[e], bv[e]) : vx[j].v[e];
+                const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+                const float ge = vg[j].v[e];
+                const Elem el = elem_fast(xe, p[e], bad);
+                float d = dx_fast(ge, el.m, p[e], bad);
+                if (RELU) d = xb > 0.0f ? d : 0.0f;
+                out.v[e] = d;
+                if (WANT_DS) {
+                    const float dd = __fsub_rn(el.q, p[e].z);
+                    const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
+                    ve[e] = ge * (dd - mv);
+                    vbz[e] = el.m ? 0.0f : ge;
+                }
+            }
+            if (bad) {  // rare: IEEE sequences for the whole vector
+#pragma unroll
+                for (int e = 0; e < kCiVec; ++e) {
+                    const float xb = BIAS ? __fadd_rn(vx[j].v[e], bv[e]) : vx[j].v[e];
+                    const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+                    const float ge = vg[j].v[e];
+                    const Elem el = elem_slow(xe, p[e]);
+                    float d = dx_slow(ge, el.m, p[e]);
+                    if (RELU) d = xb > 0.0f ? d : 0.0f;
+                    out.v[e] = d;
+                    if (WANT_DS) {
+                        const float dd = __fsub_rn(el.q, p[e].z);
+                        const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
+                        ve[e] = ge * (dd - mv);
+                        vbz[e] = el.m ? 0.0f : ge;
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < kCiVec; ++e) {
+                if (WANT_DS) {
+                    te[e] += ve[e];
+                    tb[e] += vbz[e];
+                }
+                if (BIAS) tdb[e] += out.v[e];
+            }
+            st4(dx + v * kCiVec, out);
+        }
+    }
+}
+
 template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
 __global__ void __launch_bounds__(kThreads, 2)
     ci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ g,
@@ -242,72 +317,13 @@ __global__ void __launch_bounds__(kThreads, 2)
         float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials of this tile
 #pragma unroll
         for (int e = 0; e < kCiVec; ++e) te[e] = tb[e] = tdb[e] = 0.0f;
-#pragma unroll 1
-        for (int b = 0; b < kCiBatches; ++b) {
-            Vec4 vx[kCiUnroll], vg[kCiUnroll];
-            bool ok[kCiUnroll];
-#pragma unroll
-            for (int j = 0; j < kCiUnroll; ++j) {
-                const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
-                ok[j] = v < geo.n_vec;
-                if (ok[j]) {
-                    vx[j] = ld4(x + v * kCiVec);
-                    const int64_t row = (int64_t)tile * tile_rows + (int64_t)(b * kCiUnroll + j) * rows_per_step + t_row;
-                    vg[j] = ld4(g + row * g_pitch + c0);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kCiUnroll; ++j) {
-                if (!ok[j]) continue;
-                const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
-                Vec4 out;
-                float ve[kCiVec], vbz[kCiVec];
-                bool bad = !all_fast;
-#pragma unroll
-                for (int e = 0; e < kCiVec; ++e) {
-                    const float xb = BIAS ? __fadd_rn(vx[j].v[e], bv[e]) : vx[j].v[e];
-                    const float xe = RELU ? max_nan(xb, 0.0f) : xb;
-                    const float ge = vg[j].v[e];
-                    const Elem el = elem_fast(xe, p[e], bad);
-                    float d = dx_fast(ge, el.m, p[e], bad);
-                    if (RELU) d = xb > 0.0f ? d : 0.0f;
-                    out.v[e] = d;
-                    if (WANT_DS) {
-                        const float dd = __fsub_rn(el.q, p[e].z);
-                        const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
-                        ve[e] = ge * (dd - mv);
-                        vbz[e] = el.m ? 0.0f : ge;
-                    }
-                }
-                if (bad) {  // rare: IEEE sequences for the whole vector
-#pragma unroll
-                    for (int e = 0; e < kCiVec; ++e) {
-                        const float xb = BIAS ? __fadd_rn(vx[j].v[e], bv[e]) : vx[j].v[e];
-                        const float xe = RELU ? max_nan(xb, 0.0f) : xb;
-                        const float ge = vg[j].v[e];
-                        const Elem el = elem_slow(xe, p[e]);
-                        float d = dx_slow(ge, el.m, p[e]);
-                        if (RELU) d = xb > 0.0f ? d : 0.0f;
-                        out.v[e] = d;
-                        if (WANT_DS) {
-                            const float dd = __fsub_rn(el.q, p[e].z);
-                            const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
-                            ve[e] = ge * (dd - mv);
-                            vbz[e] = el.m ? 0.0f : ge;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < kCiVec; ++e) {
-                    if (WANT_DS) {
-                        te[e] += ve[e];
-                        tb[e] += vbz[e];
-                    }
-                    if (BIAS) tdb[e] += out.v[e];
-                }
-                st4(dx + v * kCiVec, out);
-            }
-        }
+        // interior tiles carry no per-vector bounds predicates (four fewer live predicate registers in the hot loop)
+        if (vb + geo.tile_vecs <= geo.n_vec)
+            ci_bwd_tile<PCQ, BIAS, RELU, WANT_DS, true>(x, g, dx, geo, vb, tile, t, c0, t_row, rows_per_step, tile_rows,
+                                                        g_pitch, p, bv, all_fast, te, tb, tdb);
+        else
+            ci_bwd_tile<PCQ, BIAS, RELU, WANT_DS, false>(x, g, dx, geo, vb, tile, t, c0, t_row, rows_per_step, tile_rows,
+                                                         g_pitch, p, bv, all_fast, te, tb, tdb);
 #pragma unroll
         for (int e = 0; e < kCiVec; ++e) {
             if (WANT_DS) {
@@ -406,10 +422,10 @@ __global__ void __launch_bounds__(kThreads, 2)
         ci_combine_chunk(records, width, gridDim.x, base, s_part, o, qpd, PCQ, BIAS, C);
 }
 
-static int ci_grid(uint32_t n_tiles) {
+static int ci_grid(uint32_t n_tiles, uint32_t ctas_per_sm) {
     DeviceProps dp;
     if (int e = get_device_props(&dp)) return -e;
-    const uint32_t cap = (uint32_t)dp.sm_count * 2u;  // __launch_bounds__(256, 2): every CTA resident, tiles stolen dynamically
+    const uint32_t cap = (uint32_t)dp.sm_count * ctas_per_sm;  // __launch_bounds__(256, k): every CTA resident, tiles stolen dynamically
     return (int)(n_tiles < cap ? n_tiles : cap);
 }
 
@@ -437,7 +453,7 @@ extern "C" int vsiq_ci_fake_quant_fwd(const float* x, const float* bias, float* 
     if (!make_ci_geom(rows, channels, &geo)) return VSIQ_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return VSIQ_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < kWsHeader) return VSIQ_ERR_WORKSPACE;
-    const int grid = ci_grid(geo.n_tiles);
+    const int grid = ci_grid(geo.n_tiles, 3);
     if (grid < 0) return -grid;
     cudaStream_t st = (cudaStream_t)stream;
     const bool pcq = qp_channels == channels && channels > 1, relu = qp->pre_op == VSIQ_PRE_RELU, hb = bias != nullptr;
@@ -474,7 +490,7 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15u)
         return VSIQ_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < vsiq_ci_workspace_bytes(rows, channels)) return VSIQ_ERR_WORKSPACE;
-    const int grid = ci_grid(geo.n_tiles);
+    const int grid = ci_grid(geo.n_tiles, 2);
     if (grid < 0) return -grid;
     const bool pcq = qp_channels == channels && channels > 1, relu = qp->pre_op == VSIQ_PRE_RELU, hb = bias != nullptr;
     const bool want_ds = dscale != nullptr;
