@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--imgsz", type=int, default=640)
     ap.add_argument("--batches", type=int, default=50, help="GLOBAL number of calibration batches")
+    ap.add_argument("--channels-last", action="store_true",
+                    help="NHWC weights / activations (cuDNN's native layout on sm_100); observers and the BN moments "
+                         "pass walk that memory in place")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -52,6 +55,8 @@ def main():
     model = getattr(yolov8, f"yolo_v8_{args.model}")(num_classes=20).to(dev)
     cfg = create_fuse_config_manager(FuseConfig(is_fuse_bn=False, bits_w=8, bits_a=8))  # BN kept: needed for re-estimation
     model = fuse_modules_unified(model, [["conv", "bn", "relu"]], config_manager=cfg)
+    if args.channels_last:
+        model.to(memory_format=torch.channels_last)
 
     # the same GLOBAL set of batches at every world size; rank r takes batches r, r+world, ...
     def batch(i):
@@ -98,7 +103,8 @@ def main():
     bn0 = next(m for m in model.modules() if hasattr(m, "bn")).bn
     if rank == 0:
         print(json.dumps({"model": f"yolov8{args.model}", "n_gpus": world, "global_batches": args.batches,
-                          "batch": args.batch, "imgsz": args.imgsz, "observer_rows_synced": rows,
+                          "batch": args.batch, "imgsz": args.imgsz, "channels_last": args.channels_last,
+                          "observer_rows_synced": rows,
                           "calibration_s": t_cal, "calibration_images_per_s": args.batches * args.batch / t_cal,
                           "bn_reestimate_s": t_bn, "bn_reestimate_images_per_s": args.batches * args.batch / t_bn,
                           "vsiq_launches_calibration": launches_cal,

@@ -209,6 +209,34 @@ def run(args) -> dict:
         def step(i):  # noqa: F811
             imgs = cl(host[i % 2].to(device, non_blocking=True).float() / 255.0)
             return float(graphed(imgs).item())
+    # fake-quant traffic of one step (20 algorithmic bytes per quantised element, forward + backward):
+    # every weight tensor plus every tensor an activation quantiser sees, counted by hooks during one eager forward
+    fq_elems = {"w": 0, "a": 0}
+    wrapped = []
+
+    def counting(mgr, kind):
+        orig = mgr.quantize
+
+        def quantize(x, *a, **kw):
+            y = orig(x, *a, **kw)
+            if mgr.is_quantize:
+                fq_elems[kind] += y.numel()
+            return y
+        mgr.quantize = quantize
+        wrapped.append(mgr)
+    for mod in model.modules():
+        if hasattr(mod, "weight_quantizer") and hasattr(mod, "activation_quantizer"):
+            counting(mod.weight_quantizer, "w")
+            counting(mod.activation_quantizer, "a")
+    with torch.no_grad():
+        bank_on = bank.enabled if bank is not None else False
+        if bank is not None:
+            bank.enabled = False
+        model(cl(host[0].to(device).float() / 255.0))
+        if bank is not None:
+            bank.enabled = bank_on
+    for mgr in wrapped:
+        del mgr.quantize
     for i in range(max(args.warmup, 3)):
         step(i)
     if world > 1:
@@ -240,6 +268,16 @@ def run(args) -> dict:
            "calibration_s": calib_s, "calib_batches": args.calib_batches,
            "h2d_bytes_per_step": args.batch * 3 * args.imgsz * args.imgsz, "d2h_bytes_per_step": 4,
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    peak = 6531.9
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    fq_bytes = 20.0 * (fq_elems["w"] + fq_elems["a"])
+    res["fake_quant"] = {"weight_elements": fq_elems["w"], "activation_elements": fq_elems["a"],
+                         "algorithmic_gb_per_step_per_gpu": fq_bytes / 1e9, "hbm_peak_gbs": peak,
+                         "hbm_floor_ms_per_step": fq_bytes / peak / 1e6,
+                         "floor_fraction_of_step": fq_bytes / peak / 1e6 / (ms / args.steps)}
     return res
 
 

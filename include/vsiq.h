@@ -223,6 +223,15 @@ int vsiq_ci_lsq_bwd(const float *x, const float *bias, const float *g, float *dx
                     int64_t qp_channels, double grad_scale_host, const float *grad_scale_dev, int64_t g_row_pitch,
                     void *workspace, size_t workspace_bytes, vsiq_stream_t stream);
 
+/* Per-channel observer on a channel-innermost tensor [rows, channels]: the same outputs as vsiq_observe with
+ * layout {outer = N, channels, inner = H*W} on the NCHW-permuted tensor (stats[c] / state[c]; min / max exact, sums to
+ * summation order), in one read of the NHWC memory -- the moments pass of reestimate_BN_stats
+ * (utils/estimate_bn.py:82) and per-channel activation calibration under torch.channels_last.
+ * channels % 4 == 0, <= 1024, 16-byte aligned x; else VSIQ_ERR_UNSUPPORTED.  Two launches (stream pass + combine). */
+size_t vsiq_ci_observe_workspace_bytes(int64_t rows, int64_t channels);
+int vsiq_ci_observe(const float *x, int64_t rows, int64_t channels, double *stats, double *state, int bits,
+                    int symmetric, double eps, void *workspace, size_t workspace_bytes, vsiq_stream_t stream);
+
 /* ---- multi-tensor weight path ("weight bank") ---------------------------------------------
  * Every fused layer fake-quantises its (small) weight tensor each step: FakeQuantize.quantize_weights
  * (quantizers/fake_quantize.py:62-63) -> QuantizationManager.quantize (quantization_manager.py:73-90) ->

@@ -480,3 +480,33 @@ def test_channels_inner_strided_grad_output(ops):
     c = ops.ci_backward(x, b, g_view.contiguous(memory_format=torch.channels_last), s, z, spec, 0.01, None, True, True, True)
     for u, w in zip(a, c):
         assert torch.equal(u, w)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 5, 7), (3, 64, 33, 17), (2, 300, 9, 9), (1, 1024, 3, 5), (64, 32, 40, 40)])
+def test_ci_observe_matches_nchw_observer(shape):
+    """vsiq_ci_observe (per-channel statistics on channels_last memory) against vsiq_observe on the NCHW tensor and the
+    oracle: extrema bit-exact (NaN channel included), sums to 2e-6 relative (both kernels add <= 16 elements in fp32
+    before the fp64 accumulation, in different groupings; the BN-moment bar is 1e-5)."""
+    from vsiquantization_b200 import ops
+    torch.manual_seed(11)
+    x = torch.randn(shape, device="cuda") * 3 + 0.5
+    if shape[1] >= 8:
+        x[0, 3, 0, 0] = float("nan")
+    xc = x.contiguous(memory_format=torch.channels_last)
+    assert ops.ci_supported(xc)
+    st0 = ops.new_observer_state(shape[1], "cuda")
+    st1 = st0.clone()
+    a = ops.observe(x, ch_axis=1, state=st0, bits=8, symmetric=False)
+    l0 = ops._lib.launch_count
+    b = ops.observe(xc, ch_axis=1, state=st1, bits=8, symmetric=False)
+    assert ops._lib.launch_count - l0 == 2  # the channel-innermost pass + its combine; no layout conversion
+    a, b = a.cpu().numpy(), b.cpu().numpy()
+    assert np.array_equal(a[:, :2], b[:, :2], equal_nan=True)
+    mass = np.abs(x.cpu().numpy()).sum(axis=(0, 2, 3))[:, None]
+    np.testing.assert_allclose(b[:, 2:4], a[:, 2:4], rtol=0, atol=float(2e-6 * np.nanmax(mass)))
+    np.testing.assert_allclose(b[:, 4], a[:, 4], rtol=2e-6)
+    so = oracle.minmax_stats(x.cpu().numpy(), ch_axis=1)
+    assert np.array_equal(b[:, :2], so[:, :2], equal_nan=True)
+    s0, s1 = st0.cpu().numpy(), st1.cpu().numpy()
+    assert np.array_equal(s0[:, :5], s1[:, :5], equal_nan=True)  # running extrema, scale, zero-point, call count
+    np.testing.assert_allclose(s1[:, 5:], s0[:, 5:], rtol=1e-5, atol=1e-6)

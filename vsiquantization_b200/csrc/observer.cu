@@ -11,7 +11,7 @@
 //   BN re-estimation  utils/estimate_bn.py:56-99 (batch mean / UNBIASED batch var, summed, / count)
 //
 // Roofline: HBM, 4 algorithmic bytes per element (one read of x; the reference makes five passes).
-#include "common.cuh"
+#include "ci_common.cuh"
 
 namespace vsiq {
 
@@ -317,6 +317,135 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-channel statistics of a CHANNEL-INNERMOST tensor ([rows = N*H*W][C], torch.channels_last): the observer pass of
+// BN re-estimation (utils/estimate_bn.py:82) and of per-channel activation calibration without converting the conv
+// output back to NCHW first (a conversion costs a read and a write of the tensor, this pass one read).  Same mapping as
+// channels_inner.cu: thread t owns channel group t % G for the whole kernel, persistent CTAs steal tiles from the
+// look-ahead queue, one record [5][C] per CTA, records combined per channel in a fixed order by ci_observe_finalize.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCiObsFields = 5;  // min, max, sum|x|, sum x, sum x^2   (a NaN in the channel turns min and max into NaN)
+
+__global__ void __launch_bounds__(kThreads, 3)
+    ci_observe_kernel(const float* __restrict__ x, CiGeom geo, void* ws) {
+    __shared__ double s_acc[kCiObsFields * kCiVec][kThreads];  // [field * 4 + e][thread]: conflict-free columns
+    unsigned int* counter = (unsigned int*)ws + 1;
+    double* records = ws_partials(ws);
+    const int t = threadIdx.x;
+    const bool active = t < geo.threads;
+    float mn[kCiVec], mx[kCiVec];
+    bool nan[kCiVec];
+    double sa[kCiVec], s1[kCiVec], s2[kCiVec];
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        mn[e] = INFINITY;
+        mx[e] = -INFINITY;
+        nan[e] = false;
+        sa[e] = s1[e] = s2[e] = 0.0;
+    }
+    __shared__ uint32_t s_tile[2];
+    TileQueue tq;
+    tq_init(tq, counter, geo.n_tiles, s_tile);
+    constexpr int kU = 2 * kCiUnroll, kB = kCiBatches / 2;  // one input: twice the loads in flight
+    for (uint32_t tile = tq_current(tq, s_tile); tile < geo.n_tiles; tq_advance(tq, s_tile), tile = tq_current(tq, s_tile)) {
+        if (!active) continue;
+        const int64_t vb = (int64_t)tile * geo.tile_vecs;
+        float fa[kCiVec], f1[kCiVec], f2[kCiVec];  // fp32 partials of this tile (16 elements per channel per thread)
+#pragma unroll
+        for (int e = 0; e < kCiVec; ++e) fa[e] = f1[e] = f2[e] = 0.0f;
+#pragma unroll 1
+        for (int b = 0; b < kB; ++b) {
+            Vec4 vin[kU];
+            bool ok[kU];
+#pragma unroll
+            for (int j = 0; j < kU; ++j) {
+                const int64_t v = vb + (int64_t)(b * kU + j) * geo.threads + t;
+                ok[j] = v < geo.n_vec;
+                if (ok[j]) vin[j] = ld4(x + v * kCiVec);
+            }
+#pragma unroll
+            for (int j = 0; j < kU; ++j) {
+                if (!ok[j]) continue;
+#pragma unroll
+                for (int e = 0; e < kCiVec; ++e) {
+                    const float xv = vin[j].v[e];
+                    nan[e] = nan[e] || (xv != xv);
+                    mn[e] = fminf(mn[e], xv);
+                    mx[e] = fmaxf(mx[e], xv);
+                    fa[e] += fabsf(xv);
+                    f1[e] += xv;
+                    f2[e] = fmaf(xv, xv, f2[e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < kCiVec; ++e) {
+            sa[e] += (double)fa[e];
+            s1[e] += (double)f1[e];
+            s2[e] += (double)f2[e];
+        }
+    }
+    // ---- one record per CTA: fixed-order reduction over the threads that share a channel group
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        s_acc[0 * kCiVec + e][t] = active ? (double)(nan[e] ? NAN : mn[e]) : (double)INFINITY;
+        s_acc[1 * kCiVec + e][t] = active ? (double)(nan[e] ? NAN : mx[e]) : (double)-INFINITY;
+        s_acc[2 * kCiVec + e][t] = active ? sa[e] : 0.0;
+        s_acc[3 * kCiVec + e][t] = active ? s1[e] : 0.0;
+        s_acc[4 * kCiVec + e][t] = active ? s2[e] : 0.0;
+    }
+    __syncthreads();
+    const int C = geo.channels;
+    const int reps = geo.threads / geo.groups;
+    double* rec = records + (size_t)blockIdx.x * kCiObsFields * C;
+    for (int idx = t; idx < kCiObsFields * C; idx += kThreads) {
+        const int field = idx / C, c = idx - field * C;
+        const double* col = s_acc[field * kCiVec + (c % kCiVec)];
+        const int g0 = c / kCiVec;
+        double v = col[g0];
+        for (int k = 1; k < reps; ++k) {
+            const double u = col[k * geo.groups + g0];
+            if (field == 0) v = (v != v) ? v : ((u != u) ? u : (u < v ? u : v));
+            else if (field == 1) v = (v != v) ? v : ((u != u) ? u : (u > v ? u : v));
+            else v += u;
+        }
+        rec[idx] = v;
+    }
+    // the last CTA to leave resets the ticket and the tile counter for the next launch
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
+        if (tk == gridDim.x - 1) {
+            *(unsigned int*)ws = 0;
+            *counter = 0;
+        }
+    }
+}
+
+// one warp per channel: lanes stride over the per-CTA records (fixed order), then shuffle-reduce
+__global__ void __launch_bounds__(kThreads)
+    ci_observe_finalize_kernel(const void* ws, int C, uint32_t n_rec, ObserveOut o) {
+    const double* records = (const double*)((const char*)ws + kWsHeader);
+    const int lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * kWarps + (threadIdx.x >> 5); c < C; c += gridDim.x * kWarps) {
+        float mn = INFINITY, mx = -INFINITY;
+        double sa = 0.0, s1 = 0.0, s2 = 0.0;
+        for (uint32_t r = lane; r < n_rec; r += 32) {
+            const double* rec = records + (size_t)r * kCiObsFields * C + c;
+            mn = nanmin(mn, (float)__ldcg(rec));
+            mx = nanmax(mx, (float)__ldcg(rec + C));
+            sa += __ldcg(rec + 2 * C);
+            s1 += __ldcg(rec + 3 * C);
+            s2 += __ldcg(rec + 4 * C);
+        }
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        sa = warp_sum(sa);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) observe_store_channel(o, c, mn, mx, sa, s1, s2);
+    }
+}
+
 // MODE 0: thread per channel, 1: warp per channel, 2: CTA per channel
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
@@ -507,6 +636,42 @@ extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* s
         if (vec8) CALL(kThreads, 8) else CALL(kThreads, 1)
     }
 #undef CALL
+    return (int)cudaGetLastError();
+}
+
+extern "C" size_t vsiq_ci_observe_workspace_bytes(int64_t rows, int64_t channels) {
+    (void)rows;
+    DeviceProps dp;
+    int sms = 148;
+    if (get_device_props(&dp) == 0) sms = dp.sm_count;
+    return kWsHeader + (size_t)sms * 3 * (size_t)(kCiObsFields * channels) * sizeof(double);
+}
+
+extern "C" int vsiq_ci_observe(const float* x, int64_t rows, int64_t channels, double* stats, double* state, int bits,
+                               int symmetric, double eps, void* workspace, size_t workspace_bytes,
+                               vsiq_stream_t stream) {
+    if (!x || (!stats && !state) || rows <= 0) return VSIQ_ERR_INVALID_ARG;
+    if (state && (bits < 2 || bits > 8)) return VSIQ_ERR_INVALID_ARG;
+    CiGeom geo;
+    if (!make_ci_geom(rows, channels, &geo)) return VSIQ_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(x) & 15u) return VSIQ_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < vsiq_ci_observe_workspace_bytes(rows, channels)) return VSIQ_ERR_WORKSPACE;
+    DeviceProps dp;
+    if (int e = get_device_props(&dp)) return e;
+    const uint32_t cap = (uint32_t)dp.sm_count * 3u;
+    const uint32_t grid = geo.n_tiles < cap ? geo.n_tiles : cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    ObserveOut oo;
+    oo.stats = stats;
+    oo.state = state;
+    oo.bits = bits;
+    oo.symmetric = symmetric;
+    oo.eps = eps;
+    oo.count = (double)rows;
+    ci_observe_kernel<<<grid, kThreads, 0, st>>>(x, geo, workspace);
+    if (cudaError_t err = cudaGetLastError()) return (int)err;
+    const int fgrid = (int)((channels + kWarps - 1) / kWarps);
+    ci_observe_finalize_kernel<<<fgrid, kThreads, 0, st>>>(workspace, (int)channels, grid, oo);
     return (int)cudaGetLastError();
 }
 

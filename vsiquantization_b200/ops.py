@@ -369,6 +369,8 @@ def observe(x: torch.Tensor, ch_axis: Optional[int] = None, state: Optional[torc
     """One pass: per-channel {min, max, sum|x|, sum x, sum x^2} (+ running observer state, scale, zero-point).
 
     Replaces observers/minmax.py:42-47,67-74 and quantization_manager.py:66-68.  No host sync."""
+    if ch_axis == 1 and ci_supported(x):
+        return _ci_observe(x, state, bits, symmetric, eps, want_stats)  # per-channel statistics on NHWC memory in place
     x = _dense_for(x, "x", ch_axis)
     outer, C, inner = layout_of(x.shape, ch_axis)
     lay = Layout(outer, C, inner)
@@ -383,6 +385,23 @@ def observe(x: torch.Tensor, ch_axis: Optional[int] = None, state: Optional[torc
                                state.data_ptr() if state is not None else None, int(bits), int(bool(symmetric)),
                                float(eps), ws.data_ptr(), ws.numel(), _stream_ptr()), "vsiq_observe")
         _count_launch()
+    return stats
+
+
+def _ci_observe(x, state, bits, symmetric, eps, want_stats):
+    N, C, H, W = x.shape
+    rows = N * H * W
+    with torch.cuda.device(x.device):
+        stats = torch.empty(C, _lib.STATS_WIDTH, dtype=torch.float64, device=x.device) if want_stats else None
+        if state is not None:
+            if state.dtype != torch.float64 or not state.is_cuda or state.numel() != C * _lib.STATE_WIDTH \
+                    or not state.is_contiguous():
+                raise ValueError("observer state must be a contiguous CUDA float64 tensor [channels, 8]")
+        ws = _workspace(lib.vsiq_ci_observe_workspace_bytes(rows, C), x.device)
+        check(lib.vsiq_ci_observe(x.data_ptr(), rows, C, stats.data_ptr() if want_stats else None,
+                                  state.data_ptr() if state is not None else None, int(bits), int(bool(symmetric)),
+                                  float(eps), ws.data_ptr(), ws.numel(), _stream_ptr()), "vsiq_ci_observe")
+        _count_launch(2)
     return stats
 
 
