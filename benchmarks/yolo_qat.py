@@ -162,10 +162,10 @@ def run(args) -> dict:
     if args.weight_bank and args.quant_impl == "native":
         from vsiquantization_b200.bank import WeightBank
         # under DDP every layer keeps its own backward node so the gradient all-reduce still overlaps the backward pass
-        bank = WeightBank(model, backward="per_layer" if world > 1 else "bank").install()
+        bank = WeightBank(model, backward="per_layer" if (world > 1 and not args.cuda_graph) else "bank").install()
     bucket = None
     net = model
-    if world > 1:
+    if world > 1 and not args.cuda_graph:
         from torch.nn.parallel import DistributedDataParallel as DDP
         if args.quant_impl == "native":
             from vsiquantization_b200.parallel import QParamGradBucket
@@ -200,8 +200,7 @@ def run(args) -> dict:
 
     bucket_params = set(bucket.params) if bucket is not None else set()
     if args.cuda_graph:
-        if world > 1:
-            raise SystemExit("--cuda-graph is single-GPU for now (DDP's bucketed all-reduce is not captured)")
+        # world > 1: no DDP wrapper -- the graphed step all-reduces one flat gradient buffer inside the captured graph
         from vsiquantization_b200.graph import GraphedQATStep
         graphed = GraphedQATStep(model, opt, lambda outs: sum((o.float() ** 2).mean() for o in outs),
                                  cl(host[0].to(device).float() / 255.0))

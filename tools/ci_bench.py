@@ -23,6 +23,7 @@ for shp in shapes:
         ("flat lsq pt", 12, lambda: ops.lsq_backward(x, g, s_t, 0, pt, 1e-3)),
         ("ci lsq pt+b", 12, lambda: ops.ci_backward(x, b, g, s_t, 0, pt, 1e-3)),
         ("ci lsq pc+b", 12, lambda: ops.ci_backward(x, b, g, sc, zc, pc, 1e-3, None, True, True, True)),
+        ("ci observe", 4, lambda: ops.observe(x, ch_axis=1)),
         ("sum(0,2,3)", 4, lambda: g.sum((0, 2, 3))),
     ]
     line = f"{str(shp):22s} {n/1e6:6.1f}M "

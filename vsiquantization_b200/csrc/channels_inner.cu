@@ -16,6 +16,8 @@
 // and flushed ONCE per CTA; records are combined in a fixed order (deterministic) by the last CTA or a finalize launch.
 //
 // Roofline: HBM; 8 B/element forward, 12 B/element backward, as for the NCHW kernels.
+#include <stdlib.h>
+
 #include "ci_common.cuh"
 
 namespace vsiq {
@@ -58,6 +60,17 @@ __device__ __forceinline__ void ci_store(const CiOut& o, const QPDev& qpd, bool 
 // Combine 32 consecutive record entries [base, base+32) over n_rec per-CTA records: warp w sums records w, w+8, ...
 // (each read is one coalesced 256-byte row segment, four independent chains per thread), then the eight slices are
 // added in a fixed order.  Deterministic.  s_part: [kWarps][32] doubles of shared memory.
+// CTA-wide barrier over the first kThreads threads: plain __syncthreads() for 256-thread CTAs, named barrier 1 when a
+// producer warp rides along (ci_bwd_tma_kernel) and must not take part.
+template <bool NAMED>
+__device__ __forceinline__ void ci_sync() {
+    if (NAMED)
+        asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    else
+        __syncthreads();
+}
+
+template <bool NAMED = false>
 __device__ __forceinline__ void ci_combine_chunk(const double* records, int width, uint32_t n_rec, int base,
                                                  double (*s_part)[32], const CiOut& o, const QPDev& qpd, bool pcq,
                                                  bool bias, int C) {
@@ -74,9 +87,9 @@ __device__ __forceinline__ void ci_combine_chunk(const double* records, int widt
         }
         for (; r < n_rec; r += kWarps) a0 += __ldcg(records + (size_t)r * width + idx);
     }
-    __syncthreads();
+    ci_sync<NAMED>();
     s_part[warp][lane] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
+    ci_sync<NAMED>();
     if (warp == 0 && idx < width) {
         double v = 0.0;
 #pragma unroll
@@ -240,6 +253,105 @@ __device__ __forceinline__ void ci_bwd_tile(const float* __restrict__ x, const f
     }
 }
 
+// One flush per CTA: fixed-order reduction over the threads that share a channel group, record write, ticket, and (last
+// CTA, narrow records) the combine.  Runs in the first kThreads threads of the CTA; s_acc is [kThreads][12] doubles.
+template <bool PCQ, bool BIAS, bool WANT_DS, bool NAMED>
+__device__ __forceinline__ void ci_bwd_flush(const double (&acc_e)[kCiVec], const double (&acc_b)[kCiVec],
+                                             const double (&acc_db)[kCiVec], double (*s_acc)[3 * kCiVec],
+                                             const CiGeom& geo, const QPDev& qpd, void* ws, const CiOut& o,
+                                             int use_ticket, int t, bool active) {
+    unsigned int* counter = (unsigned int*)ws + 1;
+    double* records = ws_partials(ws);
+    const int C = geo.channels;
+    const uint32_t n_ctas = gridDim.x, cta = blockIdx.x;
+    // ---- one flush per CTA: fixed-order reduction over the threads that share a channel group ----
+    if (!WANT_DS && !BIAS) {
+        __shared__ int s_last0;
+        if (threadIdx.x == 0) {
+            unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
+            s_last0 = (tk == n_ctas - 1);
+            if (s_last0) {
+                *(unsigned int*)ws = 0;
+                *counter = 0;
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        s_acc[t][e] = active ? acc_e[e] : 0.0;
+        s_acc[t][kCiVec + e] = active ? acc_b[e] : 0.0;
+        s_acc[t][2 * kCiVec + e] = active ? acc_db[e] : 0.0;
+    }
+    __shared__ double s_pt[2];
+    if (WANT_DS && !PCQ) {  // per-tensor sums: warp shuffle, then the eight warps in order
+        __shared__ double s_w[kWarps][2];
+        double e = 0.0, b = 0.0;
+        if (active) {
+            e = (acc_e[0] + acc_e[1]) + (acc_e[2] + acc_e[3]);
+            b = (acc_b[0] + acc_b[1]) + (acc_b[2] + acc_b[3]);
+        }
+        e = warp_sum(e);
+        b = warp_sum(b);
+        if ((t & 31) == 0) {
+            s_w[t >> 5][0] = e;
+            s_w[t >> 5][1] = b;
+        }
+        ci_sync<NAMED>();
+        if (t == 0) {
+            double es = 0.0, bs = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                es += s_w[w][0];
+                bs += s_w[w][1];
+            }
+            s_pt[0] = es;
+            s_pt[1] = bs;
+        }
+    }
+    ci_sync<NAMED>();
+    const int nq = PCQ ? C : 1;
+    const int width = 2 * nq + (BIAS ? C : 0);
+    double* rec = records + (size_t)cta * width;
+    const int reps = geo.threads / geo.groups;
+    for (int idx = t; idx < width; idx += kThreads) {
+        double s = 0.0;
+        if (idx < 2 * nq) {
+            const int which = idx < nq ? 0 : 1;
+            if (WANT_DS) {
+                if (PCQ) {
+                    const int c = idx - which * nq;
+                    for (int k = 0; k < reps; ++k) s += s_acc[k * geo.groups + c / kCiVec][which * kCiVec + (c % kCiVec)];
+                } else {
+                    s = s_pt[which];  // block-reduced below
+                }
+            }
+        } else {
+            const int c = idx - 2 * nq;
+            for (int k = 0; k < reps; ++k) s += s_acc[k * geo.groups + c / kCiVec][2 * kCiVec + (c % kCiVec)];
+        }
+        rec[idx] = s;
+    }
+    // ticket; the last CTA also resets the tile counter
+    __shared__ int s_last;
+    __threadfence();
+    ci_sync<NAMED>();
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
+        s_last = (tk == n_ctas - 1);
+        if (s_last) {
+            *(unsigned int*)ws = 0;
+            *counter = 0;
+        }
+    }
+    ci_sync<NAMED>();
+    if (!s_last || !use_ticket) return;
+    __threadfence();
+    double(*s_part)[32] = reinterpret_cast<double(*)[32]>(&s_acc[0][0]);  // s_acc is free again
+    for (int base = 0; base < width; base += 32)
+        ci_combine_chunk<NAMED>(records, width, n_ctas, base, s_part, o, qpd, PCQ, BIAS, C);
+}
+
 template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
 __global__ void __launch_bounds__(kThreads, 2)
     ci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ g,
@@ -295,92 +407,227 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
     }
 
-    // ---- one flush per CTA: fixed-order reduction over the threads that share a channel group ----
-    if (!WANT_DS && !BIAS) {
-        __shared__ int s_last0;
-        if (threadIdx.x == 0) {
-            unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
-            s_last0 = (tk == gridDim.x - 1);
-            if (s_last0) {
-                *(unsigned int*)ws = 0;
-                *counter = 0;
+    ci_bwd_flush<PCQ, BIAS, WANT_DS, false>(acc_e, acc_b, acc_db, s_acc, geo, qpd, ws, o, use_ticket, t, active);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward with TMA-staged inputs (dense grad_output).  ncu on ci_bwd_kernel: the warps wait on global loads
+// ("long scoreboard" is the top stall, issue slots 58 % used) while 128 registers per thread cap the CTA count at two, so
+// neither more warps nor more loads per thread are available.  Here a producer warp streams x and g through a ring of
+// kCiStages shared-memory stages with bulk asynchronous copies (cp.async.bulk -> mbarrier complete_tx), the eight
+// consumer warps read 128-bit vectors from shared memory: bytes in flight per SM no longer cost registers, and the
+// consumers never touch a global load.  One stage = one batch (T * kCiUnroll vectors, <= 16 KB per input), units of a
+// tile arrive in order; tiles come from the same atomic queue as before (claimed by the producer).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCiStages = 3;
+constexpr uint32_t kCiNoTile = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ Vec4 lds4(const float* p) {
+    Vec4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+                 : "r"(smem_u32(p)));
+    return r;
+}
+
+struct CiRing {
+    uint64_t full[kCiStages];
+    uint64_t empty[kCiStages];
+    uint32_t tile[kCiStages];   // tile of the unit parked in the stage (kCiNoTile: no more work)
+    uint32_t batch[kCiStages];  // its batch index inside the tile
+};
+
+template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
+__global__ void __launch_bounds__(kThreads + 32, 2)
+    ci_bwd_tma_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ g,
+                      float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket) {
+    extern __shared__ __align__(128) unsigned char ci_smem[];  // kCiStages x [x unit | g unit]; later the flush scratch
+    __shared__ CiRing ring;
+    unsigned int* counter = (unsigned int*)ws + 1;
+    const int t = threadIdx.x;
+    const int unit_vecs = geo.threads * kCiUnroll;          // vectors per unit (per input)
+    const uint32_t unit_bytes = (uint32_t)unit_vecs * 16u;  // <= 16 KB
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < kCiStages; ++s) {
+            mbar_init(&ring.full[s], 1);        // the producer's arrive (+ the bytes of its two copies)
+            mbar_init(&ring.empty[s], kWarps);  // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (t >= kThreads) {  // ---------------------------------------------------------------- producer warp
+        if (t == kThreads) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (;;) {
+                const uint32_t tile = atomicAdd(counter, 1u);
+                const bool done = tile >= geo.n_tiles;
+                const int n_units = done ? 1 : kCiBatches;
+                for (int b = 0; b < n_units; ++b) {
+                    mbar_wait(&ring.empty[stage], phase ^ 1u);  // the consumers have drained this stage
+                    ring.tile[stage] = done ? kCiNoTile : tile;
+                    ring.batch[stage] = (uint32_t)b;
+                    int64_t v0 = 0, nv = 0;
+                    if (!done) {
+                        v0 = (int64_t)tile * geo.tile_vecs + (int64_t)b * unit_vecs;
+                        nv = geo.n_vec - v0;
+                        nv = nv < 0 ? 0 : (nv > unit_vecs ? unit_vecs : nv);
+                    }
+                    if (nv > 0) {
+                        const uint32_t bytes = (uint32_t)nv * 16u;
+                        unsigned char* xs = ci_smem + (size_t)stage * 2 * unit_bytes;
+                        mbar_arrive_expect_tx(&ring.full[stage], 2 * bytes);
+                        bulk_load(xs, x + v0 * kCiVec, bytes, &ring.full[stage]);
+                        bulk_load(xs + unit_bytes, g + v0 * kCiVec, bytes, &ring.full[stage]);
+                    } else {
+                        mbar_arrive(&ring.full[stage]);
+                    }
+                    if (++stage == kCiStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (done) break;
             }
         }
-        return;
+        return;  // the producer warp takes no part in the flush (named barrier over the consumer threads)
     }
+
+    // -------------------------------------------------------------------------------------- consumer warps
+    const bool active = t < geo.threads;
+    const int c0 = (t % geo.groups) * kCiVec;
+    QP p[kCiVec];
+    float bv[kCiVec];
+    bool all_fast = true;
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
-        s_acc[t][e] = active ? acc_e[e] : 0.0;
-        s_acc[t][kCiVec + e] = active ? acc_b[e] : 0.0;
-        s_acc[t][2 * kCiVec + e] = active ? acc_db[e] : 0.0;
+        p[e] = load_qp(qpd, PCQ ? c0 + e : 0);
+        all_fast = all_fast && p[e].fast;
+        bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
     }
-    __shared__ double s_pt[2];
-    if (WANT_DS && !PCQ) {  // per-tensor sums: warp shuffle, then the eight warps in order
-        __shared__ double s_w[kWarps][2];
-        double e = 0.0, b = 0.0;
-        if (active) {
-            e = (acc_e[0] + acc_e[1]) + (acc_e[2] + acc_e[3]);
-            b = (acc_b[0] + acc_b[1]) + (acc_b[2] + acc_b[3]);
-        }
-        e = warp_sum(e);
-        b = warp_sum(b);
-        if ((t & 31) == 0) {
-            s_w[t >> 5][0] = e;
-            s_w[t >> 5][1] = b;
-        }
-        __syncthreads();
-        if (t == 0) {
-            double es = 0.0, bs = 0.0;
+    double acc_e[kCiVec], acc_b[kCiVec], acc_db[kCiVec];
+    float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials of the current tile
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                es += s_w[w][0];
-                bs += s_w[w][1];
-            }
-            s_pt[0] = es;
-            s_pt[1] = bs;
-        }
+    for (int e = 0; e < kCiVec; ++e) {
+        acc_e[e] = acc_b[e] = acc_db[e] = 0.0;
+        te[e] = tb[e] = tdb[e] = 0.0f;
     }
-    __syncthreads();
-    const int nq = PCQ ? C : 1;
-    const int width = 2 * nq + (BIAS ? C : 0);
-    double* rec = records + (size_t)blockIdx.x * width;
-    const int reps = geo.threads / geo.groups;
-    for (int idx = t; idx < width; idx += kThreads) {
-        double s = 0.0;
-        if (idx < 2 * nq) {
-            const int which = idx < nq ? 0 : 1;
-            if (WANT_DS) {
-                if (PCQ) {
-                    const int c = idx - which * nq;
-                    for (int k = 0; k < reps; ++k) s += s_acc[k * geo.groups + c / kCiVec][which * kCiVec + (c % kCiVec)];
-                } else {
-                    s = s_pt[which];  // block-reduced below
+    int stage = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        mbar_wait(&ring.full[stage], phase);  // the unit's bytes have landed (or there is nothing left)
+        const uint32_t tile = ring.tile[stage];
+        if (tile == kCiNoTile) break;
+        const uint32_t b = ring.batch[stage];
+        const float* xs = (const float*)(ci_smem + (size_t)stage * 2 * unit_bytes);
+        const float* gs = (const float*)(ci_smem + (size_t)stage * 2 * unit_bytes + unit_bytes);
+        const int64_t v0 = (int64_t)tile * geo.tile_vecs + (int64_t)b * unit_vecs;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < kCiUnroll; ++j) {
+                const int u = j * geo.threads + t;
+                const int64_t v = v0 + u;
+                if (v >= geo.n_vec) continue;
+                const Vec4 vx = lds4(xs + (size_t)u * kCiVec);
+                const Vec4 vg = lds4(gs + (size_t)u * kCiVec);
+                Vec4 out;
+                float ve[kCiVec], vbz[kCiVec];
+                bool bad = !all_fast;
+#pragma unroll
+                for (int e = 0; e < kCiVec; ++e) {
+                    const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
+                    const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+                    const float ge = vg.v[e];
+                    const Elem el = elem_fast(xe, p[e], bad);
+                    float d = dx_fast(ge, el.m, p[e], bad);
+                    if (RELU) d = xb > 0.0f ? d : 0.0f;
+                    out.v[e] = d;
+                    if (WANT_DS) {
+                        const float dd = __fsub_rn(el.q, p[e].z);
+                        const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
+                        ve[e] = ge * (dd - mv);
+                        vbz[e] = el.m ? 0.0f : ge;
+                    }
                 }
+                if (bad) {  // rare: IEEE sequences for the whole vector
+#pragma unroll
+                    for (int e = 0; e < kCiVec; ++e) {
+                        const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
+                        const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+                        const float ge = vg.v[e];
+                        const Elem el = elem_slow(xe, p[e]);
+                        float d = dx_slow(ge, el.m, p[e]);
+                        if (RELU) d = xb > 0.0f ? d : 0.0f;
+                        out.v[e] = d;
+                        if (WANT_DS) {
+                            const float dd = __fsub_rn(el.q, p[e].z);
+                            const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
+                            ve[e] = ge * (dd - mv);
+                            vbz[e] = el.m ? 0.0f : ge;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < kCiVec; ++e) {
+                    if (WANT_DS) {
+                        te[e] += ve[e];
+                        tb[e] += vbz[e];
+                    }
+                    if (BIAS) tdb[e] += out.v[e];
+                }
+                st4(dx + v * kCiVec, out);
             }
-        } else {
-            const int c = idx - 2 * nq;
-            for (int k = 0; k < reps; ++k) s += s_acc[k * geo.groups + c / kCiVec][2 * kCiVec + (c % kCiVec)];
         }
-        rec[idx] = s;
-    }
-    // ticket; the last CTA also resets the tile counter
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
-        s_last = (tk == gridDim.x - 1);
-        if (s_last) {
-            *(unsigned int*)ws = 0;
-            *counter = 0;
+        __syncwarp();
+        if ((t & 31) == 0) mbar_arrive(&ring.empty[stage]);  // this warp has read everything it needs from the stage
+        if (b == kCiBatches - 1) {  // tile complete: fold its fp32 partials into the fp64 running sums
+#pragma unroll
+            for (int e = 0; e < kCiVec; ++e) {
+                if (WANT_DS) {
+                    acc_e[e] += (double)te[e];
+                    acc_b[e] += (double)tb[e];
+                }
+                if (BIAS) acc_db[e] += (double)tdb[e];
+                te[e] = tb[e] = tdb[e] = 0.0f;
+            }
+        }
+        if (++stage == kCiStages) {
+            stage = 0;
+            phase ^= 1u;
         }
     }
-    __syncthreads();
-    if (!s_last || !use_ticket) return;
-    __threadfence();
-    double(*s_part)[32] = reinterpret_cast<double(*)[32]>(&s_acc[0][0]);  // s_acc is free again
-    for (int base = 0; base < width; base += 32)
-        ci_combine_chunk(records, width, gridDim.x, base, s_part, o, qpd, PCQ, BIAS, C);
+    // every copy has landed and been consumed: the ring's memory is free for the flush scratch
+    ci_sync<true>();
+    ci_bwd_flush<PCQ, BIAS, WANT_DS, true>(acc_e, acc_b, acc_db, reinterpret_cast<double(*)[3 * kCiVec]>(ci_smem), geo, qpd,
+                                           ws, o, use_ticket, t, active);
 }
 
 static int ci_grid(uint32_t n_tiles, uint32_t ctas_per_sm) {
@@ -465,9 +712,33 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
     o.gs_dev = grad_scale_dev;
     const int width = 2 * (pcq ? (int)channels : 1) + (hb ? (int)channels : 0);
     const int use_ticket = width <= 64 ? 1 : 0;  // wider records: one finalize CTA per 32 entries instead
-#define B(P, H, R, D) \
-    ci_bwd_kernel<P, H, R, D><<<grid, kThreads, 0, st>>>(x, bias, g, dx, geo, qpd, workspace, o, use_ticket, g_row_pitch)
-#define B3(P, H, R) { if (want_ds) B(P, H, R, true); else B(P, H, R, false); }
+    // dense grad_output: inputs staged through shared memory by bulk asynchronous copies (ci_bwd_tma_kernel); a pitched
+    // grad_output (channel slice of a wider NHWC tensor) keeps the direct-load kernel.  VSIQ_CI_TMA=0 forces the latter.
+    static const bool tma_enabled = []() { const char* e = getenv("VSIQ_CI_TMA"); return !(e && e[0] == '0'); }();
+    const bool use_tma = tma_enabled && g_row_pitch == channels;
+    int cur_dev = 0;
+    if (use_tma && (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64)) return VSIQ_ERR_NO_DEVICE;
+    const size_t ring_bytes = (size_t)kCiStages * 2 * (size_t)geo.threads * kCiUnroll * 16;
+    const size_t flush_bytes = sizeof(double) * kThreads * 3 * kCiVec;
+    const size_t dyn_smem = ring_bytes > flush_bytes ? ring_bytes : flush_bytes;
+#define B(P, H, R, D)                                                                                                      \
+    {                                                                                                                      \
+        if (use_tma) {                                                                                                     \
+            static bool attr_set[64]; /* opt in to > 48 KB of dynamic shared memory, once per instantiation and device */ \
+            if (!attr_set[cur_dev]) {                                                                                      \
+                cudaError_t ae = cudaFuncSetAttribute(ci_bwd_tma_kernel<P, H, R, D>,                                       \
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * 16384);        \
+                if (ae != cudaSuccess) return (int)ae;                                                                     \
+                attr_set[cur_dev] = true;                                                                                  \
+            }                                                                                                              \
+            ci_bwd_tma_kernel<P, H, R, D><<<grid, kThreads + 32, dyn_smem, st>>>(x, bias, g, dx, geo, qpd, workspace, o,    \
+                                                                                use_ticket);                              \
+        } else {                                                                                                           \
+            ci_bwd_kernel<P, H, R, D><<<grid, kThreads, 0, st>>>(x, bias, g, dx, geo, qpd, workspace, o, use_ticket,        \
+                                                                 g_row_pitch);                                            \
+        }                                                                                                                  \
+    }
+#define B3(P, H, R) { if (want_ds) B(P, H, R, true) else B(P, H, R, false) }
 #define B2(P, H) { if (relu) B3(P, H, true) else B3(P, H, false) }
     if (pcq) { if (hb) B2(true, true) else B2(true, false) } else { if (hb) B2(false, true) else B2(false, false) }
 #undef B2

@@ -335,13 +335,16 @@ __global__ void __launch_bounds__(kThreads, 3)
     const bool active = t < geo.threads;
     float mn[kCiVec], mx[kCiVec];
     bool nan[kCiVec];
-    double sa[kCiVec], s1[kCiVec], s2[kCiVec];
+    // the fp64 running sums live in this thread's column of shared memory (touched once per tile; keeps the kernel at 80
+    // registers = 3 CTAs per SM without spilling)
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
         mn[e] = INFINITY;
         mx[e] = -INFINITY;
         nan[e] = false;
-        sa[e] = s1[e] = s2[e] = 0.0;
+        s_acc[2 * kCiVec + e][t] = 0.0;
+        s_acc[3 * kCiVec + e][t] = 0.0;
+        s_acc[4 * kCiVec + e][t] = 0.0;
     }
     __shared__ uint32_t s_tile[2];
     TileQueue tq;
@@ -380,19 +383,16 @@ __global__ void __launch_bounds__(kThreads, 3)
         }
 #pragma unroll
         for (int e = 0; e < kCiVec; ++e) {
-            sa[e] += (double)fa[e];
-            s1[e] += (double)f1[e];
-            s2[e] += (double)f2[e];
+            s_acc[2 * kCiVec + e][t] += (double)fa[e];
+            s_acc[3 * kCiVec + e][t] += (double)f1[e];
+            s_acc[4 * kCiVec + e][t] += (double)f2[e];
         }
     }
     // ---- one record per CTA: fixed-order reduction over the threads that share a channel group
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
         s_acc[0 * kCiVec + e][t] = active ? (double)(nan[e] ? NAN : mn[e]) : (double)INFINITY;
-        s_acc[1 * kCiVec + e][t] = active ? (double)(nan[e] ? NAN : mx[e]) : (double)-INFINITY;
-        s_acc[2 * kCiVec + e][t] = active ? sa[e] : 0.0;
-        s_acc[3 * kCiVec + e][t] = active ? s1[e] : 0.0;
-        s_acc[4 * kCiVec + e][t] = active ? s2[e] : 0.0;
+        s_acc[1 * kCiVec + e][t] = active ? (double)(nan[e] ? NAN : mx[e]) : (double)-INFINITY;  // sums: already in place
     }
     __syncthreads();
     const int C = geo.channels;

@@ -10,7 +10,13 @@ forward + backward + optimizer step can be captured once and replayed with a sin
 
 Requirements: static shapes, model and qparams on the device, optimizer state created during the warm-up (done here).
 The libvsiq.so launchers make no CUDA API call that is illegal during stream capture (device properties are cached
-before the capture starts)."""
+before the capture starts).
+
+Data parallel (``torch.distributed`` initialised, world size > 1): pass the bare model, NOT a DistributedDataParallel
+wrapper.  The step then reduces ALL gradients -- weights, biases and the LSQ step sizes / zero-points alike -- with ONE
+NCCL all-reduce(SUM) over a flat buffer, captured inside the same graph between backward and the optimizer step (one
+launch per rank per step, nothing on the host between them).  SUM matches the reference, which multiplies the loss by
+the world size to undo DDP's averaging (yolov8_qat.py:235-236)."""
 from __future__ import annotations
 
 from typing import Callable
@@ -20,10 +26,15 @@ import torch
 
 class GraphedQATStep:
     def __init__(self, model, optimizer, loss_fn: Callable, example_input: torch.Tensor, warmup: int = 3,
-                 post_backward: Callable = None):
+                 post_backward: Callable = None, group=None, average: bool = False):
         if not example_input.is_cuda:
             raise RuntimeError("GraphedQATStep needs a CUDA example input")
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
+        import torch.distributed as dist
+        self.group, self.average = group, average
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if self.world > 1 and isinstance(model, torch.nn.parallel.DistributedDataParallel):
+            raise ValueError("GraphedQATStep reduces the gradients itself: pass the bare model, not a DDP wrapper")
         self.static_input = example_input.clone()
         self.post_backward = post_backward
         side = torch.cuda.Stream()
@@ -42,10 +53,30 @@ class GraphedQATStep:
     def _fwd_bwd_step(self):
         loss = self.loss_fn(self.model(self.static_input))
         loss.backward()
+        if self.world > 1:
+            self._all_reduce_grads()
         if self.post_backward is not None:
             self.post_backward()
         self.optimizer.step()
         return loss.detach()
+
+    def _all_reduce_grads(self) -> None:
+        """One flat all-reduce per dtype over every gradient; the parameters' .grad become views of the flat buffer."""
+        import torch.distributed as dist
+        by_dtype = {}
+        for p in self.model.parameters():
+            if p.grad is not None:
+                by_dtype.setdefault(p.grad.dtype, []).append(p)
+        for ps in by_dtype.values():
+            flat = torch.cat([p.grad.reshape(-1) for p in ps])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                flat.div_(self.world)
+            off = 0
+            for p in ps:
+                n = p.numel()
+                p.grad = flat[off:off + n].view(p.shape)
+                off += n
 
     def _eager_step(self):
         self.optimizer.zero_grad(set_to_none=True)
