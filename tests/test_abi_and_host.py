@@ -214,3 +214,39 @@ def test_checkpoint_keeps_calibration_and_learned_qparams():
     e = Layer(sym=False)
     res = e.load_state_dict(ref_sd, strict=True)
     assert not res.missing_keys and e.weight_quantizer.scale.item() == 0.0123
+
+
+def test_multi_tensor_plan_geometry_on_the_host():
+    """vsiq_mt_plan is pure host code: tile prefix, per-tensor vs per-channel tiling, argument validation."""
+    from vsiquantization_b200 import _lib
+    shapes = [(16, 27, 1), (64, 288, 64), (1, 5, 1), (256, 2304, 256), (0, 10, 1)]  # (rows, inner, qp_channels)
+    tab = (_lib.MtEntry * len(shapes))()
+    out = q = 0
+    for e, (rows, inner, qpc) in zip(tab, shapes):
+        e.x = 0x1000
+        e.rows, e.inner, e.out_offset, e.qp_offset, e.qp_channels = rows, inner, out, q, (qpc if rows else 1)
+        e.qp.qmin, e.qp.qmax, e.qp.scale_host = -8, 7, 0.1
+        out += (rows * inner + 7) // 8 * 8
+        q += e.qp_channels
+    total = ctypes.c_uint32(0)
+    assert _lib.lib.vsiq_mt_plan(tab, len(shapes), ctypes.byref(total)) == 0
+    first = 0
+    for e, (rows, inner, qpc) in zip(tab, shapes):
+        assert e.first_tile == first
+        if rows == 0:
+            assert e.n_tiles == 0
+        elif qpc > 1:   # per channel: every row is cut into `chunks` tiles of <= 1024 elements
+            assert e.n_tiles == rows * e.chunks and e.chunks == -(-inner // e.tile) and 0 < e.tile <= 1024
+        else:           # per tensor: the whole tensor is one row
+            assert e.chunks == e.n_tiles == -(-(rows * inner) // e.tile) and 0 < e.tile <= 1024
+        assert (e.tlo, e.thi) == (-8.5, 7.5 - 2 ** -21)  # qmin even: tie rounds to it; qmax odd: next float below 7.5
+        first += e.n_tiles
+    assert total.value == first and _lib.lib.vsiq_mt_workspace_bytes(first) == 256 + 16 * first
+    tab[1].out_offset += 4                                   # not a multiple of 8 elements
+    assert _lib.lib.vsiq_mt_plan(tab, len(shapes), ctypes.byref(total)) == -1
+    tab[1].out_offset -= 4
+    tab[1].qp_channels = 3                                   # neither 1 nor rows
+    assert _lib.lib.vsiq_mt_plan(tab, len(shapes), ctypes.byref(total)) == -1
+    tab[1].qp_channels = 64
+    tab[0].qp.pre_op = 1                                     # fused ReLU is an activation feature
+    assert _lib.lib.vsiq_mt_plan(tab, len(shapes), ctypes.byref(total)) == -3

@@ -130,3 +130,30 @@ def test_qparam_grad_bucket_single_collective_per_dtype():
     assert g0[0] == [1.5] * 5 and g0[1] == [2.5] * 5  # mean over ranks of (rank + 1 + step)
     assert all(n.endswith(("quantizer.scale", "quantizer.zero_point")) for n in names0)
     assert ign0 == sorted(names0)
+
+
+def _flat_grad_case(rank, world):
+    """GraphedQATStep's gradient exchange (one flat all-reduce per dtype) without the graph: gloo, CPU tensors."""
+    from vsiquantization_b200.graph import GraphedQATStep
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)).double()
+    model.register_parameter("scale64", torch.nn.Parameter(torch.tensor(0.5, dtype=torch.float64)))
+    model.register_parameter("zp32", torch.nn.Parameter(torch.tensor([1.0, 2.0], dtype=torch.float32)))
+    x = torch.full((2, 5), float(rank + 1), dtype=torch.float64)
+    loss = (model(x) ** 2).sum() * model.scale64 + (model.zp32 ** 2).sum() * (rank + 1)
+    loss.backward()
+    local = [p.grad.clone() for p in model.parameters()]
+    step = GraphedQATStep.__new__(GraphedQATStep)  # the exchange only: no CUDA, no capture
+    step.model, step.group, step.average, step.world = model, None, False, world
+    step._all_reduce_grads()
+    return [g.numpy() for g in local], [p.grad.numpy().copy() for p in model.parameters()]
+
+
+def test_graphed_step_flat_gradient_all_reduce_is_a_sum_over_ranks():
+    res = _run(_flat_grad_case)
+    locals_, reduced = zip(*res)
+    for k in range(len(reduced[0])):
+        want = locals_[0][k] + locals_[1][k]
+        for r in range(2):
+            assert reduced[r][k].dtype == want.dtype and reduced[r][k].shape == want.shape
+            np.testing.assert_allclose(reduced[r][k], want, rtol=1e-12)

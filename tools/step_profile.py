@@ -10,6 +10,9 @@ model, n_fused, _ = yolo_qat.build_model(args, dev)
 model.train()
 if args.channels_last:
     model.to(memory_format=torch.channels_last)
+if args.weight_bank:
+    from vsiquantization_b200.bank import WeightBank
+    WeightBank(model).install()
 opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.9, nesterov=True)
 x = torch.rand(64, 3, 640, 640, device=dev)
 if args.channels_last:

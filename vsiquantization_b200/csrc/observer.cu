@@ -421,15 +421,17 @@ __global__ void __launch_bounds__(kThreads, 3)
     }
 }
 
-// one warp per channel: lanes stride over the per-CTA records (fixed order), then shuffle-reduce
+// one CTA per channel: threads stride over the per-CTA records (<= 444 of them: two loads deep), then a fixed-order
+// shuffle + shared-memory reduction.  (A warp per channel walked the records 14 deep and took 33 us.)
 __global__ void __launch_bounds__(kThreads)
     ci_observe_finalize_kernel(const void* ws, int C, uint32_t n_rec, ObserveOut o) {
+    __shared__ double s_red[kWarps][kPartialWidth];
     const double* records = (const double*)((const char*)ws + kWsHeader);
-    const int lane = threadIdx.x & 31;
-    for (int c = blockIdx.x * kWarps + (threadIdx.x >> 5); c < C; c += gridDim.x * kWarps) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = blockIdx.x; c < C; c += gridDim.x) {
         float mn = INFINITY, mx = -INFINITY;
         double sa = 0.0, s1 = 0.0, s2 = 0.0;
-        for (uint32_t r = lane; r < n_rec; r += 32) {
+        for (uint32_t r = threadIdx.x; r < n_rec; r += kThreads) {
             const double* rec = records + (size_t)r * kCiObsFields * C + c;
             mn = nanmin(mn, (float)__ldcg(rec));
             mx = nanmax(mx, (float)__ldcg(rec + C));
@@ -442,7 +444,28 @@ __global__ void __launch_bounds__(kThreads)
         sa = warp_sum(sa);
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
-        if (lane == 0) observe_store_channel(o, c, mn, mx, sa, s1, s2);
+        __syncthreads();  // s_red free again
+        if (lane == 0) {
+            s_red[warp][0] = (double)mn;
+            s_red[warp][1] = (double)mx;
+            s_red[warp][2] = sa;
+            s_red[warp][3] = s1;
+            s_red[warp][4] = s2;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = (float)s_red[0][0], bq = (float)s_red[0][1];
+            double x2 = s_red[0][2], x3 = s_red[0][3], x4 = s_red[0][4];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) {
+                a = nanmin(a, (float)s_red[w][0]);
+                bq = nanmax(bq, (float)s_red[w][1]);
+                x2 += s_red[w][2];
+                x3 += s_red[w][3];
+                x4 += s_red[w][4];
+            }
+            observe_store_channel(o, c, a, bq, x2, x3, x4);
+        }
     }
 }
 
@@ -670,8 +693,7 @@ extern "C" int vsiq_ci_observe(const float* x, int64_t rows, int64_t channels, d
     oo.count = (double)rows;
     ci_observe_kernel<<<grid, kThreads, 0, st>>>(x, geo, workspace);
     if (cudaError_t err = cudaGetLastError()) return (int)err;
-    const int fgrid = (int)((channels + kWarps - 1) / kWarps);
-    ci_observe_finalize_kernel<<<fgrid, kThreads, 0, st>>>(workspace, (int)channels, grid, oo);
+    ci_observe_finalize_kernel<<<(int)channels, kThreads, 0, st>>>(workspace, (int)channels, grid, oo);
     return (int)cudaGetLastError();
 }
 
