@@ -501,8 +501,9 @@ def test_compute_scale_matches_reference_golden():
     assert torch.isfinite(s.grad)
 
 
-def test_graphed_step_matches_eager_steps():
+def test_graphed_step_matches_eager_steps(monkeypatch):
     """Whole-step CUDA-graph capture (graph.py): same losses as the eager-launched steps, bit for bit."""
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)  # two separately built models must pick the same algos
     from tiny_model import make_tiny
     from vsiquantization_b200.graph import GraphedQATStep
     from vsiquantization_b200.modules.fuse import fuse_modules_unified
@@ -612,8 +613,9 @@ def test_weight_bank_matches_per_layer_path(per_channel, asym, w_bits, channels_
     assert torch.equal(ya, yb)
 
 
-def test_weight_bank_falls_back_while_calibrating_and_works_under_graph_capture():
+def test_weight_bank_falls_back_while_calibrating_and_works_under_graph_capture(monkeypatch):
     from vsiquantization_b200.bank import WeightBank
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)
     from vsiquantization_b200.graph import GraphedQATStep
     from vsiquantization_b200.utils.quantize_manager import calibrate_qat_model
     m = _bank_model(False, False, 8, False)
