@@ -138,7 +138,8 @@ def test_pattern_matching_without_tensors():
 def test_dropin_maps_reference_module_paths():
     from vsiquantization_b200 import dropin
     reg = dropin.install_plugins(registry={})
-    assert sorted(reg) == ["LSQObserver", "LSQQuantizer", "MinMaxObserver", "UniformQuantizer"]
+    assert sorted(reg) == ["LSQObserver", "LSQQuantizer", "MinMaxObserver", "MovingAverageMinMaxObserver",
+                           "MovingAveragePerChannelMinMaxObserver", "UniformQuantizer"]
     assert set(dropin._TIER2) >= {"modules.fuse", "modules.fuse_config", "utils.quantize_manager", "utils.estimate_bn",
                                   "quantizers.uniform", "observers.minmax"}
 
@@ -250,3 +251,39 @@ def test_multi_tensor_plan_geometry_on_the_host():
     tab[1].qp_channels = 64
     tab[0].qp.pre_op = 1                                     # fused ReLU is an activation feature
     assert _lib.lib.vsiq_mt_plan(tab, len(shapes), ctypes.byref(total)) == -3
+
+
+@pytest.mark.parametrize("symmetric,bits", [(True, 8), (False, 8), (True, 4), (False, 4)])
+@pytest.mark.parametrize("per_channel", [False, True])
+def test_moving_average_observer_math_matches_torch_observers(symmetric, bits, per_channel):
+    """observers/moving_average.py::ema_update_ (the [C]-sized running update + qparams that follow the CUDA observer
+    pass) against torch.ao's MovingAverage(PerChannel)MinMaxObserver -- the observer LSQFakeQuantize uses
+    (quantizers/lsq_module.py:1-2,91,113-115) -- bit for bit over several batches, NaN-free data, both schemes."""
+    from torch.ao.quantization.observer import MovingAverageMinMaxObserver, MovingAveragePerChannelMinMaxObserver
+    from vsiquantization_b200.observers.moving_average import ema_update_
+    qmin, qmax = (-(2 ** (bits - 1)), 2 ** (bits - 1) - 1) if symmetric else (0, 2 ** bits - 1)
+    kw = dict(averaging_constant=0.01, quant_min=qmin, quant_max=qmax, dtype=torch.qint8 if symmetric else torch.quint8)
+    if per_channel:
+        ref = MovingAveragePerChannelMinMaxObserver(
+            ch_axis=1, qscheme=torch.per_channel_symmetric if symmetric else torch.per_channel_affine, **kw)
+    else:
+        ref = MovingAverageMinMaxObserver(qscheme=torch.per_tensor_symmetric if symmetric else torch.per_tensor_affine, **kw)
+    C = 6 if per_channel else 1
+    state = torch.zeros(C, 8, dtype=torch.float64)
+    state[:, 2] = 1.0
+    g = torch.Generator().manual_seed(3)
+    for i in range(6):
+        x = torch.randn(3, 6, 5, 4, generator=g) * (1 + i) + 0.3 * i
+        if i == 2:
+            x = x.abs() + 0.5          # all-positive batch: min(m, 0) matters
+        ref(x)
+        s_ref, z_ref = ref.calculate_qparams()
+        if per_channel:
+            bmin, bmax = torch.aminmax(x.permute(1, 0, 2, 3).flatten(1), dim=1)
+        else:
+            bmin, bmax = (t.reshape(1) for t in torch.aminmax(x))
+        ema_update_(state, bmin, bmax, 0.01, qmin, qmax, symmetric)
+        assert torch.equal(state[:, 0].float(), ref.min_val.reshape(-1)) and torch.equal(state[:, 1].float(), ref.max_val.reshape(-1))
+        assert torch.equal(state[:, 2].float(), s_ref.reshape(-1).float()), (i, state[:, 2], s_ref)
+        assert torch.equal(state[:, 3].long(), z_ref.reshape(-1).long())
+        assert float(state[0, 4]) == i + 1

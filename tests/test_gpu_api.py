@@ -685,3 +685,40 @@ def test_multi_tensor_abi_against_single_tensor_kernels():
             assert torch.allclose(ds_flat[q0:q0 + C], ds.double().reshape(-1), rtol=1e-6, atol=tol), i
         if learn == 2:
             assert torch.allclose(dz_flat[q0:q0 + C], dz.reshape(-1), rtol=1e-5, atol=1e-6 * float(dz.abs().max())), i
+
+
+@pytest.mark.parametrize("per_channel,channels_last", [(False, False), (True, False), (True, True)])
+def test_moving_average_observer_matches_torch_observer(per_channel, channels_last):
+    """MovingAverage(PerChannel)MinMaxObserver plugins (the observer phase of LSQFakeQuantize, lsq_module.py:91,113-115)
+    fed by the CUDA observer kernel, against torch.ao's observers on the CPU: running extrema, scale and zero-point bit
+    for bit after every batch."""
+    from torch.ao.quantization.observer import MovingAverageMinMaxObserver as TM
+    from torch.ao.quantization.observer import MovingAveragePerChannelMinMaxObserver as TP
+    from vsiquantization_b200.utils.registry import CLASS_REGISTRY
+    import vsiquantization_b200.quantizers.quantization_manager  # noqa: F401
+    if per_channel:
+        obs = CLASS_REGISTRY["MovingAveragePerChannelMinMaxObserver"](False, 8, ch_axis=1)
+        ref = TP(ch_axis=1, qscheme=torch.per_channel_affine, dtype=torch.quint8, quant_min=0, quant_max=255)
+    else:
+        obs = CLASS_REGISTRY["MovingAverageMinMaxObserver"](False)
+        ref = TM(qscheme=torch.per_tensor_affine, dtype=torch.quint8, quant_min=0, quant_max=255)
+    g = torch.Generator().manual_seed(21)
+    for i in range(4):
+        x = torch.randn(4, 8, 9, 7, generator=g) * (1 + i) + 0.2 * i
+        xd = x.cuda()
+        if channels_last:
+            xd = xd.contiguous(memory_format=torch.channels_last)
+        scale, zp = obs.forward(xd)
+        ref(x)
+        s_ref, z_ref = ref.calculate_qparams()
+        lo = torch.as_tensor(obs.min_val, dtype=torch.float64).reshape(-1).float()
+        hi = torch.as_tensor(obs.max_val, dtype=torch.float64).reshape(-1).float()
+        assert torch.equal(lo, ref.min_val.reshape(-1)) and torch.equal(hi, ref.max_val.reshape(-1)), i
+        assert torch.equal(torch.as_tensor(scale, dtype=torch.float64).reshape(-1).float(), s_ref.reshape(-1).float()), i
+        assert torch.equal(torch.as_tensor(zp, dtype=torch.float64).reshape(-1).long(), z_ref.reshape(-1).long()), i
+    # and it drives a manager like any other observer plugin
+    from vsiquantization_b200.quantizers.quantization_manager import QuantizationManager
+    m = QuantizationManager("UniformQuantizer", "MovingAverageMinMaxObserver", 8, False)
+    m.is_learning_scale = False
+    y = m.quantize(torch.randn(2, 8, 5, 5, device="cuda"))
+    assert y.shape == (2, 8, 5, 5) and isinstance(m.scale, float) and isinstance(m.zero_point, int)

@@ -157,3 +157,48 @@ def test_graphed_step_flat_gradient_all_reduce_is_a_sum_over_ranks():
         for r in range(2):
             assert reduced[r][k].dtype == want.dtype and reduced[r][k].shape == want.shape
             np.testing.assert_allclose(reduced[r][k], want, rtol=1e-12)
+
+
+def _ema_sync_case(rank, world):
+    """sync_observers on moving-average observers: running extrema are AVERAGED over the ranks that observed data."""
+    from vsiquantization_b200.observers.moving_average import ema_update_, torch_qparams
+    from vsiquantization_b200.parallel import sync_observers
+    from vsiquantization_b200.quantizers.quantization_manager import QuantizationManager as M
+
+    class Layer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.weight_quantizer = M("UniformQuantizer", "MovingAveragePerChannelMinMaxObserver", 8, True)
+            self.activation_quantizer = M("UniformQuantizer", "MovingAverageMinMaxObserver", 8, False)
+    layer = Layer()
+    g = torch.Generator().manual_seed(10 + rank)
+    for q, C in ((layer.weight_quantizer, 4), (layer.activation_quantizer, 1)):
+        st = torch.zeros(C, 8, dtype=torch.float64)
+        st[:, 2] = 1.0
+        if not (rank == 1 and C == 1):  # rank 1 never observed an activation: it must not drag the average to zero
+            for _ in range(3):
+                x = torch.randn(C, 50, generator=g) * (rank + 1)
+                ema_update_(st, x.min(1).values, x.max(1).values, 0.01, q.observer.quant_min, q.observer.quant_max,
+                            bool(q.observer.symmetric))
+        q.observer.load_state(st)
+        q._calibrated = True
+    before = [q.observer.state.clone() for q in (layer.weight_quantizer, layer.activation_quantizer)]
+    rows = sync_observers(layer)
+    after = [q.observer.state.clone() for q in (layer.weight_quantizer, layer.activation_quantizer)]
+    w_obs = layer.weight_quantizer.observer
+    s, z = torch_qparams(after[0][:, 0].float(), after[0][:, 1].float(), w_obs.quant_min, w_obs.quant_max, True)
+    assert torch.equal(after[0][:, 2].float(), s) and torch.equal(after[0][:, 3].long(), z)
+    return rank, rows, [b.numpy() for b in before], [a.numpy() for a in after]
+
+
+def test_sync_observers_averages_moving_average_observers():
+    res = sorted(_run(_ema_sync_case), key=lambda r: r[0])  # the queue hands results back in arrival order
+    (_, rows0, b0, a0), (_, rows1, b1, a1) = res
+    assert rows0 == rows1 == 5
+    for k in range(2):
+        assert np.array_equal(a0[k], a1[k])  # every rank ends with the same state
+    # weights: both ranks observed -> plain mean of the running extrema (rounded to fp32); call counts summed
+    want = ((b0[0][:, :2] + b1[0][:, :2]) / 2).astype(np.float32).astype(np.float64)
+    assert np.array_equal(a0[0][:, :2], want) and np.array_equal(a0[0][:, 4], b0[0][:, 4] + b1[0][:, 4])
+    # activations: only rank 0 has data -> its extrema survive unchanged
+    assert np.array_equal(a0[1][:, :2], b0[1][:, :2]) and a0[1][0, 4] == 3

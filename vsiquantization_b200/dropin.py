@@ -36,10 +36,12 @@ def install_plugins(registry=None):
     """Register UniformQuantizer / LSQQuantizer / MinMaxObserver / LSQObserver in the REFERENCE's CLASS_REGISTRY
     (utils/registry.py:2; a later registration overwrites, :26).  Returns the registry dict."""
     from .observers.minmax import LSQObserver, MinMaxObserver
+    from .observers.moving_average import MovingAverageMinMaxObserver, MovingAveragePerChannelMinMaxObserver
     from .quantizers.uniform import LSQQuantizer, UniformQuantizer
     if registry is None:
         registry = importlib.import_module("utils.registry").CLASS_REGISTRY  # the reference's module
-    for cls in (UniformQuantizer, LSQQuantizer, MinMaxObserver, LSQObserver):
+    for cls in (UniformQuantizer, LSQQuantizer, MinMaxObserver, LSQObserver, MovingAverageMinMaxObserver,
+                MovingAveragePerChannelMinMaxObserver):
         registry[cls.__name__] = cls
     return registry
 

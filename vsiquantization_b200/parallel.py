@@ -59,9 +59,38 @@ def sync_observers(model, group=None) -> int:
     """Make every rank's observers agree after sharded calibration; returns the number of observer rows synchronised.
     Scales / zero-points are recomputed from the reduced extrema exactly as observers/minmax.py:67-74 would."""
     from . import ops
-    entries = [(m, m.observer) for _, m in quantization_managers(model) if m.observer.state is not None]
+    every = [(m, m.observer) for _, m in quantization_managers(model) if m.observer.state is not None]
+    # moving-average observers (observers/moving_average.py) hold averages, not extrema: their running min / max are
+    # AVERAGED over the ranks and their qparams recomputed with torch's formula; the call statistics are summed
+    ema = [(m, o) for m, o in every if hasattr(o, "averaging_constant")]
+    entries = [(m, o) for m, o in every if not hasattr(o, "averaging_constant")]
+    rows_ema = 0
+    if ema:
+        from .observers.moving_average import torch_qparams
+        arena = torch.cat([o.state for _, o in ema]).contiguous()
+        w = _world(group)
+        if w > 1:
+            # ranks that never observed (n_calls == 0) carry no information: weight by "has data"
+            has = (arena[:, 4:5] > 0).to(arena.dtype)
+            packed = torch.cat([arena[:, 0:2] * has, has, arena[:, 4:8]], dim=1).contiguous()
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+            n = torch.clamp(packed[:, 2:3], min=1.0)
+            arena[:, 0:2] = (packed[:, 0:2] / n).to(torch.float32).to(arena.dtype)
+            arena[:, 4:8] = packed[:, 3:7]
+        row = 0
+        for m, o in ema:
+            k = o.state.shape[0]
+            blk = arena[row:row + k]
+            s_, z_ = torch_qparams(blk[:, 0].to(torch.float32), blk[:, 1].to(torch.float32), o.quant_min, o.quant_max,
+                                   bool(o.symmetric), float(o.eps))
+            blk[:, 2], blk[:, 3] = s_.to(arena.dtype), z_.to(arena.dtype)
+            o.state.copy_(blk)
+            o._host = None
+            m._invalidate()
+            row += k
+        rows_ema = row
     if not entries:
-        return 0
+        return rows_ema
     arena = torch.cat([o.state for _, o in entries]).contiguous()
     reduce_observer_states(arena, group)
     bits = torch.cat([torch.full((o.state.shape[0],), int(o.num_bits), dtype=torch.int32) for _, o in entries])
@@ -77,7 +106,7 @@ def sync_observers(model, group=None) -> int:
         o._host = None
         m._invalidate()
         row += k
-    return row
+    return row + rows_ema
 
 
 class QParamGradBucket:

@@ -33,6 +33,7 @@ import torch
 import torch.nn as nn
 
 from ..observers.minmax import MinMaxObserver  # noqa: F401  (registers the plugin classes)
+from ..observers.moving_average import MovingAverageMinMaxObserver  # noqa: F401
 from ..quantizers.uniform import UniformQuantizer  # noqa: F401
 from ..utils.registry import CLASS_REGISTRY
 
