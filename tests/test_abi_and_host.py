@@ -287,3 +287,39 @@ def test_moving_average_observer_math_matches_torch_observers(symmetric, bits, p
         assert torch.equal(state[:, 2].float(), s_ref.reshape(-1).float()), (i, state[:, 2], s_ref)
         assert torch.equal(state[:, 3].long(), z_ref.reshape(-1).long())
         assert float(state[0, 4]) == i + 1
+
+
+def test_tier1_plugins_inside_the_unmodified_reference():
+    """Tier 1 of INTEGRATION.md against the REAL reference tree (build container only; skipped where /root/reference
+    is absent): dropin.install_plugins() registers the native classes in the reference's own CLASS_REGISTRY, and the
+    reference's QuantizationManager / ConvBnReLU then build them by name with its positional conventions
+    (quantization_manager.py:41-42).  Construction only -- no kernel runs on this CPU-only host."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from oracle import ref_shim; ref_shim.install()\n"
+        "import torch\n"
+        "from utils.registry import CLASS_REGISTRY\n"
+        "import quantizers.quantization_manager as rqm\n"
+        "assert rqm.__file__.startswith(ref_shim.REFERENCE_ROOT)\n"
+        "before = sorted(CLASS_REGISTRY)\n"
+        "import vsiquantization_b200.dropin as d; d.install_plugins()\n"
+        "m = rqm.QuantizationManager('LSQQuantizer', 'LSQObserver', 4, True)\n"
+        "assert type(m.quantizer).__module__ == 'vsiquantization_b200.quantizers.uniform', type(m.quantizer)\n"
+        "assert type(m.observer).__module__ == 'vsiquantization_b200.observers.minmax'\n"
+        "assert (m.quantizer.qmin, m.quantizer.qmax, m.quantizer.calib_grad_scale, m.observer.num_bits) == (-8, 7, 1, 8)\n"
+        "import modules.fused as rf\n"
+        "assert rf.__file__.startswith(ref_shim.REFERENCE_ROOT)\n"
+        "layer = rf.ConvBnReLU(torch.nn.Conv2d(3, 4, 3, bias=False), torch.nn.BatchNorm2d(4), torch.nn.ReLU(),\n"
+        "                      'MinMaxObserver', 'UniformQuantizer', 'MinMaxObserver', 'UniformQuantizer', True, True, True, 8, 8)\n"
+        "assert type(layer.weight_quantizer.quantizer).__module__.startswith('vsiquantization_b200')\n"
+        "assert type(layer.activation_quantizer.observer).__module__.startswith('vsiquantization_b200')\n"
+        "print('before', before, 'after', sorted(CLASS_REGISTRY))\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stderr[-800:]
+    assert "before ['MinMaxObserver', 'UniformQuantizer'] after" in out.stdout and "LSQQuantizer" in out.stdout
