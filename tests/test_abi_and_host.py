@@ -323,3 +323,37 @@ def test_tier1_plugins_inside_the_unmodified_reference():
     out = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=180)
     assert out.returncode == 0, out.stderr[-800:]
     assert "before ['MinMaxObserver', 'UniformQuantizer'] after" in out.stdout and "LSQQuantizer" in out.stdout
+
+
+def test_yolov8_fixture_is_the_reference_network():
+    """vsiquantization_b200/nets/yolov8.py (the model behind every YOLOv8 number in DESIGN.md) against the reference's
+    nets/yolov8.py (build container only): same parameter / buffer names, shapes and order for n, s, m, l, and the same
+    float forward, bit for bit, with the same weights (YOLOv8n, 64x64 input, training-mode heads)."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from oracle import ref_shim; ref_shim.install()\n"
+        "import torch\n"
+        "import nets.yolov8 as ry\n"
+        "from vsiquantization_b200.nets import yolov8 as oy\n"
+        "assert ry.__file__.startswith(ref_shim.REFERENCE_ROOT)\n"
+        "for name in 'nsml':\n"
+        "    a = getattr(ry, 'yolo_v8_' + name)(20); b = getattr(oy, 'yolo_v8_' + name)(num_classes=20)\n"
+        "    assert [(n, tuple(p.shape)) for n, p in a.named_parameters()] == [(n, tuple(p.shape)) for n, p in b.named_parameters()], name\n"
+        "    assert [(n, tuple(p.shape)) for n, p in a.named_buffers()] == [(n, tuple(p.shape)) for n, p in b.named_buffers()], name\n"
+        "torch.manual_seed(0)\n"
+        "a = ry.yolo_v8_n(20); b = oy.yolo_v8_n(num_classes=20)\n"
+        "b.load_state_dict(a.state_dict(), strict=True)\n"
+        "x = torch.rand(2, 3, 64, 64)\n"
+        "a.train(); b.train()\n"
+        "ya, yb = a(x), b(x)\n"
+        "assert len(ya) == len(yb) and all(torch.equal(u, v) for u, v in zip(ya, yb))\n"
+        "print('same network', len(ya))\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-800:]
+    assert "same network" in out.stdout
