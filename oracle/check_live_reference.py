@@ -1,0 +1,161 @@
+"""Randomised oracle-vs-LIVE-reference check (build container only).
+
+TEST INFRASTRUCTURE.  The golden vectors under tests/golden pin the oracle on a fixed set of cases; this script pins it
+on hundreds of fresh ones by running the UNMODIFIED reference (imported through oracle/ref_shim.py, torch on CPU) beside
+the C oracle on the same seeded inputs:
+
+  * UniformQuantizer.quantize, fixed qparams (quantizers/uniform.py:34-56,81-96): y bit for bit, any bit width 2..8,
+    symmetric / asymmetric, arbitrary integer zero-point, inputs salted with ties (k + 1/2) * s, +-0, denormals, +-inf, NaN;
+  * the learnable-scale path (uniform.py:47-52,242-271; 0-dim float64 Parameter, quantization_manager.py:99):
+    y and dx bit for bit, dscale within 1e-5 of the absolute mass of its terms (the reference's own fp32 sums cancel);
+  * MinMaxObserver traces (observers/minmax.py:32-74): running min / max, scale and zero-point exactly (Python doubles);
+  * LSQFakeQuantize per-channel learn phase (quantizers/lsq_module.py:147-173,254-274,317-358): y, dx bit for bit, per-channel
+    dscale / dzero_point within 1e-5 of their mass.
+
+Usage: python oracle/check_live_reference.py [--cases N] [--seed S]     (exit code 0 = all equal)
+/root/reference does not exist on the GPU box: nothing that runs there may import this file."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import oracle  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+
+def bits_equal(a, b) -> bool:
+    a, b = np.ascontiguousarray(a, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and bool(np.array_equal(na, nb)) and bool(
+        np.array_equal(a[~na].view(np.uint32), b[~nb].view(np.uint32)))
+
+
+def salted(rng, shape, s):
+    x = (rng.standard_normal(shape) * rng.choice([0.3, 1.0, 4.0, 40.0])).astype(np.float32)
+    flat = x.reshape(-1)
+    k = rng.integers(-140, 140, size=max(1, flat.size // 8))
+    pos = rng.choice(flat.size, size=k.size, replace=False)
+    flat[pos] = ((k + 0.5) * np.float64(s)).astype(np.float32)          # rounding ties
+    specials = np.array([0.0, -0.0, 1e-42, -1e-42, np.inf, -np.inf, np.nan, 3.0e38, -3.0e38], dtype=np.float32)
+    pos = rng.choice(flat.size, size=min(flat.size, specials.size), replace=False)
+    flat[pos] = specials[:pos.size]
+    return x
+
+
+def mass(x, g, s, z, qmin, qmax):
+    with np.errstate(all="ignore"):
+        v = x.astype(np.float32) / np.float32(s)
+        q = np.clip(np.rint(v + np.float32(z)), qmin, qmax)
+        t = np.abs(g.astype(np.float64) * (q - z)) + np.abs(g.astype(np.float64) * v)
+    return float(np.nansum(t[np.isfinite(t)]))
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=60)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    if not ref_shim.available():
+        print("reference tree not present")
+        return 2
+    ref_shim.install()
+    import torch
+    from quantizers.uniform import UniformQuantizer as RefQ
+    from observers.minmax import MinMaxObserver as RefObs
+    from quantizers.lsq_module import LSQFakeQuantize
+    from torch.quantization import MovingAveragePerChannelMinMaxObserver
+    rng = np.random.default_rng(args.seed)
+    bad = []
+
+    for case in range(args.cases):
+        bits = int(rng.integers(2, 9))
+        sym = bool(rng.integers(0, 2))
+        shape = tuple(int(d) for d in rng.integers(1, 9, size=int(rng.integers(1, 5))))
+        s = float(rng.choice([0.004, 0.0236, 0.11, 0.43, 1.0, 7.5]) * rng.uniform(0.5, 2.0))
+        q = RefQ(bits, sym)
+        zp = 0 if sym else int(rng.integers(q.qmin, q.qmax + 1))
+        x = salted(rng, shape, s)
+        # ---- fixed qparams: forward
+        with torch.no_grad():
+            y_ref = q.quantize(torch.from_numpy(x.copy()), s, zp, False).numpy()
+        y = oracle.fake_quant_fwd(x, s, zp, q.qmin, q.qmax)
+        if not bits_equal(y, y_ref):
+            bad.append(("fixed fwd", case, bits, sym, shape, s, zp))
+        # ---- learnable scale (symmetric: the only learning flow the reference can execute)
+        if sym:
+            xf = np.where(np.isfinite(x), x, np.float32(0.25)).astype(np.float32)  # autograd of inf / NaN is NaN soup
+            g = rng.standard_normal(shape).astype(np.float32)
+            xt = torch.from_numpy(xf.copy()).requires_grad_(True)
+            sp = torch.nn.Parameter(torch.tensor(np.float64(s)))
+            yl = q.quantize(xt, sp, 0, True)
+            yl.backward(torch.from_numpy(g))
+            gs = oracle.grad_scale(q.qmax, xf.size)
+            yo = oracle.fake_quant_fwd(xf, s, 0, q.qmin, q.qmax)
+            dx, ds, _ = oracle.fake_quant_bwd(xf, g, s, 0, q.qmin, q.qmax, grad_scale=gs)
+            if not bits_equal(yo, yl.detach().numpy()) or not bits_equal(dx, xt.grad.numpy()):
+                bad.append(("learned y/dx", case, bits, shape, s))
+            if abs(ds[0] - float(sp.grad)) > 1e-5 * gs * mass(xf, g, s, 0, q.qmin, q.qmax) + 1e-30:
+                bad.append(("learned ds", case, bits, shape, s, ds[0], float(sp.grad)))
+        # ---- observer trace
+        obs = RefObs(sym)
+        run_min = run_max = 0.0
+        for _ in range(3):
+            xb = (rng.standard_normal(shape) * rng.uniform(0.1, 5.0) + rng.uniform(-1, 1)).astype(np.float32)
+            sc_ref, zp_ref = obs.forward(torch.from_numpy(xb))
+            st = oracle.minmax_stats(xb)
+            run_min, run_max = oracle.minmax_update(run_min, run_max, st[0, 0], st[0, 1])
+            sc, zz = oracle.qparams(run_min, run_max, 8, sym)
+            if (run_min, run_max, sc, zz) != (obs.min_val, obs.max_val, sc_ref, zp_ref):
+                bad.append(("observer", case, sym, (run_min, run_max, sc, zz), (obs.min_val, obs.max_val, sc_ref, zp_ref)))
+                break
+
+    # ---- LSQFakeQuantize, per channel, learn phase (asymmetric quint8 activations and symmetric qint8 weights)
+    for case in range(max(4, args.cases // 6)):
+        affine = bool(case % 2)
+        C = int(rng.integers(2, 7))
+        shape = (int(rng.integers(1, 4)), C, int(rng.integers(1, 6)), int(rng.integers(1, 6)))
+        kw = dict(observer=MovingAveragePerChannelMinMaxObserver, ch_axis=1,
+                  quant_min=0 if affine else -128, quant_max=255 if affine else 127,
+                  dtype=torch.quint8 if affine else torch.qint8,
+                  qscheme=torch.per_channel_affine if affine else torch.per_channel_symmetric)
+        fq = LSQFakeQuantize(learn_scale=True, config_act=affine, **kw)
+        x0 = (rng.standard_normal(shape) * 2 + (1.0 if affine else 0.0)).astype(np.float32)
+        fq(torch.from_numpy(x0))            # observer phase: initialises scale_param / zero_point_param_float
+        fq.disable_observer()
+        x = (rng.standard_normal(shape) * 2.5 + (1.0 if affine else 0.0)).astype(np.float32)
+        g = rng.standard_normal(shape).astype(np.float32)
+        xt = torch.from_numpy(x.copy()).requires_grad_(True)
+        y = fq(xt)
+        y.backward(torch.from_numpy(g))
+        s = fq.scale_param.detach().numpy().reshape(-1).astype(np.float64)
+        zf = fq.zero_point_param_float.detach().numpy().reshape(-1).astype(np.float64)
+        qmin, qmax = kw["quant_min"], kw["quant_max"]
+        gs = oracle.grad_scale(qmax, x.size, C) * (5000.0 if affine else 1.0)
+        yo = oracle.fake_quant_fwd(x, s, zf, qmin, qmax, ch_axis=1, zp_learned=True)
+        dx, ds, dz = oracle.fake_quant_bwd(x, g, s, zf, qmin, qmax, ch_axis=1, zp_learned=True, grad_scale=gs,
+                                           want_ds=True, want_dz=True)
+        if not bits_equal(yo, y.detach().numpy()) or not bits_equal(dx, xt.grad.numpy()):
+            bad.append(("lsq per-channel y/dx", case, shape, affine))
+        ds_ref = fq.scale_param.grad.numpy().reshape(-1)
+        dz_ref = fq.zero_point_param_float.grad.numpy().reshape(-1)
+        for c in range(C):
+            zc = float(np.clip(np.rint(np.float32(zf[c])), qmin, qmax))
+            m = gs * mass(x[:, c], g[:, c], s[c], zc, qmin, qmax)
+            zm = gs * float(np.sum(np.abs(g[:, c].astype(np.float64) * np.float32(s[c]))))
+            if abs(ds[c] - ds_ref[c]) > 1e-5 * m + 1e-30 or abs(dz[c] - dz_ref[c]) > 1e-5 * zm + 1e-30:
+                bad.append(("lsq per-channel ds/dz", case, c, ds[c], ds_ref[c], dz[c], dz_ref[c]))
+    for b in bad[:20]:
+        print("MISMATCH", b)
+    print(f"{args.cases} uniform/observer cases, {max(4, args.cases // 6)} LSQFakeQuantize cases, {len(bad)} mismatches")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -4,6 +4,8 @@ This is what pins the oracle: every fixture under tests/golden/ was written by o
 running the reference's own Python classes on CPU.  Bit-exact for fake-quantised values, codes, dx,
 observer min/max and scales; stated tolerances for the order-dependent sums (ds, dz, BN moments).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -215,3 +217,20 @@ def test_torch_port_matches_golden():
                                    int(qmin), int(qmax), learn=True)
     assert bits_equal(y.numpy(), G["b8_sym_0_y"]) and bits_equal(dx.numpy(), G["b8_sym_0_dx"])
     assert ds.item() == G["b8_sym_0_ds"][0]
+
+
+@pytest.mark.parametrize("seed", [0, 11])
+def test_oracle_against_the_live_reference(seed):
+    """oracle/check_live_reference.py: the C oracle beside the UNMODIFIED reference (torch on CPU) on fresh random
+    cases -- UniformQuantizer fixed / learnable, MinMaxObserver traces, LSQFakeQuantize per channel.  Build container
+    only (skipped where /root/reference is absent); the golden vectors cover the same ground everywhere else."""
+    import subprocess
+    import sys
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "oracle", "check_live_reference.py"), "--cases", "120",
+                          "--seed", str(seed)], cwd="/tmp", capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-500:])
+    assert "0 mismatches" in out.stdout
