@@ -8,6 +8,7 @@ the C oracle on the same seeded inputs:
     symmetric / asymmetric, arbitrary integer zero-point, inputs salted with ties (k + 1/2) * s, +-0, denormals, +-inf, NaN;
   * the learnable-scale path (uniform.py:47-52,242-271; 0-dim float64 Parameter, quantization_manager.py:99):
     y and dx bit for bit, dscale within 1e-5 of the absolute mass of its terms (the reference's own fp32 sums cancel);
+  * the same forward with degenerate scales (0, negative, 1e-30, 1e30, inf, NaN, 2^-41, 2^41);
   * MinMaxObserver traces (observers/minmax.py:32-74): running min / max, scale and zero-point exactly (Python doubles);
   * LSQFakeQuantize per-channel learn phase (quantizers/lsq_module.py:147-173,254-274,317-358): y, dx bit for bit, per-channel
     dscale / dzero_point within 1e-5 of their mass.
@@ -115,6 +116,17 @@ def main() -> int:
             if (run_min, run_max, sc, zz) != (obs.min_val, obs.max_val, sc_ref, zp_ref):
                 bad.append(("observer", case, sym, (run_min, run_max, sc, zz), (obs.min_val, obs.max_val, sc_ref, zp_ref)))
                 break
+
+    # ---- degenerate scales (zero, negative, tiny, huge, inf, NaN): the reference divides by whatever it is given
+    for sdeg in (0.0, -0.05, 1e-30, 1e30, float("inf"), float("nan"), 2.0 ** -41, 2.0 ** 41):
+        for sym in (True, False):
+            q = RefQ(8, sym)
+            zp = 0 if sym else 77
+            x = salted(rng, (5, 7), 0.1)
+            with torch.no_grad(), np.errstate(all="ignore"):
+                y_ref = q.quantize(torch.from_numpy(x.copy()), sdeg, zp, False).numpy()
+            if not bits_equal(oracle.fake_quant_fwd(x, sdeg, zp, q.qmin, q.qmax), y_ref):
+                bad.append(("degenerate scale", sdeg, sym))
 
     # ---- LSQFakeQuantize, per channel, learn phase (asymmetric quint8 activations and symmetric qint8 weights)
     for case in range(max(4, args.cases // 6)):
