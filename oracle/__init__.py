@@ -236,3 +236,25 @@ def fake_quant_fwd_bwd(x, g, scale, zero_point, qmin, qmax, y=None, dx=None):
                                          ctypes.c_float(np.float32(scale)), ctypes.c_float(np.float32(zero_point)),
                                          int(qmin), int(qmax))
     return y, dx
+
+
+_proof = None
+
+
+def proof_division(scale: float, mode: int = 0, first: int = 0, stride: int = 1):
+    """(mismatches, inputs on the fast path) of the kernels' division-free arithmetic against IEEE division over the bit
+    patterns first, first+stride, ... of the input, emulated on the host (oracle/fastpath_proof.c).  mode 0: x / s;
+    mode 1: RN(RN(g*s) / s)."""
+    global _proof
+    if _proof is None:
+        so = os.path.join(_HERE, "_build", "libvsiq_fastpath_proof.so")
+        src = os.path.join(_HERE, "fastpath_proof.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+        _proof = ctypes.CDLL(so)
+        _proof.vsiq_proof_division.restype = ctypes.c_ulonglong
+        _proof.vsiq_proof_division.argtypes = [ctypes.c_float, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
+                                               ctypes.POINTER(ctypes.c_ulonglong)]
+    covered = ctypes.c_ulonglong(0)
+    wrong = _proof.vsiq_proof_division(float(scale), int(mode), int(first), int(stride), ctypes.byref(covered))
+    return int(wrong), int(covered.value)

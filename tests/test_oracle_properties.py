@@ -1,6 +1,7 @@
 """Property tests (hypothesis) of the oracle's fake-quant semantics -- the size-independent invariants the GPU tests
 re-check at full size: idempotence, integer codes inside [qmin, qmax], monotonicity, mask <=> in range, dx in {0, ~g}."""
 import numpy as np
+import pytest
 from hypothesis import given, settings, strategies as st
 from hypothesis.extra import numpy as hnp
 
@@ -73,3 +74,20 @@ def test_qparams_formula(a, c, b, sym):
         assert z == 0 and s == max(abs(mn), abs(mx)) / (2 ** (b - 1) - 1 + 1e-8)
     else:
         assert s == (mx - mn) / (2 ** b - 1 + 1e-8) and z == round(-mn / (s + 1e-8))
+
+
+@pytest.mark.parametrize("scale", [3.0 / 127, 3.0 / 7, 1.0 / 3.0, -0.05, 2.0 ** -40, 2.0 ** 40])
+def test_division_free_arithmetic_is_exact_for_every_input(scale):
+    """The kernels' hoisted-reciprocal + exact-residual-FMA division (csrc/common.cuh div_fast / dx_fast), emulated on
+    the host (oracle/fastpath_proof.c: fmaf and float division are the same IEEE operations as on the GPU), against
+    x / s and RN(RN(g*s) / s) for ALL 2^32 bit patterns that take the fast path: zero mismatches.  The GPU repeats this
+    on the device (vsiq_selftest_division, tests/test_gpu_kernels.py::test_division_exhaustive)."""
+    for mode in (0, 1):
+        wrong, covered = oracle.proof_division(scale, mode)
+        assert wrong == 0, (scale, mode, wrong)
+        assert covered == 2030043138  # 2 * (121 binades * 2^23) + the two zeros
+
+
+def test_division_free_arithmetic_declines_out_of_range_scales():
+    for scale in (2.0 ** -41, 2.0 ** 41, 0.0, float("inf"), float("nan")):
+        assert oracle.proof_division(scale, 0, 0, 65537) == (0, 0)  # such tiles always run the IEEE sequence
