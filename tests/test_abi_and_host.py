@@ -153,6 +153,7 @@ def test_dropin_install_modules_in_a_fresh_interpreter():
             "from utils.quantize_manager import calibrate_qat_model, activate_learning_qparam, activate_quantizer;"
             "from utils.estimate_bn import reestimate_BN_stats, compute_scale; from utils.registry import CLASS_REGISTRY;"
             "from quantizers.quantization_manager import QuantizationManager;"
+            "from quantizers.lsq_module import LSQFakeQuantize;"
             "print(fuse_modules_unified.__module__, sorted(CLASS_REGISTRY))")
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr[-500:]
@@ -357,3 +358,33 @@ def test_yolov8_fixture_is_the_reference_network():
     out = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-800:]
     assert "same network" in out.stdout
+
+
+def test_lsq_fake_quantize_module_against_the_live_reference():
+    """quantizers/lsq_module.py::LSQFakeQuantize (the reference's torch FakeQuantize subclass, lsq_module.py:73-173):
+    same constructor, buffers, parameters, state_dict keys, phases, outputs and gradients as the live reference in
+    eight configurations (tests/live_reference_facade_check.py; kernels replaced by oracle-backed stand-ins on this
+    GPU-less host).  Skipped where /root/reference is absent."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "live_reference_facade_check.py")], cwd="/tmp",
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-1500:]
+    assert "facade matches the live reference in 8 configurations" in out.stdout
+
+
+def test_lsq_fake_quantize_module_has_no_cpu_fallback():
+    from vsiquantization_b200.quantizers.lsq_module import LSQFakeQuantize
+    fq = LSQFakeQuantize(learn_scale=True, quant_min=-128, quant_max=127, dtype=torch.qint8,
+                         qscheme=torch.per_tensor_symmetric)
+    assert set(fq.state_dict()) >= {"scale", "zero_point", "observer_enabled", "fake_quant_enabled",
+                                    "activation_post_process.min_val", "activation_post_process.max_val"}
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            fq(torch.zeros(2, 3))
+    fq.disable_observer()
+    assert fq._obs_on is False and int(fq.observer_enabled[0]) == 0

@@ -722,3 +722,57 @@ def test_moving_average_observer_matches_torch_observer(per_channel, channels_la
     m.is_learning_scale = False
     y = m.quantize(torch.randn(2, 8, 5, 5, device="cuda"))
     assert y.shape == (2, 8, 5, 5) and isinstance(m.scale, float) and isinstance(m.zero_point, int)
+
+
+@pytest.mark.parametrize("per_channel,affine", [(False, False), (True, True)])
+def test_lsq_fake_quantize_module_on_the_gpu(per_channel, affine):
+    """quantizers/lsq_module.py::LSQFakeQuantize end to end on the device: observer phase against torch.ao's observers
+    (buffers bit for bit) and the oracle (outputs), learn phase against the oracle (y, dx bit for bit; per-channel dscale /
+    dzero_point within 1e-5 of their mass, gradient scale x 5000 for activations)."""
+    from torch.ao.quantization.observer import MovingAverageMinMaxObserver as TM
+    from torch.ao.quantization.observer import MovingAveragePerChannelMinMaxObserver as TP
+    from vsiquantization_b200.quantizers.lsq_module import LSQFakeQuantize
+    qmin, qmax = (0, 255) if affine else (-128, 127)
+    kw = dict(quant_min=qmin, quant_max=qmax, dtype=torch.quint8 if affine else torch.qint8)
+    if per_channel:
+        kw.update(observer=TP, ch_axis=1, qscheme=torch.per_channel_affine if affine else torch.per_channel_symmetric)
+    else:
+        kw.update(observer=TM, qscheme=torch.per_tensor_affine if affine else torch.per_tensor_symmetric)
+    fq = LSQFakeQuantize(learn_scale=True, config_act=affine, **kw).cuda()
+    ref_obs = kw["observer"](**{k: v for k, v in kw.items() if k != "observer"})
+    ax = 1 if per_channel else None
+    C = 8 if per_channel else 1
+    g = torch.Generator().manual_seed(5)
+    for i in range(3):
+        x = torch.randn(2, 8, 6, 5, generator=g) * (1 + i) + (0.7 if affine else 0.0)
+        y = fq(x.cuda())
+        ref_obs(x)
+        s_ref, z_ref = ref_obs.calculate_qparams()
+        assert torch.equal(fq.scale.cpu(), s_ref.float().reshape(-1)), i
+        assert torch.equal(fq.zero_point.cpu().long(), z_ref.long().reshape(-1)), i
+        yo = oracle.fake_quant_fwd(x.numpy(), s_ref.double().numpy().reshape(-1), z_ref.double().numpy().reshape(-1),
+                                   qmin, qmax, ch_axis=ax)
+        assert bits_equal(y.cpu().numpy(), yo), i
+    assert tuple(fq.scale_param.shape) == ((1, 8, 1, 1) if per_channel else (1,))
+    assert ("theta" in dict(fq.named_parameters())) == (not affine)
+    fq.disable_observer()
+    x = torch.randn(2, 8, 6, 5, generator=g) * 2.5 + (0.7 if affine else 0.0)
+    gr = torch.randn(2, 8, 6, 5, generator=g)
+    xt = x.cuda().requires_grad_(True)
+    y = fq(xt)
+    y.backward(gr.cuda())
+    s = fq.scale_param.detach().cpu().numpy().reshape(-1).astype(np.float64)
+    zf = fq.zero_point_param_float.detach().cpu().numpy().reshape(-1).astype(np.float64)
+    gs = oracle.grad_scale(qmax, x.numel(), C) * (5000.0 if affine else 1.0)
+    xn, gn = x.numpy(), gr.numpy()
+    yo = oracle.fake_quant_fwd(xn, s, zf, qmin, qmax, ch_axis=ax, zp_learned=True)
+    dx, ds, dz = oracle.fake_quant_bwd(xn, gn, s, zf, qmin, qmax, ch_axis=ax, zp_learned=True, grad_scale=gs,
+                                       want_ds=True, want_dz=True)
+    assert bits_equal(y.detach().cpu().numpy(), yo) and bits_equal(xt.grad.cpu().numpy(), dx)
+    ds_k = fq.scale_param.grad.cpu().numpy().reshape(-1).astype(np.float64)
+    dz_k = fq.zero_point_param_float.grad.cpu().numpy().reshape(-1).astype(np.float64)
+    for c in range(C):
+        xc, gc = (xn[:, c], gn[:, c]) if per_channel else (xn, gn)
+        bound = gs * float(np.sum(np.abs(gc.astype(np.float64)) * ((qmax - qmin) + np.abs(xc.astype(np.float64)) / s[c])))
+        assert abs(ds_k[c] - ds[c]) <= 1e-5 * bound, (c, ds_k[c], ds[c], bound)
+        assert abs(dz_k[c] - dz[c]) <= 1e-5 * gs * s[c] * float(np.abs(gc).sum()) + 1e-12, (c, dz_k[c], dz[c])

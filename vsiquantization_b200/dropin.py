@@ -26,6 +26,7 @@ _TIER2 = {
     "quantizers.uniform": "vsiquantization_b200.quantizers.uniform",
     "quantizers.quantization_manager": "vsiquantization_b200.quantizers.quantization_manager",
     "quantizers.fake_quantize": "vsiquantization_b200.quantizers.fake_quantize",
+    "quantizers.lsq_module": "vsiquantization_b200.quantizers.lsq_module",
     "modules.fused": "vsiquantization_b200.modules.fused",
     "modules.fuse": "vsiquantization_b200.modules.fuse",
     "modules.fuse_config": "vsiquantization_b200.modules.fuse_config",
