@@ -18,6 +18,7 @@ Reference entry points exercised (file:line):
   reestimate_BN_stats                  utils/estimate_bn.py:38-101
   fuse_modules_unified + calibrate_qat_model + activate_learning_qparam
                                        modules/fuse.py:254-277, utils/quantize_manager.py:4-66
+  the same sequence on YOLOv8n         nets/yolov8.py (57 fused layers, 64x64 input)
 """
 from __future__ import annotations
 
@@ -405,6 +406,45 @@ def gen_tiny_e2e(gen):
     save("tiny_e2e", **out)
 
 
+def gen_yolov8n_e2e(gen):
+    """The tiny_e2e sequence on the reference's YOLOv8n (nets/yolov8.py, 57 fused layers) at 64x64: fuse -> calibrate ->
+    activate_learning_qparam -> activate_quantizer -> fwd+bwd.  Weights come from tests/golden/yolo_fill.py (seeded), so
+    only a few hundred scalars are stored: per-layer digests of the folded weights, calibration extrema / scales,
+    LSQ-initialised scales and the loss."""
+    import hashlib
+    from nets.yolov8 import yolo_v8_n
+    from yolo_fill import fill_
+    model = fill_(yolo_v8_n(20), 0)
+    cfg = create_fuse_config_manager(default_config=FuseConfig(bits_w=8, bits_a=8))
+    model = fuse_modules_unified(model, [["conv", "bn", "relu"]], is_trace=False, config_manager=cfg)
+    layers = [(n, m) for n, m in model.named_modules() if hasattr(m, "weight_quantizer")]
+    calib = [torch.randint(0, 256, (2, 3, 64, 64), generator=gen, dtype=torch.uint8) for _ in range(2)]
+    out = {"calib": np.stack([c.numpy() for c in calib]), "fused_names": np.array([n for n, _ in layers])}
+    out["fold_sha256"] = np.array([hashlib.sha256(m.conv_fuse.weight.detach().numpy().tobytes()
+                                                  + m.conv_fuse.bias.detach().numpy().tobytes()).hexdigest()
+                                   for _, m in layers])
+    calibrate_qat_model(model, _Loader(calib), _data_calib, "cpu")
+    for kind in ("weight_quantizer", "activation_quantizer"):
+        out[f"calib_{kind}"] = np.array([[getattr(m, kind).observer.min_val, getattr(m, kind).observer.max_val,
+                                          getattr(m, kind).scale, getattr(m, kind).zero_point] for _, m in layers],
+                                        dtype=np.float64)
+    activate_learning_qparam(model, use_init=True)
+    activate_quantizer(model)
+    for kind in ("weight_quantizer", "activation_quantizer"):
+        out[f"init_{kind}"] = np.array([float(getattr(m, kind).scale.detach()) for _, m in layers], dtype=np.float64)
+    model.train()
+    x = torch.rand(2, 3, 64, 64, generator=gen)
+    outs = model(x)
+    loss = sum((o ** 2).mean() for o in outs)
+    loss.backward()
+    out["x"] = x.numpy()
+    out["loss"] = np.array(loss.item())
+    out["out_abs_mean"] = np.array([float(o.detach().abs().mean()) for o in outs])
+    out["scale_grads"] = np.array([[float(getattr(m, k).scale.grad) for k in ("weight_quantizer", "activation_quantizer")]
+                                   for _, m in layers], dtype=np.float64)
+    save("yolov8n_e2e", **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
@@ -420,6 +460,7 @@ def main():
     gen_bn_reestimate(gen)
     gen_tiny_e2e(gen)
     gen_compute_scale(torch.Generator().manual_seed(4321))
+    gen_yolov8n_e2e(torch.Generator().manual_seed(777))
 
 
 def gen_compute_scale(gen):
@@ -442,5 +483,7 @@ def gen_compute_scale(gen):
 if __name__ == "__main__":
     if os.environ.get("VSIQ_GOLDEN_ONLY") == "compute_scale":
         gen_compute_scale(torch.Generator().manual_seed(4321))
+    elif os.environ.get("VSIQ_GOLDEN_ONLY") == "yolov8n_e2e":
+        gen_yolov8n_e2e(torch.Generator().manual_seed(777))
     else:
         main()

@@ -776,3 +776,66 @@ def test_lsq_fake_quantize_module_on_the_gpu(per_channel, affine):
         bound = gs * float(np.sum(np.abs(gc.astype(np.float64)) * ((qmax - qmin) + np.abs(xc.astype(np.float64)) / s[c])))
         assert abs(ds_k[c] - ds[c]) <= 1e-5 * bound, (c, ds_k[c], ds[c], bound)
         assert abs(dz_k[c] - dz[c]) <= 1e-5 * gs * s[c] * float(np.abs(gc).sum()) + 1e-12, (c, dz_k[c], dz[c])
+
+
+def test_yolov8n_end_to_end_against_reference_golden(monkeypatch):
+    """The tiny end-to-end sequence at YOLOv8n scale (57 fused layers, 64x64 input; golden: the REFERENCE's modules on its
+    own nets/yolov8.py on CPU, weights from tests/golden/yolo_fill.py): BN fold and weight calibration bit for bit on
+    every layer, activation calibration and LSQ initialisation to conv rounding, the quantised training step's loss."""
+    import hashlib
+    from yolo_fill import fill_
+    from vsiquantization_b200.modules.fuse import fuse_modules_unified
+    from vsiquantization_b200.modules.fuse_config import FuseConfig, create_fuse_config_manager
+    from vsiquantization_b200.nets import yolov8
+    from vsiquantization_b200.utils.quantize_manager import activate_learning_qparam, activate_quantizer, calibrate_qat_model
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)   # the golden is fp32 on CPU
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    G = load_golden("yolov8n_e2e")
+    model = fill_(yolov8.yolo_v8_n(num_classes=20), 0)
+    cfg = create_fuse_config_manager(default_config=FuseConfig(bits_w=8, bits_a=8))
+    model = fuse_modules_unified(model, [["conv", "bn", "relu"]], is_trace=False, config_manager=cfg)
+    layers = [(n, m) for n, m in model.named_modules() if hasattr(m, "weight_quantizer")]
+    assert len(layers) == 57 and [n for n, _ in layers] == list(G["fused_names"])
+    # BN fold on all 57 layers: bit for bit the IEEE op sequence of modules/fused.py:98-108 (what torch computes on CUDA and
+    # numpy on any host).  torch-on-CPU, where the golden comes from, takes its vectorised sqrt from Sleef, which is off by
+    # one ulp for ~0.7 % of inputs, so the golden's digests differ on the layers that hold such a channel.
+    plain = fill_(yolov8.yolo_v8_n(num_classes=20), 0)
+    blocks = {n + ".conv": b for n, b in plain.named_modules() if hasattr(b, "conv") and hasattr(b, "norm")}
+    same_as_golden = 0
+    for i, (n, m) in enumerate(layers):
+        cv, bn = blocks[n].conv, blocks[n].norm
+        t = (bn.weight.detach().numpy() / np.sqrt(bn.running_var.numpy() + np.float32(bn.eps))).astype(np.float32)
+        Wf = (cv.weight.detach().numpy() * t.reshape(-1, 1, 1, 1)).astype(np.float32)
+        bf = (bn.bias.detach().numpy() + (np.float32(0) - bn.running_mean.numpy()) * t).astype(np.float32)
+        assert bits_equal(m.conv_fuse.weight.detach().cpu().numpy(), Wf), n
+        assert bits_equal(m.conv_fuse.bias.detach().cpu().numpy(), bf), n
+        same_as_golden += hashlib.sha256(Wf.tobytes() + bf.tobytes()).hexdigest() == str(G["fold_sha256"][i])
+    assert same_as_golden >= 20  # the layers without a Sleef-affected channel match the reference's CPU bits exactly
+    model.cuda()
+    calibrate_qat_model(model, _loader([torch.as_tensor(c) for c in G["calib"]]), _data_calib, "cuda")
+    for i, (n, m) in enumerate(layers):
+        q, a = m.weight_quantizer, m.activation_quantizer
+        wmn, wmx, ws, wz = G["calib_weight_quantizer"][i]  # within one ulp of the reference's CPU fold (see above)
+        assert q.observer.min_val == pytest.approx(wmn, rel=3e-7) and q.observer.max_val == pytest.approx(wmx, rel=3e-7), n
+        assert q.scale == pytest.approx(ws, rel=3e-7) and q.zero_point == wz == 0, n
+        assert (q.scale, q.zero_point) == oracle.qparams(q.observer.min_val, q.observer.max_val, 8, True), n
+        mn, mx, s, z = G["calib_activation_quantizer"][i]
+        assert a.observer.max_val == pytest.approx(mx, rel=1e-3) and a.scale == pytest.approx(s, rel=1e-3), n
+        assert (a.scale, a.zero_point) == oracle.qparams(a.observer.min_val, a.observer.max_val, 8, True), n
+    activate_learning_qparam(model, use_init=True)
+    activate_quantizer(model)
+    for i, (n, m) in enumerate(layers):
+        assert float(m.weight_quantizer.scale.detach()) == pytest.approx(float(G["init_weight_quantizer"][i]), rel=2e-6), n
+        assert float(m.activation_quantizer.scale.detach()) == pytest.approx(float(G["init_activation_quantizer"][i]), rel=1e-3), n
+        with torch.no_grad():  # pin the reference's initial scales so the step below is comparable
+            m.weight_quantizer.scale.fill_(float(G["init_weight_quantizer"][i]))
+            m.activation_quantizer.scale.fill_(float(G["init_activation_quantizer"][i]))
+    model.train()
+    outs = model(dev(G["x"]))
+    loss = sum((o ** 2).mean() for o in outs)
+    loss.backward()
+    assert loss.item() == pytest.approx(float(G["loss"]), rel=0.1)
+    for o, ref in zip(outs, G["out_abs_mean"]):
+        assert float(o.detach().abs().mean()) == pytest.approx(float(ref), rel=0.1)
+    grads = torch.stack([torch.stack([m.weight_quantizer.scale.grad, m.activation_quantizer.scale.grad]) for _, m in layers])
+    assert bool(torch.isfinite(grads).all()) and grads.dtype == torch.float64
