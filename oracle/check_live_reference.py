@@ -9,6 +9,8 @@ the C oracle on the same seeded inputs:
   * the learnable-scale path (uniform.py:47-52,242-271; 0-dim float64 Parameter, quantization_manager.py:99):
     y and dx bit for bit, dscale within 1e-5 of the absolute mass of its terms (the reference's own fp32 sums cancel);
   * the same forward with degenerate scales (0, negative, 1e-30, 1e30, inf, NaN, 2^-41, 2^41);
+  * the construction-time BN fold (modules/fused.py:92-108): bit for bit except where torch-on-CPU's vectorised sqrt
+    (Sleef) is itself one ulp off the correctly rounded value -- there W' may differ by up to three ulps;
   * MinMaxObserver traces (observers/minmax.py:32-74): running min / max, scale and zero-point exactly (Python doubles);
   * LSQFakeQuantize per-channel learn phase (quantizers/lsq_module.py:147-173,254-274,317-358): y, dx bit for bit, per-channel
     dscale / dzero_point within 1e-5 of their mass.
@@ -163,8 +165,41 @@ def main() -> int:
             zm = gs * float(np.sum(np.abs(g[:, c].astype(np.float64) * np.float32(s[c]))))
             if abs(ds[c] - ds_ref[c]) > 1e-5 * m + 1e-30 or abs(dz[c] - dz_ref[c]) > 1e-5 * zm + 1e-30:
                 bad.append(("lsq per-channel ds/dz", case, c, ds[c], ds_ref[c], dz[c], dz_ref[c]))
+    # ---- BN fold (modules/fused.py:92-108): the oracle is the IEEE op sequence; torch-on-CPU's vectorised sqrt (Sleef) is
+    # one ulp off for a fraction of a percent of inputs, so the comparison is "within one ulp", and mostly bit for bit
+    from modules.fused import ConvBnReLU
+    ulp_off = total = 0
+    for case in range(max(3, args.cases // 10)):
+        cin, cout, k = int(rng.integers(1, 9)), int(rng.integers(1, 40)), int(rng.choice([1, 3]))
+        cv = torch.nn.Conv2d(cin, cout, k, bias=bool(case % 2))
+        bn = torch.nn.BatchNorm2d(cout, eps=0.001)
+        with torch.no_grad():
+            bn.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32)))
+            bn.bias.copy_(torch.from_numpy(rng.standard_normal(cout).astype(np.float32) * 0.1))
+            bn.running_mean.copy_(torch.from_numpy(rng.standard_normal(cout).astype(np.float32) * 0.1))
+            bn.running_var.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32)))
+        layer = ConvBnReLU(cv, bn, torch.nn.ReLU(), "MinMaxObserver", "UniformQuantizer", "MinMaxObserver",
+                           "UniformQuantizer", True, True, True, 8, 8)
+        Wf, bf = oracle.bn_fold(cv.weight.detach().numpy(), cv.bias.detach().numpy() if cv.bias is not None else None,
+                                bn.weight.detach().numpy(), bn.bias.detach().numpy(), bn.running_mean.numpy(),
+                                bn.running_var.numpy(), bn.eps)
+        # a one-ulp sqrt moves t = gamma / std by at most one ulp, W * t by at most two more after rounding
+        Wr, br = layer.conv_fuse.weight.detach().numpy(), layer.conv_fuse.bias.detach().numpy()
+        d = np.abs(Wf.view(np.int32).astype(np.int64) - Wr.view(np.int32).astype(np.int64))
+        total += d.size + br.size
+        ulp_off += int((d > 0).sum()) + int((bf != br).sum())
+        if d.max() > 3:
+            bad.append(("bn fold: W' more than three ulps from the reference", case, int(d.max())))
+        t_mag = np.abs(bn.weight.detach().numpy()) / np.sqrt(bn.running_var.numpy() + np.float32(bn.eps))
+        b0 = np.abs(cv.bias.detach().numpy()) if cv.bias is not None else 0.0
+        mass_b = np.abs(bn.bias.detach().numpy()) + (b0 + np.abs(bn.running_mean.numpy())) * t_mag
+        if np.any(np.abs(bf.astype(np.float64) - br) > 4e-7 * mass_b):
+            bad.append(("bn fold: b' off", case, float(np.abs(bf - br).max())))
+    if total and ulp_off > 0.05 * total:
+        bad.append(("bn fold: too many one-ulp differences", ulp_off, total))
     for b in bad[:20]:
         print("MISMATCH", b)
+    print(f"bn fold: {ulp_off} of {total} values differ from torch-on-CPU by its Sleef sqrt (<= 3 ulps), the rest bit for bit")
     print(f"{args.cases} uniform/observer cases, {max(4, args.cases // 6)} LSQFakeQuantize cases, {len(bad)} mismatches")
     return 1 if bad else 0
 
