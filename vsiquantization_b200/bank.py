@@ -21,12 +21,12 @@ backward pass; the one-launch backward can only run after the LAST weight gradie
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional
+from typing import List
 
 import torch
 
 from . import _lib, ops
-from ._lib import F32, MtEntry, check, lib
+from ._lib import MtEntry, check, lib
 
 
 def _dense_in_memory(w: torch.Tensor) -> bool:

@@ -6,7 +6,6 @@ used for device memory, streams and autograd bookkeeping only; all arithmetic ha
 from __future__ import annotations
 
 import ctypes
-import math
 from dataclasses import dataclass
 from typing import Optional, Tuple, Union
 

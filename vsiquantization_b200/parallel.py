@@ -15,7 +15,7 @@ torch.distributed (NCCL over NVLink on the box, gloo in the CPU tests) is the tr
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 import torch.distributed as dist
