@@ -170,16 +170,19 @@ __device__ __forceinline__ float clamp_t(float t, const QP& p) { return min_nan(
 __device__ __forceinline__ float quantize_t(float t, const QP& p) { return rintf(clamp_t(t, p)); }
 __device__ __forceinline__ float dequant(float q, const QP& p) { return __fmul_rn(__fsub_rn(q, p.z), p.s); }
 
-static __device__ __noinline__ Elem elem_slow(float x, const QP& p) {
+// The IEEE division is the only out-of-line piece: scalar in, scalar out, so the call passes everything in registers and
+// no caller ever has to park its QP (or the op that holds it) in local memory for the sake of this rare path.
+static __device__ __noinline__ float div_ieee(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ Elem elem_slow(float x, const QP& p) {
     Elem e;
-    e.v = __fdiv_rn(x, p.s);
+    e.v = div_ieee(x, p.s);
     e.t = __fadd_rn(e.v, p.z);
     e.q = quantize_t(e.t, p);
     e.m = (e.t >= p.tlo) && (e.t <= p.thi);
     return e;
 }
-static __device__ __noinline__ float dx_slow(float g, bool m, const QP& p) {
-    return __fdiv_rn(m ? __fmul_rn(g, p.s) : 0.0f, p.s);
+__device__ __forceinline__ float dx_slow(float g, bool m, const QP& p) {
+    return div_ieee(m ? __fmul_rn(g, p.s) : 0.0f, p.s);
 }
 
 // ---- the same results without a per-element MUFU.RCP + FCHK + branch ------------------------------
