@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vsiquantization_b200 import ops
 from tools.microbench import timed
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+if os.environ.get("BENCH_SIDE_STREAM", "1") != "0":  # programmatic dependent launch needs a non-default stream
+    torch.cuda.set_stream(torch.cuda.Stream())
 shapes = [(B, 32, 320, 320), (B, 64, 160, 160), (B, 128, 80, 80), (B, 256, 40, 40), (B, 512, 20, 20), (B, 64, 80, 80), (B, 128, 20, 20)]
 flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
 for shp in shapes:

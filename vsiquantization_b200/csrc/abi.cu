@@ -60,6 +60,32 @@ int launch_grid(uint32_t n_ctas_wanted) {
     return (int)(n_ctas_wanted < cap ? n_ctas_wanted : cap);
 }
 
+bool pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("VSIQ_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+int ci_sched_override() {
+    static const int v = []() {
+        const char* e = getenv("VSIQ_CI_SCHED");
+        if (!e) return -1;
+        if (e[0] == 's') return 0;
+        if (e[0] == 'd') return 1;
+        if (e[0] == 'i') return 2;
+        return -1;
+    }();
+    return v;
+}
+
+int ci_tile_override() {
+    static const int v = []() {
+        const char* e = getenv("VSIQ_CI_TILE");
+        const int n = e ? atoi(e) : 0;
+        return n > 0 && n <= 4096 ? n : 0;
+    }();
+    return v;
+}
+
 bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 int check_layout(const vsiq_layout* l) {

@@ -9,14 +9,17 @@
 // 317-358); the bias add is the fused layer's conv bias (modules/fused.py:124-130) moved into this epilogue so that its
 // gradient (ATen: a separate full-tensor reduction per layer) rides along with dx.
 //
-// Mapping: C % 4 == 0 and C <= 1024.  A 128-bit vector holds 4 consecutive channels; with G = C/4 vector groups per row
-// only T = (256 / G) * G threads of a CTA are active, so thread t ALWAYS owns channel group t % G: its four channels'
-// qparams, bias and gradient accumulators live in registers for the whole kernel.  Tiles are handed out dynamically
-// (atomic counter: hardware-like balancing without a CTA launch per tile), accumulators are carried across tiles in fp64
-// and flushed ONCE per CTA; records are combined in a fixed order (deterministic) by the last CTA or a finalize launch.
+// Mapping (ci_common.cuh): C % 4 == 0 and C <= 1024.  A 128-bit vector holds 4 consecutive channels; with G = C/4 vector
+// groups per row only T = (256 / G) * G threads of a CTA are active, so thread t ALWAYS owns channel group t % G: its four
+// channels' qparams, bias and gradient accumulators live in registers for the whole kernel.  CTAs are persistent and own
+// a range of steps (static equal split by default, 16-step tiles from an atomic queue as the alternative); accumulators
+// are carried in fp64 and flushed ONCE per CTA; records are combined in a fixed order (deterministic) by the last CTA
+// (narrow records) or by ci_finalize_kernel, launched as a programmatic dependent of the streaming kernel.
 //
 // Roofline: HBM; 8 B/element forward, 12 B/element backward, as for the NCHW kernels.
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "ci_common.cuh"
 
@@ -32,8 +35,6 @@ struct CiOut {
 };
 
 // Record layout per CTA (doubles): [E: nq][B: nq][DB: C]   with nq = C (per-channel qparams) or 1 (per tensor)
-__device__ __forceinline__ int ci_record_width(int C, bool pcq, bool bias) { return 2 * (pcq ? C : 1) + (bias ? C : 0); }
-
 __device__ __forceinline__ void ci_store(const CiOut& o, const QPDev& qpd, bool pcq, bool bias, int C, int idx, double v) {
     // idx addresses the record: [0,nq) E, [nq,2nq) B, [2nq, 2nq+C) DB
     const int nq = pcq ? C : 1;
@@ -57,9 +58,6 @@ __device__ __forceinline__ void ci_store(const CiOut& o, const QPDev& qpd, bool 
     }
 }
 
-// Combine 32 consecutive record entries [base, base+32) over n_rec per-CTA records: warp w sums records w, w+8, ...
-// (each read is one coalesced 256-byte row segment, four independent chains per thread), then the eight slices are
-// added in a fixed order.  Deterministic.  s_part: [kWarps][32] doubles of shared memory.
 // CTA-wide barrier over the first kThreads threads: plain __syncthreads() for 256-thread CTAs, named barrier 1 when a
 // producer warp rides along (ci_bwd_tma_kernel) and must not take part.
 template <bool NAMED>
@@ -70,6 +68,9 @@ __device__ __forceinline__ void ci_sync() {
         __syncthreads();
 }
 
+// Combine 32 consecutive record entries [base, base+32) over n_rec per-CTA records (last-CTA path, narrow records): warp
+// w sums records w, w+8, ... (each read is one coalesced 256-byte row segment, four independent chains per thread), then
+// the eight slices are added in a fixed order.  Deterministic.  s_part: [kWarps][32] doubles of shared memory.
 template <bool NAMED = false>
 __device__ __forceinline__ void ci_combine_chunk(const double* records, int width, uint32_t n_rec, int base,
                                                  double (*s_part)[32], const CiOut& o, const QPDev& qpd, bool pcq,
@@ -98,12 +99,28 @@ __device__ __forceinline__ void ci_combine_chunk(const double* records, int widt
     }
 }
 
+// Wide records: one CTA per 8 record entries (ci_combine8_sum), resident early as a programmatic dependent of the
+// streaming kernel.
 __global__ void __launch_bounds__(kThreads)
     ci_finalize_kernel(const void* ws, int width, uint32_t n_rec, CiOut o, QPDev qpd, int pcq, int bias, int C) {
-    __shared__ double s_part[kWarps][32];
+    __shared__ double s_part[kWarps][kCombineEntries];
     const double* records = (const double*)((const char*)ws + kWsHeader);
-    for (int base = blockIdx.x * 32; base < width; base += gridDim.x * 32)
-        ci_combine_chunk(records, width, n_rec, base, s_part, o, qpd, pcq, bias, C);
+    const int idx = blockIdx.x * kCombineEntries + (threadIdx.x & 7);
+    pdl_wait();  // the streaming grid has completed and its records are visible
+    const double v = ci_combine8_sum(records, (size_t)width, n_rec, (size_t)idx, idx < width, s_part);
+    if (threadIdx.x < kCombineEntries && idx < width) ci_store(o, qpd, pcq != 0, bias != 0, C, idx, v);
+}
+
+// The last CTA to leave resets the ticket (and the tile counter of the dynamic schedule) for the next launch.
+__device__ __forceinline__ void ci_leave(void* ws) {
+    if (threadIdx.x == 0) {
+        unsigned int* counter = (unsigned int*)ws + 1;
+        unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
+        if (tk == gridDim.x - 1) {
+            *(unsigned int*)ws = 0;
+            *counter = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -111,10 +128,13 @@ template <bool PCQ, bool BIAS, bool RELU>
 __global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: measured 5.84 -> 6.39 TB/s on [64,32,320,320]
     ci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y, CiGeom geo,
                   QPDev qpd, void* ws) {
-    unsigned int* counter = (unsigned int*)ws + 1;
     const int t = threadIdx.x;
     const bool active = t < geo.threads;
     const int c0 = (t % geo.groups) * kCiVec;
+    constexpr int kU = 2 * kCiUnroll;  // forward: one input, so twice the loads in flight
+    __shared__ uint32_t s_tile[2];
+    CiSched sc;
+    CiRange r = ci_sched_first(geo, sc, ws, s_tile, t);
     QP p[kCiVec];
     float bv[kCiVec];
     bool all_fast = true;
@@ -124,157 +144,109 @@ __global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: 
         all_fast = all_fast && p[e].fast;
         bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
     }
-    __shared__ uint32_t s_tile[2];
-    TileQueue tq;
-    tq_init(tq, counter, geo.n_tiles, s_tile);
-    constexpr int kU = 2 * kCiUnroll, kB = kCiBatches / 2;  // forward: one input, so twice the loads in flight
-    for (uint32_t tile = tq_current(tq, s_tile); tile < geo.n_tiles; tq_advance(tq, s_tile), tile = tq_current(tq, s_tile)) {
-        if (!active) continue;
-        const int64_t vb = (int64_t)tile * geo.tile_vecs;
+    const int64_t stride = (int64_t)geo.threads * kCiVec;  // floats between a thread's consecutive vectors
+    const int64_t dy = y - x;
+    for (;;) {
+        if (active) {
+            const float* xp = x + ((int64_t)r.s0 * geo.threads + t) * kCiVec;
 #pragma unroll 1
-        for (int b = 0; b < kB; ++b) {
-            Vec4 vin[kU];
-            bool ok[kU];
+            for (uint32_t s = r.s0; s < r.s1; s += kU, xp += kU * stride) {
+                Vec4 vin[kU];
 #pragma unroll
-            for (int j = 0; j < kU; ++j) {
-                const int64_t v = vb + (int64_t)(b * kU + j) * geo.threads + t;
-                ok[j] = v < geo.n_vec;
-                if (ok[j]) vin[j] = ld4(x + v * kCiVec);
-            }
+                for (int j = 0; j < kU; ++j)
+                    if (s + j < r.s1) vin[j] = ld4(xp + j * stride);
 #pragma unroll
-            for (int j = 0; j < kU; ++j) {
-                if (!ok[j]) continue;
-                const int64_t v = vb + (int64_t)(b * kU + j) * geo.threads + t;
-                Vec4 out;
-                bool bad = !all_fast;
-#pragma unroll
-                for (int e = 0; e < kCiVec; ++e) {
-                    float xe = BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e];
-                    if (RELU) xe = max_nan(xe, 0.0f);
-                    out.v[e] = dequant(elem_fast(xe, p[e], bad).q, p[e]);
-                }
-                if (bad) {
+                for (int j = 0; j < kU; ++j) {
+                    if (s + j >= r.s1) continue;
+                    Vec4 out;
+                    bool bad = !all_fast;
 #pragma unroll
                     for (int e = 0; e < kCiVec; ++e) {
                         float xe = BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e];
                         if (RELU) xe = max_nan(xe, 0.0f);
-                        out.v[e] = dequant(elem_slow(xe, p[e]).q, p[e]);
+                        out.v[e] = dequant(elem_fast(xe, p[e], bad).q, p[e]);
                     }
+                    if (bad) {
+#pragma unroll
+                        for (int e = 0; e < kCiVec; ++e) {
+                            float xe = BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e];
+                            if (RELU) xe = max_nan(xe, 0.0f);
+                            out.v[e] = dequant(elem_slow(xe, p[e]).q, p[e]);
+                        }
+                    }
+                    st4(const_cast<float*>(xp) + j * stride + dy, out);
                 }
-                st4(y + v * kCiVec, out);
             }
         }
+        if (!ci_sched_next(geo, sc, s_tile, t, r)) break;
     }
-    // the last CTA to leave resets the tile counter for the next launch
-    __shared__ int s_last;
-    if (threadIdx.x == 0) {
-        unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
-        s_last = (tk == gridDim.x - 1);
-        if (s_last) {
-            *(unsigned int*)ws = 0;
-            *counter = 0;
-        }
-    }
+    if (geo.sched == kCiDynamic) ci_leave(ws);
 }
 
 // --------------------------------------------------------------------------------------------- backward
-// One tile of the backward: kCiBatches x kCiUnroll vectors per thread.  FULL = every vector of the tile is in bounds.
-template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS, bool FULL>
-__device__ __forceinline__ void ci_bwd_tile(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx,
-                                            const CiGeom& geo, int64_t vb, uint32_t tile, int t, int c0, int t_row,
-                                            int rows_per_step, int64_t tile_rows, int64_t g_pitch, const QP (&p)[kCiVec],
-                                            const float (&bv)[kCiVec], bool all_fast, float (&te)[kCiVec],
-                                            float (&tb)[kCiVec], float (&tdb)[kCiVec]) {
-#pragma unroll 1
-    for (int b = 0; b < kCiBatches; ++b) {
-        Vec4 vx[kCiUnroll], vg[kCiUnroll];
-        bool ok[kCiUnroll];
+// The element arithmetic of one vector (four channels): dx, and the LSQ terms when WANT_DS.
+template <bool BIAS, bool RELU, bool WANT_DS>
+__device__ __forceinline__ void ci_bwd_vec(const Vec4& vx, const Vec4& vg, const QP (&p)[kCiVec], const float (&bv)[kCiVec],
+                                           bool all_fast, Vec4& out, float (&te)[kCiVec], float (&tb)[kCiVec],
+                                           float (&tdb)[kCiVec]) {
+    float ve[kCiVec], vbz[kCiVec];
+    bool bad = !all_fast;
 #pragma unroll
-        for (int j = 0; j < kCiUnroll; ++j) {
-            const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
-            ok[j] = FULL || v < geo.n_vec;
-            if (ok[j]) {
-                vx[j] = ld4(x + v * kCiVec);
-                const int64_t row = (int64_t)tile * tile_rows + (int64_t)(b * kCiUnroll + j) * rows_per_step + t_row;
-                vg[j] = ld4(g + row * g_pitch + c0);
+    for (int e = 0; e < kCiVec; ++e) {
+        const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
+        const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+        const float ge = vg.v[e];
+        const Elem el = elem_fast(xe, p[e], bad);
+        float d = dx_fast(ge, el.m, p[e], bad);
+        if (RELU) d = xb > 0.0f ? d : 0.0f;
+        out.v[e] = d;
+        if (WANT_DS) {
+            const float dd = __fsub_rn(el.q, p[e].z);
+            const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
+            ve[e] = ge * (dd - mv);
+            vbz[e] = el.m ? 0.0f : ge;
+        }
+    }
+    if (bad) {  // rare: IEEE sequences for the whole vector
+#pragma unroll
+        for (int e = 0; e < kCiVec; ++e) {
+            const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
+            const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+            const float ge = vg.v[e];
+            const Elem el = elem_slow(xe, p[e]);
+            float d = dx_slow(ge, el.m, p[e]);
+            if (RELU) d = xb > 0.0f ? d : 0.0f;
+            out.v[e] = d;
+            if (WANT_DS) {
+                const float dd = __fsub_rn(el.q, p[e].z);
+                const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
+                ve[e] = ge * (dd - mv);
+                vbz[e] = el.m ? 0.0f : ge;
             }
         }
+    }
 #pragma unroll
-        for (int j = 0; j < kCiUnroll; ++j) {
-            if (!ok[j]) continue;
-            const int64_t v = vb + (int64_t)(b * kCiUnroll + j) * geo.threads + t;
-            Vec4 out;
-            float ve[kCiVec], vbz[kCiVec];
-            bool bad = !all_fast;
-#pragma unroll
-            for (int e = 0; e < kCiVec; ++e) {
-                const float xb = BIAS ? __fadd_rn(vx[j].v[e], bv[e]) : vx[j].v[e];
-                const float xe = RELU ? max_nan(xb, 0.0f) : xb;
-                const float ge = vg[j].v[e];
-                const Elem el = elem_fast(xe, p[e], bad);
-                float d = dx_fast(ge, el.m, p[e], bad);
-                if (RELU) d = xb > 0.0f ? d : 0.0f;
-                out.v[e] = d;
-                if (WANT_DS) {
-                    const float dd = __fsub_rn(el.q, p[e].z);
-                    const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
-                    ve[e] = ge * (dd - mv);
-                    vbz[e] = el.m ? 0.0f : ge;
-                }
-            }
-            if (bad) {  // rare: IEEE sequences for the whole vector
-#pragma unroll
-                for (int e = 0; e < kCiVec; ++e) {
-                    const float xb = BIAS ? __fadd_rn(vx[j].v[e], bv[e]) : vx[j].v[e];
-                    const float xe = RELU ? max_nan(xb, 0.0f) : xb;
-                    const float ge = vg[j].v[e];
-                    const Elem el = elem_slow(xe, p[e]);
-                    float d = dx_slow(ge, el.m, p[e]);
-                    if (RELU) d = xb > 0.0f ? d : 0.0f;
-                    out.v[e] = d;
-                    if (WANT_DS) {
-                        const float dd = __fsub_rn(el.q, p[e].z);
-                        const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
-                        ve[e] = ge * (dd - mv);
-                        vbz[e] = el.m ? 0.0f : ge;
-                    }
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < kCiVec; ++e) {
-                if (WANT_DS) {
-                    te[e] += ve[e];
-                    tb[e] += vbz[e];
-                }
-                if (BIAS) tdb[e] += out.v[e];
-            }
-            st4(dx + v * kCiVec, out);
+    for (int e = 0; e < kCiVec; ++e) {
+        if (WANT_DS) {
+            te[e] += ve[e];
+            tb[e] += vbz[e];
         }
+        if (BIAS) tdb[e] += out.v[e];
     }
 }
 
-// One flush per CTA: fixed-order reduction over the threads that share a channel group, record write, ticket, and (last
-// CTA, narrow records) the combine.  Runs in the first kThreads threads of the CTA; s_acc is [kThreads][12] doubles.
+// One flush per CTA: fixed-order reduction over the threads that share a channel group, record write, and (narrow
+// records) ticket + combine by the last CTA.  Runs in the first kThreads threads; s_acc is [kThreads][12] doubles.
 template <bool PCQ, bool BIAS, bool WANT_DS, bool NAMED>
 __device__ __forceinline__ void ci_bwd_flush(const double (&acc_e)[kCiVec], const double (&acc_b)[kCiVec],
                                              const double (&acc_db)[kCiVec], double (*s_acc)[3 * kCiVec],
                                              const CiGeom& geo, const QPDev& qpd, void* ws, const CiOut& o,
                                              int use_ticket, int t, bool active) {
-    unsigned int* counter = (unsigned int*)ws + 1;
     double* records = ws_partials(ws);
     const int C = geo.channels;
     const uint32_t n_ctas = gridDim.x, cta = blockIdx.x;
-    // ---- one flush per CTA: fixed-order reduction over the threads that share a channel group ----
-    if (!WANT_DS && !BIAS) {
-        __shared__ int s_last0;
-        if (threadIdx.x == 0) {
-            unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
-            s_last0 = (tk == n_ctas - 1);
-            if (s_last0) {
-                *(unsigned int*)ws = 0;
-                *counter = 0;
-            }
-        }
+    if (!WANT_DS && !BIAS) {  // plain STE: nothing to reduce
+        if (geo.sched == kCiDynamic) ci_leave(ws);
         return;
     }
 #pragma unroll
@@ -323,7 +295,7 @@ __device__ __forceinline__ void ci_bwd_flush(const double (&acc_e)[kCiVec], cons
                     const int c = idx - which * nq;
                     for (int k = 0; k < reps; ++k) s += s_acc[k * geo.groups + c / kCiVec][which * kCiVec + (c % kCiVec)];
                 } else {
-                    s = s_pt[which];  // block-reduced below
+                    s = s_pt[which];
                 }
             }
         } else {
@@ -332,11 +304,14 @@ __device__ __forceinline__ void ci_bwd_flush(const double (&acc_e)[kCiVec], cons
         }
         rec[idx] = s;
     }
-    // ticket; the last CTA also resets the tile counter
+    // wide records under the static schedule: nothing else to do -- ci_finalize_kernel (a programmatic dependent of this
+    // grid) sees the records once the grid has completed
+    if (!use_ticket && geo.sched != kCiDynamic) return;
     __shared__ int s_last;
     __threadfence();
     ci_sync<NAMED>();
     if (threadIdx.x == 0) {
+        unsigned int* counter = (unsigned int*)ws + 1;
         unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
         s_last = (tk == n_ctas - 1);
         if (s_last) {
@@ -352,17 +327,20 @@ __device__ __forceinline__ void ci_bwd_flush(const double (&acc_e)[kCiVec], cons
         ci_combine_chunk<NAMED>(records, width, n_ctas, base, s_part, o, qpd, PCQ, BIAS, C);
 }
 
+// Direct-load backward: used when grad_output is pitched (a channel slice of a wider NHWC tensor, which is what the
+// backward of torch.cat hands out: row r of g starts at g + r * g_pitch) or when VSIQ_CI_TMA=0.
 template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
 __global__ void __launch_bounds__(kThreads, 2)
     ci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ g,
                   float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket, int64_t g_pitch) {
     __shared__ double s_acc[kThreads][3 * kCiVec];  // per thread: e[4], b[4], db[4]
-    unsigned int* counter = (unsigned int*)ws + 1;
-    double* records = ws_partials(ws);
     const int t = threadIdx.x;
     const bool active = t < geo.threads;
-    const int C = geo.channels;
     const int c0 = (t % geo.groups) * kCiVec;
+    pdl_launch_dependents();
+    __shared__ uint32_t s_tile[2];
+    CiSched sc;
+    CiRange r = ci_sched_first(geo, sc, ws, s_tile, t);
     QP p[kCiVec];
     float bv[kCiVec];
     bool all_fast = true;
@@ -373,54 +351,69 @@ __global__ void __launch_bounds__(kThreads, 2)
         bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
     }
     double acc_e[kCiVec], acc_b[kCiVec], acc_db[kCiVec];
+    float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials, folded into the fp64 sums every 16 vectors
 #pragma unroll
-    for (int e = 0; e < kCiVec; ++e) acc_e[e] = acc_b[e] = acc_db[e] = 0.0;
-    // grad_output may be a channel slice of a wider NHWC tensor (the backward of torch.cat hands out such views): row r
-    // of g starts at g + r * g_pitch.  Thread t's vectors sit in rows tile*tile_rows + step*rows_per_step + t/G.
-    const int rows_per_step = geo.threads / geo.groups;
-    const int64_t tile_rows = geo.tile_vecs / geo.groups;
-    const int t_row = t / geo.groups;
-
-    __shared__ uint32_t s_tile[2];
-    TileQueue tq;
-    tq_init(tq, counter, geo.n_tiles, s_tile);
-    for (uint32_t tile = tq_current(tq, s_tile); tile < geo.n_tiles; tq_advance(tq, s_tile), tile = tq_current(tq, s_tile)) {
-        if (!active) continue;
-        const int64_t vb = (int64_t)tile * geo.tile_vecs;
-        float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials of this tile
-#pragma unroll
-        for (int e = 0; e < kCiVec; ++e) te[e] = tb[e] = tdb[e] = 0.0f;
-        // interior tiles carry no per-vector bounds predicates (four fewer live predicate registers in the hot loop)
-        if (vb + geo.tile_vecs <= geo.n_vec)
-            ci_bwd_tile<PCQ, BIAS, RELU, WANT_DS, true>(x, g, dx, geo, vb, tile, t, c0, t_row, rows_per_step, tile_rows,
-                                                        g_pitch, p, bv, all_fast, te, tb, tdb);
-        else
-            ci_bwd_tile<PCQ, BIAS, RELU, WANT_DS, false>(x, g, dx, geo, vb, tile, t, c0, t_row, rows_per_step, tile_rows,
-                                                         g_pitch, p, bv, all_fast, te, tb, tdb);
-#pragma unroll
-        for (int e = 0; e < kCiVec; ++e) {
-            if (WANT_DS) {
-                acc_e[e] += (double)te[e];
-                acc_b[e] += (double)tb[e];
-            }
-            if (BIAS) acc_db[e] += (double)tdb[e];
-        }
+    for (int e = 0; e < kCiVec; ++e) {
+        acc_e[e] = acc_b[e] = acc_db[e] = 0.0;
+        te[e] = tb[e] = tdb[e] = 0.0f;
     }
-
+    // thread t's vector of step s sits in row s * (T/G) + t/G: x / dx advance by T vectors per step, g by T/G pitched rows
+    const int rows_per_step = geo.threads / geo.groups;
+    const int64_t stride = (int64_t)geo.threads * kCiVec;
+    const int64_t gstride = (int64_t)rows_per_step * g_pitch;
+    const int64_t ddx = dx - x;
+    for (;;) {
+        if (active) {
+            const float* xp = x + ((int64_t)r.s0 * geo.threads + t) * kCiVec;
+            const float* gp = g + ((int64_t)r.s0 * rows_per_step + t / geo.groups) * g_pitch + c0;
+            int it = 0;
+#pragma unroll 1
+            for (uint32_t s = r.s0; s < r.s1; s += kCiUnroll, xp += kCiUnroll * stride, gp += kCiUnroll * gstride) {
+                Vec4 vx[kCiUnroll], vg[kCiUnroll];
+#pragma unroll
+                for (int j = 0; j < kCiUnroll; ++j) {
+                    if (s + j < r.s1) {
+                        vx[j] = ld4(xp + j * stride);
+                        vg[j] = ld4(gp + j * gstride);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kCiUnroll; ++j) {
+                    if (s + j >= r.s1) continue;
+                    Vec4 out;
+                    ci_bwd_vec<BIAS, RELU, WANT_DS>(vx[j], vg[j], p, bv, all_fast, out, te, tb, tdb);
+                    st4(const_cast<float*>(xp) + j * stride + ddx, out);
+                }
+                if ((++it & (kCiBatches - 1)) == 0 || s + kCiUnroll >= r.s1) {
+#pragma unroll
+                    for (int e = 0; e < kCiVec; ++e) {
+                        if (WANT_DS) {
+                            acc_e[e] += (double)te[e];
+                            acc_b[e] += (double)tb[e];
+                        }
+                        if (BIAS) acc_db[e] += (double)tdb[e];
+                        te[e] = tb[e] = tdb[e] = 0.0f;
+                    }
+                }
+            }
+        }
+        if (!ci_sched_next(geo, sc, s_tile, t, r)) break;
+    }
     ci_bwd_flush<PCQ, BIAS, WANT_DS, false>(acc_e, acc_b, acc_db, s_acc, geo, qpd, ws, o, use_ticket, t, active);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Backward with TMA-staged inputs (dense grad_output).  ncu on ci_bwd_kernel: the warps wait on global loads
+// Backward with TMA-staged inputs (dense grad_output).  ncu on the direct-load kernel: the warps wait on global loads
 // ("long scoreboard" is the top stall, issue slots 58 % used) while 128 registers per thread cap the CTA count at two, so
 // neither more warps nor more loads per thread are available.  Here a producer warp streams x and g through a ring of
 // kCiStages shared-memory stages with bulk asynchronous copies (cp.async.bulk -> mbarrier complete_tx), the eight
 // consumer warps read 128-bit vectors from shared memory: bytes in flight per SM no longer cost registers, and the
-// consumers never touch a global load.  One stage = one batch (T * kCiUnroll vectors, <= 16 KB per input), units of a
-// tile arrive in order; tiles come from the same atomic queue as before (claimed by the producer).
+// consumers never touch a global load.  One stage = one unit of up to kCiUnroll steps (T * kCiUnroll vectors, <= 16 KB per
+// input); the producer walks the CTA's step range (static split) or claims 16-step tiles from the atomic queue.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kCiStages = 3;
-constexpr uint32_t kCiNoTile = 0xffffffffu;
+constexpr uint32_t kCiDone = 0xffffffffu;
+constexpr uint32_t kCiTileEnd = 0x80000000u;  // the consumers fold their fp32 partials at tile ends (deterministic sums)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -459,8 +452,9 @@ __device__ __forceinline__ Vec4 lds4(const float* p) {
 struct CiRing {
     uint64_t full[kCiStages];
     uint64_t empty[kCiStages];
-    uint32_t tile[kCiStages];   // tile of the unit parked in the stage (kCiNoTile: no more work)
-    uint32_t batch[kCiStages];  // its batch index inside the tile
+    uint32_t nvec[kCiStages];  // vectors of the unit parked in the stage | kCiTileEnd on the last unit of a tile
+                               // (kCiDone: no more work)
+    int64_t vec0[kCiStages];   // its first vector
 };
 
 template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
@@ -469,9 +463,8 @@ __global__ void __launch_bounds__(kThreads + 32, 2)
                       float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket) {
     extern __shared__ __align__(128) unsigned char ci_smem[];  // kCiStages x [x unit | g unit]; later the flush scratch
     __shared__ CiRing ring;
-    unsigned int* counter = (unsigned int*)ws + 1;
     const int t = threadIdx.x;
-    const int unit_vecs = geo.threads * kCiUnroll;          // vectors per unit (per input)
+    const int unit_vecs = geo.threads * kCiUnroll;          // vectors per full unit (per input)
     const uint32_t unit_bytes = (uint32_t)unit_vecs * 16u;  // <= 16 KB
     if (t == 0) {
 #pragma unroll
@@ -485,38 +478,46 @@ __global__ void __launch_bounds__(kThreads + 32, 2)
 
     if (t >= kThreads) {  // ---------------------------------------------------------------- producer warp
         if (t == kThreads) {
+            pdl_launch_dependents();
+            unsigned int* counter = (unsigned int*)ws + 1;
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t s0 = 0, s1 = 0, tile = blockIdx.x;
+            if (geo.sched == kCiStatic) {
+                const uint64_t S = (uint64_t)geo.steps;
+                s0 = (uint32_t)(S * blockIdx.x / gridDim.x);
+                s1 = (uint32_t)(S * (blockIdx.x + 1) / gridDim.x);
+            }
             for (;;) {
-                const uint32_t tile = atomicAdd(counter, 1u);
-                const bool done = tile >= geo.n_tiles;
-                const int n_units = done ? 1 : kCiBatches;
-                for (int b = 0; b < n_units; ++b) {
+                if (geo.sched != kCiStatic) {
+                    if (geo.sched == kCiDynamic) tile = atomicAdd(counter, 1u);
+                    if (tile >= geo.n_tiles) break;
+                    s0 = tile * (uint32_t)geo.tile_steps;
+                    s1 = s0 + geo.tile_steps < (uint32_t)geo.steps ? s0 + geo.tile_steps : (uint32_t)geo.steps;
+                    tile += gridDim.x;  // interleaved: the next tile of this CTA
+                }
+                for (uint32_t s = s0; s < s1; s += kCiUnroll) {
+                    const int64_t v0 = (int64_t)s * geo.threads;
+                    int64_t nv = (int64_t)((s + kCiUnroll < s1 ? s + kCiUnroll : s1) - s) * geo.threads;
+                    if (v0 + nv > geo.n_vec) nv = geo.n_vec - v0;
                     mbar_wait(&ring.empty[stage], phase ^ 1u);  // the consumers have drained this stage
-                    ring.tile[stage] = done ? kCiNoTile : tile;
-                    ring.batch[stage] = (uint32_t)b;
-                    int64_t v0 = 0, nv = 0;
-                    if (!done) {
-                        v0 = (int64_t)tile * geo.tile_vecs + (int64_t)b * unit_vecs;
-                        nv = geo.n_vec - v0;
-                        nv = nv < 0 ? 0 : (nv > unit_vecs ? unit_vecs : nv);
-                    }
-                    if (nv > 0) {
-                        const uint32_t bytes = (uint32_t)nv * 16u;
-                        unsigned char* xs = ci_smem + (size_t)stage * 2 * unit_bytes;
-                        mbar_arrive_expect_tx(&ring.full[stage], 2 * bytes);
-                        bulk_load(xs, x + v0 * kCiVec, bytes, &ring.full[stage]);
-                        bulk_load(xs + unit_bytes, g + v0 * kCiVec, bytes, &ring.full[stage]);
-                    } else {
-                        mbar_arrive(&ring.full[stage]);
-                    }
+                    ring.vec0[stage] = v0;
+                    ring.nvec[stage] = (uint32_t)nv | (s + kCiUnroll >= s1 ? kCiTileEnd : 0u);
+                    const uint32_t bytes = (uint32_t)nv * 16u;
+                    unsigned char* xs = ci_smem + (size_t)stage * 2 * unit_bytes;
+                    mbar_arrive_expect_tx(&ring.full[stage], 2 * bytes);
+                    bulk_load(xs, x + v0 * kCiVec, bytes, &ring.full[stage]);
+                    bulk_load(xs + unit_bytes, g + v0 * kCiVec, bytes, &ring.full[stage]);
                     if (++stage == kCiStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                if (done) break;
+                if (geo.sched == kCiStatic) break;
             }
+            mbar_wait(&ring.empty[stage], phase ^ 1u);
+            ring.nvec[stage] = kCiDone;
+            mbar_arrive(&ring.full[stage]);
         }
         return;  // the producer warp takes no part in the flush (named barrier over the consumer threads)
     }
@@ -534,81 +535,38 @@ __global__ void __launch_bounds__(kThreads + 32, 2)
         bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
     }
     double acc_e[kCiVec], acc_b[kCiVec], acc_db[kCiVec];
-    float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials of the current tile
+    float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials, folded into the fp64 sums every kCiBatches units
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
         acc_e[e] = acc_b[e] = acc_db[e] = 0.0;
         te[e] = tb[e] = tdb[e] = 0.0f;
     }
-    int stage = 0;
+    int stage = 0, it = 0;
     uint32_t phase = 0;
     for (;;) {
         mbar_wait(&ring.full[stage], phase);  // the unit's bytes have landed (or there is nothing left)
-        const uint32_t tile = ring.tile[stage];
-        if (tile == kCiNoTile) break;
-        const uint32_t b = ring.batch[stage];
+        const uint32_t tag = ring.nvec[stage];
+        if (tag == kCiDone) break;
+        const uint32_t nv = tag & ~kCiTileEnd;
+        const int64_t v0 = ring.vec0[stage];
         const float* xs = (const float*)(ci_smem + (size_t)stage * 2 * unit_bytes);
         const float* gs = (const float*)(ci_smem + (size_t)stage * 2 * unit_bytes + unit_bytes);
-        const int64_t v0 = (int64_t)tile * geo.tile_vecs + (int64_t)b * unit_vecs;
         if (active) {
 #pragma unroll
             for (int j = 0; j < kCiUnroll; ++j) {
-                const int u = j * geo.threads + t;
-                const int64_t v = v0 + u;
-                if (v >= geo.n_vec) continue;
+                const uint32_t u = (uint32_t)(j * geo.threads + t);
+                if (u >= nv) continue;
                 const Vec4 vx = lds4(xs + (size_t)u * kCiVec);
                 const Vec4 vg = lds4(gs + (size_t)u * kCiVec);
                 Vec4 out;
-                float ve[kCiVec], vbz[kCiVec];
-                bool bad = !all_fast;
-#pragma unroll
-                for (int e = 0; e < kCiVec; ++e) {
-                    const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
-                    const float xe = RELU ? max_nan(xb, 0.0f) : xb;
-                    const float ge = vg.v[e];
-                    const Elem el = elem_fast(xe, p[e], bad);
-                    float d = dx_fast(ge, el.m, p[e], bad);
-                    if (RELU) d = xb > 0.0f ? d : 0.0f;
-                    out.v[e] = d;
-                    if (WANT_DS) {
-                        const float dd = __fsub_rn(el.q, p[e].z);
-                        const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
-                        ve[e] = ge * (dd - mv);
-                        vbz[e] = el.m ? 0.0f : ge;
-                    }
-                }
-                if (bad) {  // rare: IEEE sequences for the whole vector
-#pragma unroll
-                    for (int e = 0; e < kCiVec; ++e) {
-                        const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
-                        const float xe = RELU ? max_nan(xb, 0.0f) : xb;
-                        const float ge = vg.v[e];
-                        const Elem el = elem_slow(xe, p[e]);
-                        float d = dx_slow(ge, el.m, p[e]);
-                        if (RELU) d = xb > 0.0f ? d : 0.0f;
-                        out.v[e] = d;
-                        if (WANT_DS) {
-                            const float dd = __fsub_rn(el.q, p[e].z);
-                            const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
-                            ve[e] = ge * (dd - mv);
-                            vbz[e] = el.m ? 0.0f : ge;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < kCiVec; ++e) {
-                    if (WANT_DS) {
-                        te[e] += ve[e];
-                        tb[e] += vbz[e];
-                    }
-                    if (BIAS) tdb[e] += out.v[e];
-                }
-                st4(dx + v * kCiVec, out);
+                ci_bwd_vec<BIAS, RELU, WANT_DS>(vx, vg, p, bv, all_fast, out, te, tb, tdb);
+                st4(dx + (v0 + u) * kCiVec, out);
             }
         }
         __syncwarp();
         if ((t & 31) == 0) mbar_arrive(&ring.empty[stage]);  // this warp has read everything it needs from the stage
-        if (b == kCiBatches - 1) {  // tile complete: fold its fp32 partials into the fp64 running sums
+        if ((++it & (kCiBatches - 1)) == 0 || (tag & kCiTileEnd)) {  // fold the fp32 partials into the fp64 running sums
+            it = 0;
 #pragma unroll
             for (int e = 0; e < kCiVec; ++e) {
                 if (WANT_DS) {
@@ -624,17 +582,31 @@ __global__ void __launch_bounds__(kThreads + 32, 2)
             phase ^= 1u;
         }
     }
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        if (WANT_DS) {
+            acc_e[e] += (double)te[e];
+            acc_b[e] += (double)tb[e];
+        }
+        if (BIAS) acc_db[e] += (double)tdb[e];
+    }
     // every copy has landed and been consumed: the ring's memory is free for the flush scratch
     ci_sync<true>();
     ci_bwd_flush<PCQ, BIAS, WANT_DS, true>(acc_e, acc_b, acc_db, reinterpret_cast<double(*)[3 * kCiVec]>(ci_smem), geo, qpd,
                                            ws, o, use_ticket, t, active);
 }
 
-static int ci_grid(uint32_t n_tiles, uint32_t ctas_per_sm) {
-    DeviceProps dp;
-    if (int e = get_device_props(&dp)) return -e;
-    const uint32_t cap = (uint32_t)dp.sm_count * ctas_per_sm;  // __launch_bounds__(256, k): every CTA resident, tiles stolen dynamically
-    return (int)(n_tiles < cap ? n_tiles : cap);
+// opt in to > 48 KB of dynamic shared memory once per kernel instantiation and device (thread-safe)
+template <auto Kernel>  // a non-type parameter: every instantiation of the kernel gets its own flags
+static cudaError_t ci_set_smem_once(int device, int bytes) {
+    static std::mutex mu;
+    static bool done[64];
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (done[device]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done[device] = true;
+    return e;
 }
 
 }  // namespace vsiq
@@ -660,9 +632,10 @@ extern "C" int vsiq_ci_fake_quant_fwd(const float* x, const float* bias, float* 
     CiGeom geo;
     if (!make_ci_geom(rows, channels, &geo)) return VSIQ_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return VSIQ_ERR_UNSUPPORTED;
-    if (!workspace || workspace_bytes < kWsHeader) return VSIQ_ERR_WORKSPACE;
-    const int grid = ci_grid(geo.n_tiles, 3);
-    if (grid < 0) return -grid;
+    DeviceProps dp;
+    if (int e = get_device_props(&dp)) return e;
+    const int grid = ci_pick_grid(&geo, dp.sm_count, 3, 2 * kCiUnroll);
+    if (geo.sched == kCiDynamic && (!workspace || workspace_bytes < kWsHeader)) return VSIQ_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const bool pcq = qp_channels == channels && channels > 1, relu = qp->pre_op == VSIQ_PRE_RELU, hb = bias != nullptr;
 #define F(P, B, R) ci_fwd_kernel<P, B, R><<<grid, kThreads, 0, st>>>(x, bias, y, geo, qpd, workspace)
@@ -698,8 +671,9 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15u)
         return VSIQ_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < vsiq_ci_workspace_bytes(rows, channels)) return VSIQ_ERR_WORKSPACE;
-    const int grid = ci_grid(geo.n_tiles, 2);
-    if (grid < 0) return -grid;
+    DeviceProps dp;
+    if (int e = get_device_props(&dp)) return e;
+    const int grid = ci_pick_grid(&geo, dp.sm_count, 2, kCiUnroll);
     const bool pcq = qp_channels == channels && channels > 1, relu = qp->pre_op == VSIQ_PRE_RELU, hb = bias != nullptr;
     const bool want_ds = dscale != nullptr;
     CiOut o;
@@ -711,26 +685,20 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
     o.gs_host = grad_scale_host;
     o.gs_dev = grad_scale_dev;
     const int width = 2 * (pcq ? (int)channels : 1) + (hb ? (int)channels : 0);
-    const int use_ticket = width <= 64 ? 1 : 0;  // wider records: one finalize CTA per 32 entries instead
+    const int use_ticket = width <= 64 ? 1 : 0;  // wider records: ci_finalize_kernel, one CTA per 8 entries
     // dense grad_output: inputs staged through shared memory by bulk asynchronous copies (ci_bwd_tma_kernel); a pitched
     // grad_output (channel slice of a wider NHWC tensor) keeps the direct-load kernel.  VSIQ_CI_TMA=0 forces the latter.
     static const bool tma_enabled = []() { const char* e = getenv("VSIQ_CI_TMA"); return !(e && e[0] == '0'); }();
     const bool use_tma = tma_enabled && g_row_pitch == channels;
     int cur_dev = 0;
-    if (use_tma && (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64)) return VSIQ_ERR_NO_DEVICE;
+    if (use_tma && cudaGetDevice(&cur_dev) != cudaSuccess) return VSIQ_ERR_NO_DEVICE;
     const size_t ring_bytes = (size_t)kCiStages * 2 * (size_t)geo.threads * kCiUnroll * 16;
     const size_t flush_bytes = sizeof(double) * kThreads * 3 * kCiVec;
     const size_t dyn_smem = ring_bytes > flush_bytes ? ring_bytes : flush_bytes;
 #define B(P, H, R, D)                                                                                                      \
     {                                                                                                                      \
         if (use_tma) {                                                                                                     \
-            static bool attr_set[64]; /* opt in to > 48 KB of dynamic shared memory, once per instantiation and device */ \
-            if (!attr_set[cur_dev]) {                                                                                      \
-                cudaError_t ae = cudaFuncSetAttribute(ci_bwd_tma_kernel<P, H, R, D>,                                       \
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2 * 16384);        \
-                if (ae != cudaSuccess) return (int)ae;                                                                     \
-                attr_set[cur_dev] = true;                                                                                  \
-            }                                                                                                              \
+            if (cudaError_t ae = ci_set_smem_once<ci_bwd_tma_kernel<P, H, R, D>>(cur_dev, 3 * 2 * 16384)) return (int)ae;   \
             ci_bwd_tma_kernel<P, H, R, D><<<grid, kThreads + 32, dyn_smem, st>>>(x, bias, g, dx, geo, qpd, workspace, o,    \
                                                                                 use_ticket);                              \
         } else {                                                                                                           \
@@ -744,10 +712,12 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
 #undef B2
 #undef B3
 #undef B
+    if (cudaError_t le = cudaGetLastError()) return (int)le;
     if ((want_ds || hb) && !use_ticket) {
-        const int fgrid = (width + 31) / 32;
-        ci_finalize_kernel<<<fgrid, kThreads, 0, st>>>(workspace, width, (uint32_t)grid, o, qpd, pcq ? 1 : 0, hb ? 1 : 0,
-                                                      (int)channels);
+        const int fgrid = (width + kCombineEntries - 1) / kCombineEntries;
+        if (cudaError_t fe = launch_pdl(ci_finalize_kernel, dim3(fgrid), dim3(kThreads), 0, st, (const void*)workspace, width,
+                                        (uint32_t)grid, o, qpd, pcq ? 1 : 0, hb ? 1 : 0, (int)channels))
+            return (int)fe;
     }
     return (int)cudaGetLastError();
 }

@@ -559,6 +559,9 @@ inline int reduce_tile_mult(int64_t outer, int64_t channels, int64_t inner) {
     return 1;
 }
 bool aligned32(const void* p);
+bool pdl_enabled();         // programmatic dependent launch for the combine kernels (VSIQ_PDL=0 disables; A/B knob)
+int ci_sched_override();    // VSIQ_CI_SCHED=static|dynamic|interleaved -> 0 | 1 | 2, else -1 (automatic)
+int ci_tile_override();     // VSIQ_CI_TILE=<steps per tile>, else 0 (automatic)
 int check_layout(const vsiq_layout* l);
 int fill_qp(const vsiq_qparams* in, QPDev* out);
 

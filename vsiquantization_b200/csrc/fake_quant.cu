@@ -166,7 +166,7 @@ __device__ __forceinline__ void lsq_combine_cta(const double* partials, const Ti
 }
 
 template <int GROUP, int V, int MASK_MODE, bool WANT_DZ, bool RELU>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)  // <= 85 registers: three CTAs per SM (the RELU variants drifted to 95-110)
     lsq_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, Tiles tiles,
                    QPDev qpd, void* ws, LsqOut o, int64_t outer, int use_ticket) {
     __shared__ double s_red[kWarps][2];
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kThreads)
 // Keeps the hardware-like balance of the per-tile grid without a block reduction per tile: mid-size activations
 // (2^22..2^26 elements) no longer pay for the reduction epilogue.
 template <int V, int MASK_MODE, bool WANT_DZ, bool RELU>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)  // <= 85 registers: three CTAs per SM (the RELU variants drifted to 95-110)
     lsq_bwd_pt_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, Tiles tiles,
                       QPDev qpd, void* ws, LsqOut o) {
     __shared__ double s_red[kWarps][2];
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kThreads)
 
 // Per-channel LSQ backward on [outer, C, inner] with the channel-item schedule (see PcGeom): one flush per CTA.
 template <int GROUP, int V, bool WANT_DZ, bool RELU>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)  // <= 85 registers: three CTAs per SM (the RELU variants drifted to 95-110)
     lsq_bwd_pc_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, PcGeom geo,
                       QPDev qpd, void* ws, LsqOut o, int use_ticket) {
     __shared__ double s_red[kWarps][2];

@@ -329,14 +329,14 @@ constexpr int kCiObsFields = 5;  // min, max, sum|x|, sum x, sum x^2   (a NaN in
 __global__ void __launch_bounds__(kThreads, 3)
     ci_observe_kernel(const float* __restrict__ x, CiGeom geo, void* ws) {
     __shared__ double s_acc[kCiObsFields * kCiVec][kThreads];  // [field * 4 + e][thread]: conflict-free columns
-    unsigned int* counter = (unsigned int*)ws + 1;
     double* records = ws_partials(ws);
     const int t = threadIdx.x;
     const bool active = t < geo.threads;
+    pdl_launch_dependents();
     float mn[kCiVec], mx[kCiVec];
     bool nan[kCiVec];
-    // the fp64 running sums live in this thread's column of shared memory (touched once per tile; keeps the kernel at 80
-    // registers = 3 CTAs per SM without spilling)
+    // the fp64 running sums live in this thread's column of shared memory (touched once per 16 vectors; keeps the kernel
+    // at 80 registers = 3 CTAs per SM without spilling)
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
         mn[e] = INFINITY;
@@ -347,46 +347,49 @@ __global__ void __launch_bounds__(kThreads, 3)
         s_acc[4 * kCiVec + e][t] = 0.0;
     }
     __shared__ uint32_t s_tile[2];
-    TileQueue tq;
-    tq_init(tq, counter, geo.n_tiles, s_tile);
-    constexpr int kU = 2 * kCiUnroll, kB = kCiBatches / 2;  // one input: twice the loads in flight
-    for (uint32_t tile = tq_current(tq, s_tile); tile < geo.n_tiles; tq_advance(tq, s_tile), tile = tq_current(tq, s_tile)) {
-        if (!active) continue;
-        const int64_t vb = (int64_t)tile * geo.tile_vecs;
-        float fa[kCiVec], f1[kCiVec], f2[kCiVec];  // fp32 partials of this tile (16 elements per channel per thread)
+    CiSched sc;
+    CiRange r = ci_sched_first(geo, sc, ws, s_tile, t);
+    constexpr int kU = 2 * kCiUnroll;  // one input: twice the loads in flight
+    const int64_t stride = (int64_t)geo.threads * kCiVec;
+    for (;;) {
+        if (active) {
+            float fa[kCiVec], f1[kCiVec], f2[kCiVec];  // fp32 partials of 16 vectors (16 elements per channel per thread)
 #pragma unroll
-        for (int e = 0; e < kCiVec; ++e) fa[e] = f1[e] = f2[e] = 0.0f;
+            for (int e = 0; e < kCiVec; ++e) fa[e] = f1[e] = f2[e] = 0.0f;
+            int it = 0;
+            const float* xp = x + ((int64_t)r.s0 * geo.threads + t) * kCiVec;
 #pragma unroll 1
-        for (int b = 0; b < kB; ++b) {
-            Vec4 vin[kU];
-            bool ok[kU];
+            for (uint32_t s = r.s0; s < r.s1; s += kU, xp += kU * stride) {
+                Vec4 vin[kU];
 #pragma unroll
-            for (int j = 0; j < kU; ++j) {
-                const int64_t v = vb + (int64_t)(b * kU + j) * geo.threads + t;
-                ok[j] = v < geo.n_vec;
-                if (ok[j]) vin[j] = ld4(x + v * kCiVec);
-            }
+                for (int j = 0; j < kU; ++j)
+                    if (s + j < r.s1) vin[j] = ld4(xp + j * stride);
 #pragma unroll
-            for (int j = 0; j < kU; ++j) {
-                if (!ok[j]) continue;
+                for (int j = 0; j < kU; ++j) {
+                    if (s + j >= r.s1) continue;
 #pragma unroll
-                for (int e = 0; e < kCiVec; ++e) {
-                    const float xv = vin[j].v[e];
-                    nan[e] = nan[e] || (xv != xv);
-                    mn[e] = fminf(mn[e], xv);
-                    mx[e] = fmaxf(mx[e], xv);
-                    fa[e] += fabsf(xv);
-                    f1[e] += xv;
-                    f2[e] = fmaf(xv, xv, f2[e]);
+                    for (int e = 0; e < kCiVec; ++e) {
+                        const float xv = vin[j].v[e];
+                        nan[e] = nan[e] || (xv != xv);
+                        mn[e] = fminf(mn[e], xv);
+                        mx[e] = fmaxf(mx[e], xv);
+                        fa[e] += fabsf(xv);
+                        f1[e] += xv;
+                        f2[e] = fmaf(xv, xv, f2[e]);
+                    }
+                }
+                if ((++it & 1) == 0 || s + kU >= r.s1) {
+#pragma unroll
+                    for (int e = 0; e < kCiVec; ++e) {
+                        s_acc[2 * kCiVec + e][t] += (double)fa[e];
+                        s_acc[3 * kCiVec + e][t] += (double)f1[e];
+                        s_acc[4 * kCiVec + e][t] += (double)f2[e];
+                        fa[e] = f1[e] = f2[e] = 0.0f;
+                    }
                 }
             }
         }
-#pragma unroll
-        for (int e = 0; e < kCiVec; ++e) {
-            s_acc[2 * kCiVec + e][t] += (double)fa[e];
-            s_acc[3 * kCiVec + e][t] += (double)f1[e];
-            s_acc[4 * kCiVec + e][t] += (double)f2[e];
-        }
+        if (!ci_sched_next(geo, sc, s_tile, t, r)) break;
     }
     // ---- one record per CTA: fixed-order reduction over the threads that share a channel group
 #pragma unroll
@@ -411,8 +414,8 @@ __global__ void __launch_bounds__(kThreads, 3)
         }
         rec[idx] = v;
     }
-    // the last CTA to leave resets the ticket and the tile counter for the next launch
-    if (threadIdx.x == 0) {
+    if (geo.sched == kCiDynamic && threadIdx.x == 0) {  // the last CTA to leave resets the ticket and the tile counter
+        unsigned int* counter = (unsigned int*)ws + 1;
         unsigned int tk = atomicAdd((unsigned int*)ws, 1u);
         if (tk == gridDim.x - 1) {
             *(unsigned int*)ws = 0;
@@ -421,17 +424,21 @@ __global__ void __launch_bounds__(kThreads, 3)
     }
 }
 
-// one CTA per channel: threads stride over the per-CTA records (<= 444 of them: two loads deep), then a fixed-order
-// shuffle + shared-memory reduction.  (A warp per channel walked the records 14 deep and took 33 us.)
+// One CTA per 8 channels (a programmatic dependent of ci_observe_kernel, parked in griddepcontrol.wait until the records
+// are complete): lane & 7 selects the channel, the 32 (warp, lane >> 3) phases walk the per-CTA records 32 apart (each
+// load instruction of a warp reads four 64-byte segments), then a fixed-order shuffle + shared-memory reduction.
 __global__ void __launch_bounds__(kThreads)
     ci_observe_finalize_kernel(const void* ws, int C, uint32_t n_rec, ObserveOut o) {
-    __shared__ double s_red[kWarps][kPartialWidth];
+    __shared__ double s_red[kWarps][kCombineEntries][kCiObsFields];
     const double* records = (const double*)((const char*)ws + kWsHeader);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = blockIdx.x; c < C; c += gridDim.x) {
-        float mn = INFINITY, mx = -INFINITY;
-        double sa = 0.0, s1 = 0.0, s2 = 0.0;
-        for (uint32_t r = threadIdx.x; r < n_rec; r += kThreads) {
+    const int c = blockIdx.x * kCombineEntries + (lane & 7);
+    const uint32_t phase = (uint32_t)warp * 4u + (uint32_t)(lane >> 3);
+    pdl_wait();
+    float mn = INFINITY, mx = -INFINITY;
+    double sa = 0.0, s1 = 0.0, s2 = 0.0;
+    if (c < C) {
+        for (uint32_t r = phase; r < n_rec; r += 32) {
             const double* rec = records + (size_t)r * kCiObsFields * C + c;
             mn = nanmin(mn, (float)__ldcg(rec));
             mx = nanmax(mx, (float)__ldcg(rec + C));
@@ -439,33 +446,35 @@ __global__ void __launch_bounds__(kThreads)
             s1 += __ldcg(rec + 3 * C);
             s2 += __ldcg(rec + 4 * C);
         }
-        mn = warp_min(mn);
-        mx = warp_max(mx);
-        sa = warp_sum(sa);
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        __syncthreads();  // s_red free again
-        if (lane == 0) {
-            s_red[warp][0] = (double)mn;
-            s_red[warp][1] = (double)mx;
-            s_red[warp][2] = sa;
-            s_red[warp][3] = s1;
-            s_red[warp][4] = s2;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float a = (float)s_red[0][0], bq = (float)s_red[0][1];
-            double x2 = s_red[0][2], x3 = s_red[0][3], x4 = s_red[0][4];
+    }
 #pragma unroll
-            for (int w = 1; w < kWarps; ++w) {
-                a = nanmin(a, (float)s_red[w][0]);
-                bq = nanmax(bq, (float)s_red[w][1]);
-                x2 += s_red[w][2];
-                x3 += s_red[w][3];
-                x4 += s_red[w][4];
-            }
-            observe_store_channel(o, c, a, bq, x2, x3, x4);
+    for (int d = 8; d <= 16; d <<= 1) {
+        mn = nanmin(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = nanmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        sa += __longlong_as_double(__shfl_xor_sync(0xffffffffu, __double_as_longlong(sa), d));
+        s1 += __longlong_as_double(__shfl_xor_sync(0xffffffffu, __double_as_longlong(s1), d));
+        s2 += __longlong_as_double(__shfl_xor_sync(0xffffffffu, __double_as_longlong(s2), d));
+    }
+    if (lane < kCombineEntries) {
+        s_red[warp][lane][0] = (double)mn;
+        s_red[warp][lane][1] = (double)mx;
+        s_red[warp][lane][2] = sa;
+        s_red[warp][lane][3] = s1;
+        s_red[warp][lane][4] = s2;
+    }
+    __syncthreads();
+    if (warp == 0 && lane < kCombineEntries && c < C) {
+        float a = (float)s_red[0][lane][0], bq = (float)s_red[0][lane][1];
+        double x2 = s_red[0][lane][2], x3 = s_red[0][lane][3], x4 = s_red[0][lane][4];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) {
+            a = nanmin(a, (float)s_red[w][lane][0]);
+            bq = nanmax(bq, (float)s_red[w][lane][1]);
+            x2 += s_red[w][lane][2];
+            x3 += s_red[w][lane][3];
+            x4 += s_red[w][lane][4];
         }
+        observe_store_channel(o, c, a, bq, x2, x3, x4);
     }
 }
 
@@ -681,8 +690,7 @@ extern "C" int vsiq_ci_observe(const float* x, int64_t rows, int64_t channels, d
     if (!workspace || workspace_bytes < vsiq_ci_observe_workspace_bytes(rows, channels)) return VSIQ_ERR_WORKSPACE;
     DeviceProps dp;
     if (int e = get_device_props(&dp)) return e;
-    const uint32_t cap = (uint32_t)dp.sm_count * 3u;
-    const uint32_t grid = geo.n_tiles < cap ? geo.n_tiles : cap;
+    const uint32_t grid = (uint32_t)ci_pick_grid(&geo, dp.sm_count, 3, 2 * kCiUnroll);
     cudaStream_t st = (cudaStream_t)stream;
     ObserveOut oo;
     oo.stats = stats;
@@ -693,8 +701,9 @@ extern "C" int vsiq_ci_observe(const float* x, int64_t rows, int64_t channels, d
     oo.count = (double)rows;
     ci_observe_kernel<<<grid, kThreads, 0, st>>>(x, geo, workspace);
     if (cudaError_t err = cudaGetLastError()) return (int)err;
-    ci_observe_finalize_kernel<<<(int)channels, kThreads, 0, st>>>(workspace, (int)channels, grid, oo);
-    return (int)cudaGetLastError();
+    const int fgrid = (int)((channels + kCombineEntries - 1) / kCombineEntries);
+    return (int)launch_pdl(ci_observe_finalize_kernel, dim3(fgrid), dim3(kThreads), 0, st, (const void*)workspace,
+                           (int)channels, grid, oo);
 }
 
 extern "C" int vsiq_qparams_from_minmax(double* state, int64_t n, const int32_t* bits, const int32_t* symmetric,
