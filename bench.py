@@ -3,19 +3,31 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--log2n L]
 
-Workload (BASELINE.json configs[1], the configuration the metric is quoted on): one per-tensor W8 symmetric
-UniformQuantizer over a 2^28-element fp32 tensor; one step = the forward kernel + the STE backward kernel
+Contract workload (BASELINE.json configs[1], the configuration the first half of the metric is quoted on): one per-tensor
+W8 symmetric UniformQuantizer over a 2^28-element fp32 tensor; one step = the forward kernel + the STE backward kernel
 (20 algorithmic bytes per element: read x / write y, then read g, read x / write dx).  x is 1 GiB, larger than the
 126 MB L2, so nothing survives between launches.
 
 Prints ONE JSON line (rank 0).  `value` is whole-job GB/s with inputs resident in HBM; `e2e` is the same metric
 through the host-buffer entry of the C ABI (pinned host x, g -> y, dx; both PCIe directions inside the timed region);
 `roofline` is the dominant kernel (STE backward, 12 B/element) against the measured HBM copy bandwidth; `cpu_baseline`
-is the reference's op sequence (torch-eager port, oracle/torch_port.py) on the host cores over a bounded sample.
+is the reference's own CPU code (baseline/_ref, kind "reference"; the torch-eager port oracle/torch_port.py when the
+reference tree is absent) on the host cores over a bounded sample; `gpu_eager_baseline` is the same reference code on
+the same B200 (CUDA tensors, ATen eager kernels): the GPU-vs-GPU yardstick.
 
-`--impl reference`: the reference arm -- the same CPU port, all host threads, rank 0 only.
-Under torchrun (N > 1) every rank runs the same per-GPU workload (weak scaling, no data-path collective); the time is
-the max over ranks.
+The second half of BASELINE.json's metric -- YOLOv8 QAT images/s at 1/2/4/8 B200 -- rides in the same line:
+  `yolo_qat`     BASELINE configs[2]: YOLOv8s, batch 64 per GPU @640, W4A8 per-channel asymmetric LSQ, channels_last,
+                 weight bank, one CUDA graph per rank with the flat NCCL gradient all-reduce captured inside, input
+                 prefetch; images/s, ms/step (max over ranks), the captured all-reduce's device time, the H2D time, the
+                 fake-quant kernels' device time against their HBM floor, the loss;
+  `calibration`  BASELINE configs[3]: YOLOv8m calibrate_qat_model over 50 global batches of 64 @640 sharded over the
+                 ranks + sync_observers (one packed all_reduce(MIN) + one SUM) + reestimate_BN_stats (SyncBN-style sums);
+                 images/s, the sync time, scale digests, and whether every rank ended with bit-identical scales.
+
+`--impl reference`: the reference arm -- the reference's own UniformQuantizer on the host CPU, all host threads, the SAME
+2^28-element workload (same `config`), rank 0 only.
+Under torchrun (N > 1) the microbench runs the same per-GPU workload on every rank (weak scaling, no data-path collective);
+every time is the max over ranks.
 """
 from __future__ import annotations
 
@@ -47,7 +59,61 @@ def parse_args():
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 2^20..2^30 x quantiser-kind sweep (N=1 only)")
     ap.add_argument("--sweep-log2n", type=int, nargs="+", default=[20, 22, 24, 26, 28, 30])
+    ap.add_argument("--no-yolo", action="store_true", help="skip the YOLOv8s data-parallel QAT step section")
+    ap.add_argument("--no-calibration", action="store_true", help="skip the YOLOv8m calibration section")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the same-GPU eager yardstick")
+    ap.add_argument("--yolo-steps", type=int, default=0, help="timed steps of the YOLO section (default: 16..32 from --steps)")
+    ap.add_argument("--yolo-batch", type=int, default=64)
+    ap.add_argument("--yolo-model", default="s")
+    ap.add_argument("--calib-batches", type=int, default=50)
+    ap.add_argument("--calib-model", default="m")
     return ap.parse_args()
+
+
+def workload_config(args, world: int) -> dict:
+    """The `config` object -- identical for the native and the reference arm (the driver compares them)."""
+    n = 1 << args.log2n
+    return {"workload": f"fake-quant microbench (BASELINE configs[1]): per-tensor W8 symmetric UniformQuantizer, "
+                        f"2^{args.log2n} fp32 elements per GPU, step = forward + STE backward",
+            "elements_per_gpu": n, "qmin": QMIN, "qmax": QMAX, "scale": SCALE,
+            "l2_policy": "inputs larger than L2 (x = %d MiB > 126 MB); no flush needed" % (4 * n >> 20),
+            "parallelism": f"dp{world} (independent per-GPU tensors, no data-path collective)"}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
+def reference_quantizer():
+    """(UniformQuantizer instance of the UNMODIFIED reference, "reference") when the tree is available (baseline/_ref on
+    the GPU box, /root/reference in the build container), else (None, "port")."""
+    try:
+        from oracle import ref_shim
+        if not ref_shim.available():
+            return None, "port"
+        ref_shim.install()
+        import importlib
+        mod = importlib.import_module("quantizers.uniform")
+        if not (getattr(mod, "__file__", "") or "").startswith(ref_shim.REFERENCE_ROOT):
+            return None, "port"
+        return mod.UniformQuantizer(8, True), "reference"
+    except Exception:
+        return None, "port"
+
+
+def reference_step(q, x, g, scale):
+    """One forward + backward of the reference's fake-quant (quantizers/uniform.py:34-56 + autograd) -- or of its
+    torch-eager port when `q` is None.  Works on CPU and CUDA tensors alike."""
+    if q is None:
+        from oracle import torch_port
+        return torch_port.fwd_bwd(x, g, scale, ZP, QMIN, QMAX)
+    xr = x.detach().requires_grad_(True)
+    y = q.quantize(xr, scale, ZP, False)
+    y.backward(g)
+    return y.detach(), xr.grad
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -121,27 +187,26 @@ def ncu_traffic(kernel: str, log2n: int):
 
 
 def cpu_baseline(log2n: int, iters: int = 5, warm: int = 2):
-    """The reference's op sequence on the host cores (torch eager, all threads) over 2^log2n elements."""
+    """The reference's fake-quant on the host cores (its own code when baseline/_ref is there, else the torch-eager
+    port; all threads) over a bounded sample of 2^log2n elements."""
     import torch
-    from oracle import torch_port
-    try:
-        torch.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1
-    except (AttributeError, OSError):
-        torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1
+    q, kind = reference_quantizer()
     n = 1 << log2n
     torch.manual_seed(0)
     x, g = torch.randn(n), torch.randn(n)
     ts = []
     for i in range(warm + iters):
         t0 = time.perf_counter()
-        torch_port.fwd_bwd(x, g, SCALE, ZP, QMIN, QMAX)
+        reference_step(q, x, g, SCALE)
         if i >= warm:
             ts.append(time.perf_counter() - t0)
     ts.sort()
     med = ts[len(ts) // 2]
-    out = {"value": 20.0 * n / med / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
-           "sample": f"2^{log2n} elements per iteration, median of {iters} after {warm} warm-ups; torch-eager port of "
-                     f"quantizers/uniform.py:54-55,95 + autograd (oracle/torch_port.py)",
+    what = ("the reference's UniformQuantizer.quantize + autograd (baseline/_ref/quantizers/uniform.py:34-56)" if kind == "reference"
+            else "torch-eager port of quantizers/uniform.py:54-55,95 + autograd (oracle/torch_port.py)")
+    out = {"value": 20.0 * n / med / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": kind,
+           "sample": f"2^{log2n} elements per iteration, median of {iters} after {warm} warm-ups; {what}",
            "ms_per_step": med * 1e3, "host_cpus": os.cpu_count()}
     # the single-sweep C port (OpenMP) as a second, stronger yardstick
     try:
@@ -162,6 +227,35 @@ def cpu_baseline(log2n: int, iters: int = 5, warm: int = 2):
         out["c_port_fused_gbs"] = None
         out["c_port_note"] = str(e)[:80]
     return out
+
+
+def gpu_eager_baseline(dev, x, g, iters: int = 5):
+    """The reference's code on the SAME B200: ATen eager kernels composed in Python, autograd backward, scale as a CUDA
+    tensor (ATen then divides exactly like the CPU path; a Python-float scale would multiply by 1/s).  SURVEY 8(d)."""
+    import torch
+    q, kind = reference_quantizer()
+    scale = torch.tensor(SCALE, dtype=torch.float64, device=dev)
+    try:
+        for _ in range(2):
+            reference_step(q, x, g, scale)
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            reference_step(q, x, g, scale)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        med = ts[len(ts) // 2]
+        return {"value": 20.0 * x.numel() / (med * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": med, "kind": kind,
+                "what": "the reference's fake-quant forward + autograd backward as ATen eager kernels on this GPU, "
+                        f"2^{x.numel().bit_length() - 1} elements, CUDA-tensor scale, median of {iters}"}
+    except Exception as e:
+        return {"value": None, "error": str(e)[:120], "kind": kind}
+    finally:
+        torch.cuda.empty_cache()
 
 
 def size_sweep(dev, log2ns, peak, iters: int = 10):
@@ -240,35 +334,76 @@ def run_reference(args):
     if rank != 0:
         return 0  # the reference arm runs on rank 0 alone
     import torch
-    from oracle import torch_port
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core it can use
-    try:
-        torch.set_num_threads(len(os.sched_getaffinity(0)))
-    except (AttributeError, OSError):
-        torch.set_num_threads(os.cpu_count() or 1)
-    n = 1 << args.cpu_log2n
+    torch.set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1; this arm may use every host core
+    q, kind = reference_quantizer()
+    log2n = args.log2n
+    try:  # the full 2^28 workload needs ~12 GB of host memory for the autograd intermediates
+        import psutil
+        while log2n > 20 and psutil.virtual_memory().available < 14 * 4 * (1 << log2n):
+            log2n -= 1
+    except Exception:
+        pass
+    n = 1 << log2n
     torch.manual_seed(0)
     x, g = torch.randn(n), torch.randn(n)
     for _ in range(args.warmup):
-        torch_port.fwd_bwd(x, g, SCALE, ZP, QMIN, QMAX)
+        reference_step(q, x, g, SCALE)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        torch_port.fwd_bwd(x, g, SCALE, ZP, QMIN, QMAX)
+        reference_step(q, x, g, SCALE)
     dt = time.perf_counter() - t0
     value = 20.0 * n * args.steps / dt / 1e9
-    sample = (f"each step = fwd+bwd over a bounded sample of 2^{args.cpu_log2n} elements of the 2^{args.log2n}-element "
-              f"workload; torch-eager port of the reference's op sequence (oracle/torch_port.py), all host threads")
+    what = ("the unmodified reference's UniformQuantizer.quantize + autograd backward (baseline/_ref)" if kind == "reference"
+            else "torch-eager port of the reference's op sequence (oracle/torch_port.py; reference tree not available)")
+    sample = (f"each step = fwd+bwd over {'the whole' if log2n == args.log2n else 'a bounded sample of'} 2^{log2n} elements of "
+              f"the 2^{args.log2n}-element workload; {what}, all host threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"per-tensor W8 symmetric UniformQuantizer fwd+STE bwd, CPU sample 2^{args.cpu_log2n} fp32 "
-                                   f"elements per step (workload 2^{args.log2n})"},
-            "cpu_baseline": {"value": value, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample, "host_cpus": os.cpu_count()},
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": sample, "host_cpus": os.cpu_count(), "elements_per_step": n},
             "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ------------------------------------------------------------------------------------ model sections
+def yolo_section(args, world):
+    """BASELINE configs[2] through benchmarks/yolo_qat.py (the same code path as its command line)."""
+    from benchmarks import yolo_qat
+    steps = args.yolo_steps or min(max(args.steps, 16), 32)
+    argv = ["--model", args.yolo_model, "--batch", str(args.yolo_batch), "--imgsz", "640", "--steps", str(steps),
+            "--warmup", "3", "--w-bits", "4", "--a-bits", "8", "--asym", "--per-channel", "--lsq", "--channels-last",
+            "--weight-bank", "--cuda-graph", "--profile-steps", "2"]
+    r = yolo_qat.run(yolo_qat.parse(argv))
+    fq = r.get("fake_quant", {})
+    out = {"config": f"YOLOv8{args.yolo_model} QAT, batch {args.yolo_batch}/GPU @640, W4A8 per-channel asymmetric LSQQuantizer "
+                     f"(learnable step + zero-point), channels_last, weight bank, CUDA graph + captured flat NCCL all-reduce, "
+                     f"input prefetch; synthetic uint8 images, loss = sum of mean(out^2)",
+           "images_per_s": r["images_per_s"], "ms_per_step": r["ms_per_step"], "steps": r["steps"], "n_gpus": r["n_gpus"],
+           "allreduce_ms": r.get("allreduce_ms"), "allreduce_alone": r.get("allreduce_alone"),
+           "h2d_ms": r.get("h2d_ms"), "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"],
+           "fake_quant_ms": fq.get("kernel_ms_per_step"), "hbm_floor_ms": fq.get("hbm_floor_ms_per_step"),
+           "fake_quant_frac_of_floor": fq.get("fraction_of_hbm_floor"), "fake_quant_kernels": fq.get("kernels"),
+           "device_ms_per_step": fq.get("device_ms_per_step"), "fake_quant_gb_per_step": fq.get("algorithmic_gb_per_step_per_gpu"),
+           "loss": r["loss"], "ms_per_step_by_rank": r.get("ms_per_step_by_rank"), "peak_mem_gb": r["peak_mem_gb"],
+           "fused_layers": r["fused_layers"], "prefetch": r["prefetch"], "weight_bank": r["weight_bank"]}
+    if fq.get("profile_error"):
+        out["profile_error"] = fq["profile_error"]
+    return out
+
+
+def calibration_section(args, world):
+    """BASELINE configs[3] through benchmarks/calibration.py."""
+    from benchmarks import calibration
+    batches = max(args.calib_batches, world)
+    r = calibration.run(calibration.parse(["--model", args.calib_model, "--batch", "64", "--imgsz", "640", "--batches",
+                                           str(batches), "--channels-last"]))
+    r["config"] = (f"YOLOv8{args.calib_model}, {batches} global batches of 64 @640 sharded over {world} rank(s), is_fuse_bn=False, "
+                   f"calibrate_qat_model + sync_observers (packed all_reduce MIN + SUM) + reestimate_BN_stats (SyncBN-style sums)")
+    return r
 
 
 # -------------------------------------------------------------------------------------- native arm
@@ -383,7 +518,49 @@ def run_native(args):
                "pcie_gbs_each_way": 8.0 * e2e_n * e2e_steps / dt / 1e9,
                "api": "vsiq_host_pipeline_fwd_bwd (ops.HostPipeline): 4 Mi-element chunks on 4 streams, fused fwd+bwd kernel"}
         pipe.close()
+        # what the host side can deliver by itself: concurrent H2D + D2H copies of the same pinned buffers, all ranks at
+        # once, no kernel -- the PCIe / host-DRAM ceiling the e2e number sits under (8 ranks share one socket's memory)
+        try:
+            m = min(e2e_n, 1 << 26)
+            dbuf, dbuf2 = torch.empty(m, device=dev), torch.empty(m, device=dev)
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                with torch.cuda.stream(s1):
+                    dbuf.copy_(xh[:m], non_blocking=True)
+                with torch.cuda.stream(s2):
+                    yh[:m].copy_(dbuf2, non_blocking=True)
+            torch.cuda.synchronize()
+            dtc = time.perf_counter() - t0
+            tc_ = torch.tensor([dtc], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tc_, op=dist.ReduceOp.MAX)
+            e2e["copy_only_gbs_each_way_per_gpu"] = 4.0 * m * 4 / float(tc_.item()) / 1e9
+            e2e["host_cpus_visible"] = host_threads()
+            del dbuf, dbuf2
+        except Exception as e:
+            e2e["copy_only_note"] = str(e)[:80]
         del xh, gh, yh, dh
+
+    # ---- the same reference code on the same GPU (eager ATen kernels): GPU-vs-GPU yardstick, rank 0
+    gpu_eager = None
+    if rank == 0 and not args.no_gpu_eager:
+        gpu_eager = gpu_eager_baseline(dev, x, g)
+    del x, g
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[2] and [3]: every rank takes part (NCCL collectives inside)
+    def guarded(fn):
+        try:
+            return fn(args, world)
+        except Exception as e:  # never lose the contract line to a model-section failure: say what failed
+            import traceback
+            return {"error": f"{type(e).__name__}: {str(e)[:300]}", "where": traceback.format_exc(limit=3)[-400:]}
+        finally:
+            torch.cuda.empty_cache()
+    yolo = None if args.no_yolo else guarded(yolo_section)
+    calib = None if args.no_calibration else guarded(calibration_section)
 
     if rank != 0:
         if world > 1:
@@ -397,11 +574,7 @@ def run_native(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "step_ms": {"median": step_ms[len(step_ms) // 2], "min": step_ms[0], "max": step_ms[-1]},
-        "config": {"workload": f"fake-quant microbench (BASELINE configs[1]): per-tensor W8 symmetric UniformQuantizer, "
-                               f"2^{args.log2n} fp32 elements per GPU, step = forward kernel + STE backward kernel",
-                   "elements_per_gpu": n, "qmin": QMIN, "qmax": QMAX, "scale": SCALE,
-                   "l2_policy": "inputs larger than L2 (x = %d MiB > 126 MB); no flush needed" % (4 * n >> 20),
-                   "parallelism": f"dp{world} (independent per-GPU tensors, no data-path collective)"},
+        "config": workload_config(args, world),
         "roofline": {"bound": "hbm", "kernel": "fq_bwd_ste_kernel<256,8> (read g, read x, write dx: 12 B/element)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": ncu_traffic("fq_bwd_ste_kernel", args.log2n),
@@ -409,9 +582,14 @@ def run_native(args):
                      "fwd_kernel": {"achieved": 8.0 * n / (fwd_ms * 1e-3) / 1e9, "avg_launch_ms": fwd_ms,
                                     "frac": 8.0 * n / (fwd_ms * 1e-3) / 1e9 / peak}},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "oracle_spot_check_bit_exact": check,
+        "yolo_qat": yolo, "calibration": calib, "gpu_eager_baseline": gpu_eager,
     }
+    if gpu_eager and gpu_eager.get("value"):
+        line["vs_gpu_eager"] = value / world / gpu_eager["value"]
     if world == 1 and not args.no_sweep:
         line["sweep"] = size_sweep(dev, args.sweep_log2n, peak)
+        big = [r["frac_of_peak"] for r in line["sweep"] if r.get("log2n", 0) >= 26 and "frac_of_peak" in r]
+        line["sweep_worst_frac_of_peak_ge_2p26"] = min(big) if big else None
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.cpu_log2n)
     print(json.dumps(line), flush=True)

@@ -96,6 +96,32 @@ def _eager_manager_patch():
     M.collect_qparameter, M.init_scaling_factor_for_learning = collect, init
 
 
+def kernel_time_profile(step, n_steps: int):
+    """Device time of this library's kernels inside the step (CUPTI activity records of `n_steps` extra steps, outside
+    the timed region): the measured counterpart of the HBM floor."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(n_steps):
+                step(i)
+            torch.cuda.synchronize()
+        ours, total, by = 0.0, 0.0, {}
+        for e in prof.key_averages():
+            t = float(e.device_time_total)
+            total += t
+            if "vsiq::" in e.key:
+                ours += t
+                name = e.key.split("vsiq::")[1].split("<")[0].split("(")[0]
+                d = by.setdefault(name, [0.0, 0])
+                d[0] += t
+                d[1] += e.count
+        return {"kernel_ms_per_step": ours / n_steps / 1e3, "device_ms_per_step": total / n_steps / 1e3,
+                "kernels": {k: {"ms_per_step": round(v[0] / n_steps / 1e3, 4), "launches_per_step": v[1] / n_steps}
+                            for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])}}
+    except Exception as e:  # CUPTI unavailable (e.g. under ncu): report why, never fail the benchmark
+        return {"kernel_ms_per_step": None, "profile_error": str(e)[:120]}
+
+
 def build_model(args, device):
     from vsiquantization_b200.modules.fuse import fuse_modules_unified
     from vsiquantization_b200.modules.fuse_config import FuseConfig, create_fuse_config_manager
@@ -192,13 +218,21 @@ def run(args) -> dict:
                 e.record()
             self.next_i = 0   # batches issued
             self.cur = 0      # batches consumed
+            self.h2d = []     # (start, end) timing events of the copies issued inside the timed region
+            self.timing = False
             self.issue()
 
         def issue(self):
             k = self.next_i % 2
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(self.free[k])
+                if self.timing:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(self.stream)
                 self.dev[k].copy_(host[k], non_blocking=True)
+                if self.timing:
+                    e1.record(self.stream)
+                    self.h2d.append((e0, e1))
                 self.ready[k].record(self.stream)
             self.next_i += 1
 
@@ -238,6 +272,7 @@ def run(args) -> dict:
         return float(loss.item())  # device -> host read of the step's result
 
     bucket_params = set(bucket.params) if bucket is not None else set()
+    graphed = None
     if args.cuda_graph:
         # world > 1: no DDP wrapper -- the graphed step all-reduces one flat gradient buffer inside the captured graph
         from vsiquantization_b200.graph import GraphedQATStep
@@ -279,22 +314,59 @@ def run(args) -> dict:
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if pre is not None:
+        pre.timing = True
     l0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loss = 0.0
+    ar_ms = []
     for i in range(args.steps):
-        loss = step(i)
+        loss = step(i)  # reads the loss back: the device is idle here, the in-graph events of this step are final
+        if graphed is not None and graphed.allreduce_ms() is not None:
+            ar_ms.append(graphed.allreduce_ms())
     e1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if pre is not None:
+        pre.timing = False
     ms = e0.elapsed_time(e1)
+    mine = ms
     t = torch.tensor([ms], device=device, dtype=torch.float64)
+    spread = None
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        spread = [float(v.item()) / args.steps for v in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     launches = _lib.launch_count - l0
+    h2d_ms = None
+    if pre is not None and pre.h2d:
+        v = sorted(a.elapsed_time(b) for a, b in pre.h2d)
+        h2d_ms = v[len(v) // 2]
+    # the gradient all-reduce timed on its own (same buffer size, idle GPU): what the collective costs when nothing
+    # competes with it, against its duration inside the step (which includes waiting for the slowest rank)
+    ar_alone = None
+    if world > 1:
+        nbytes = graphed.allreduce_bytes if graphed is not None else sum(p.numel() * p.element_size() for p in model.parameters())
+        buf = torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
+        for _ in range(3):
+            dist.all_reduce(buf)
+        ts = []
+        for _ in range(10):
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dist.all_reduce(buf)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        ar_alone = {"ms": ts[len(ts) // 2], "bytes": int(nbytes)}
+        del buf
+    fq_prof = kernel_time_profile(step, args.profile_steps) if args.profile_steps > 0 else None
     res = {"model": f"yolov8{args.model}", "fused_layers": n_fused, "batch_per_gpu": args.batch, "imgsz": args.imgsz,
            "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps,
            "images_per_s": args.batch * world * args.steps / (ms * 1e-3), "quant_impl": args.quant_impl,
@@ -304,7 +376,9 @@ def run(args) -> dict:
            "loss": loss, "vsiq_launches_per_step": launches / args.steps,
            "calibration_s": calib_s, "calib_batches": args.calib_batches,
            "h2d_bytes_per_step": args.batch * 3 * args.imgsz * args.imgsz, "d2h_bytes_per_step": 4,
-           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+           "h2d_ms": h2d_ms, "allreduce_ms": (sorted(ar_ms)[len(ar_ms) // 2] if ar_ms else None),
+           "allreduce_alone": ar_alone, "ms_per_step_by_rank": spread, "ms_per_step_this_rank": mine / args.steps}
     peak = 6531.9
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -315,6 +389,10 @@ def run(args) -> dict:
                          "algorithmic_gb_per_step_per_gpu": fq_bytes / 1e9, "hbm_peak_gbs": peak,
                          "hbm_floor_ms_per_step": fq_bytes / peak / 1e6,
                          "floor_fraction_of_step": fq_bytes / peak / 1e6 / (ms / args.steps)}
+    if fq_prof is not None:
+        res["fake_quant"].update(fq_prof)
+        if fq_prof.get("kernel_ms_per_step"):
+            res["fake_quant"]["fraction_of_hbm_floor"] = res["fake_quant"]["hbm_floor_ms_per_step"] / fq_prof["kernel_ms_per_step"]
     return res
 
 
@@ -339,6 +417,8 @@ def parse(argv=None):
     ap.add_argument("--cuda-graph", action="store_true", help="capture fwd+bwd+optimizer once, replay per step")
     ap.add_argument("--no-prefetch", action="store_true", help="copy each batch on the compute stream (no overlap)")
     ap.add_argument("--weight-bank", action="store_true", help="all weight quantisers in one multi-tensor launch each way")
+    ap.add_argument("--profile-steps", type=int, default=0,
+                    help="after the timed region, profile this many extra steps (CUPTI) and report the fake-quant kernel time")
     return ap.parse_args(argv)
 
 

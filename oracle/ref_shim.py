@@ -1,9 +1,9 @@
-"""Import the UNMODIFIED reference from /root/reference -- build-container only.
+"""Import the UNMODIFIED reference -- from /root/reference in the build container, else from the git-ignored
+verbatim install ``baseline/_ref`` (tools/install_reference.sh, run by ``__graft_entry__.build()``), which travels to
+the GPU box with the gpurun snapshot.
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing
-that runs there (``-m gpu`` tests, smoke(), bench.py) may import this module;
-it is used by ``oracle/gen_golden.py`` (fixture generation) and by the
-``reference``-marked CPU tests that skip when the tree is absent.
+TEST / BASELINE INFRASTRUCTURE.  Used by ``oracle/gen_golden.py`` (fixture generation), the ``reference``-marked tests
+(they skip when no tree is available) and ``bench.py --impl reference``.  The product never imports it.
 
 The reference's hot-path modules carry three junk imports that no longer
 resolve on Python 3.12 (``import imp`` -- quantizers/fake_quantize.py:1,
@@ -16,7 +16,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("VSIQ_REFERENCE_ROOT", "/root/reference")
+_INSTALLED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("VSIQ_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _INSTALLED):
+        if os.path.isdir(os.path.join(cand, "quantizers")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 # Top-level package names the reference uses (implicit namespace packages).
 _REF_PACKAGES = ("utils", "observers", "quantizers", "modules", "nets", "dataset")

@@ -37,6 +37,15 @@ class GraphedQATStep:
             raise ValueError("GraphedQATStep reduces the gradients itself: pass the bare model, not a DDP wrapper")
         self.static_input = example_input.clone()
         self.post_backward = post_backward
+        # timing events recorded INSIDE the captured graph (external event-record nodes): each replay re-records them, so
+        # after a replay ``allreduce_ms()`` is the device time of that step's captured gradient all-reduce
+        self._ar_events = None
+        if self.world > 1:
+            try:
+                self._ar_events = (torch.cuda.Event(enable_timing=True, external=True),
+                                   torch.cuda.Event(enable_timing=True, external=True))
+            except TypeError:  # older torch: no external events, no in-graph timing
+                self._ar_events = None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -67,9 +76,16 @@ class GraphedQATStep:
         for p in self.model.parameters():
             if p.grad is not None:
                 by_dtype.setdefault(p.grad.dtype, []).append(p)
-        for ps in by_dtype.values():
-            flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        self.allreduce_bytes = sum(p.grad.numel() * p.grad.element_size() for ps in by_dtype.values() for p in ps)
+        flats = [(ps, torch.cat([p.grad.reshape(-1) for p in ps])) for ps in by_dtype.values()]
+        ev = getattr(self, "_ar_events", None)
+        if ev is not None:
+            ev[0].record()
+        for _, flat in flats:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        if ev is not None:
+            ev[1].record()
+        for ps, flat in flats:
             if self.average:
                 flat.div_(self.world)
             off = 0
@@ -77,6 +93,16 @@ class GraphedQATStep:
                 n = p.numel()
                 p.grad = flat[off:off + n].view(p.shape)
                 off += n
+
+    def allreduce_ms(self):
+        """Device time of the captured NCCL gradient all-reduce(s) in the last replayed step, or
+        None (single process / no external-event support).  Call after a synchronisation."""
+        if self._ar_events is None:
+            return None
+        try:
+            return float(self._ar_events[0].elapsed_time(self._ar_events[1]))
+        except RuntimeError:
+            return None
 
     def _eager_step(self):
         self.optimizer.zero_grad(set_to_none=True)

@@ -33,16 +33,26 @@ class ReestimateBNStats:
         reestimate_BN_stats(self.model, self.data_loader, self.num_batches)
 
 
-def _make_hook(sync: bool):
+def _dist_on(sync: bool) -> bool:
+    d = torch.distributed
+    return bool(sync and d.is_available() and d.is_initialized() and d.get_world_size() > 1)
+
+
+def _make_hook(ctx: dict):
+    """ctx carries the per-iteration facts the hook needs: ``sync`` (all-reduce the sums), ``weight`` (0.0 when this rank
+    only replays a batch to keep the collectives aligned), ``local_images`` / ``global_images`` (this rank's and all
+    ranks' image count of the iteration -- the global per-channel element count follows without a per-layer sync)."""
     def hook(module: ConvBnReLU, x: torch.Tensor) -> torch.Tensor:
         bn = module.bn
         stats = ops.observe(x, ch_axis=1)                      # [C,5]: .., sum x, sum x^2  -- one read of x
         count = float(x.numel() // x.shape[1])
-        if sync and torch.distributed.is_available() and torch.distributed.is_initialized():
+        if ctx["sync"]:
             sums = stats[:, 2:].contiguous()  # NCCL wants a dense buffer
+            if ctx["weight"] != 1.0:
+                sums.mul_(ctx["weight"])
             torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM)
             stats[:, 2:] = sums
-            count *= torch.distributed.get_world_size()
+            count = count / ctx["local_images"] * ctx["global_images"]  # ranks may hold different batch sizes
         mean, var_b, _ = ops.bn_moments_finalize(stats, count, module.running_mean_sum, module.running_var_sum)
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
@@ -53,10 +63,17 @@ def _make_hook(sync: bool):
 
 def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=False, sync=True):
     """Same signature as estimate_bn.py:38 (+ ``sync``).  Requires layers built with is_fuse_bn=False (the reference
-    needs ``module.bn`` too, :60)."""
+    needs ``module.bn`` too, :60).
+
+    With torch.distributed initialised and ``sync=True`` the per-channel sums of every layer are all-reduced (SyncBN-style):
+    iteration k re-estimates from the union of every rank's k-th batch.  Ranks may hold different numbers of batches and
+    different batch sizes: one tiny all-reduce per iteration tells every rank how many images take part, a rank that has
+    run out of data replays its last batch with weight zero so the per-layer collectives stay aligned, and the loop ends
+    when no rank has data left."""
     model.eval()
     layers = [(n, m) for n, m in model.named_modules() if isinstance(m, ConvBnReLU) and hasattr(m, "bn")]
-    hook = _make_hook(sync)
+    ctx = {"sync": _dist_on(sync), "weight": 1.0, "local_images": 1, "global_images": 1}
+    hook = _make_hook(ctx)
     for _, m in layers:
         m.running_mean_sum = torch.zeros_like(m.bn.running_mean)
         m.running_var_sum = torch.zeros_like(m.bn.running_var)
@@ -70,14 +87,32 @@ def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=Fals
         m._bn_reestimate = hook
     device = next(model.parameters()).device
     batch_count = 0
+    it = iter(data_loader)
+    last = None
+    taken = 0
     try:
         with torch.no_grad():
-            for imgs, _targets in data_loader:
-                imgs = imgs.to(device, non_blocking=True).float() / 255.0
+            while True:
+                item = next(it, None) if taken < num_batches else None
+                if item is not None:
+                    taken += 1
+                    last = item[0]
+                if ctx["sync"]:
+                    n_local = float(item[0].shape[0]) if item is not None else 0.0
+                    t = torch.tensor([1.0 if item is not None else 0.0, n_local], dtype=torch.float64, device=device)
+                    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+                    n_have, n_global = t.tolist()  # the one host synchronisation of the iteration
+                    if n_have == 0:
+                        break
+                    if last is None:
+                        raise RuntimeError("reestimate_BN_stats(sync=True): this rank has no batch at all")
+                    ctx["weight"] = 1.0 if item is not None else 0.0
+                    ctx["local_images"], ctx["global_images"] = float(last.shape[0]), n_global
+                elif item is None:
+                    break
+                imgs = last.to(device, non_blocking=True).float() / 255.0
                 model(imgs)
                 batch_count += 1
-                if batch_count == num_batches:
-                    break
     finally:
         for _, m in layers:
             m._bn_reestimate = None
