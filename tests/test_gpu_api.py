@@ -284,7 +284,7 @@ def test_bn_reestimate_api_matches_golden():
     from vsiquantization_b200.utils.estimate_bn import _make_hook
     layer.running_mean_sum = torch.zeros(C, device="cuda")
     layer.running_var_sum = torch.zeros(C, device="cuda")
-    got = _make_hook(False)(layer, x)
+    got = _make_hook({"sync": False, "weight": 1.0, "local_images": 1.0, "global_images": 1.0})(layer, x)
     assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
 
 

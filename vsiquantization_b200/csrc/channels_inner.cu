@@ -159,14 +159,16 @@ __global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: 
                 for (int j = 0; j < kU; ++j) {
                     if (s + j >= r.s1) continue;
                     Vec4 out;
-                    bool bad = !all_fast;
+                    FastGuard guard;
+                    guard_reset(guard);
 #pragma unroll
                     for (int e = 0; e < kCiVec; ++e) {
                         float xe = BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e];
                         if (RELU) xe = max_nan(xe, 0.0f);
-                        out.v[e] = dequant(elem_fast(xe, p[e], bad).q, p[e]);
+                        guard_note(guard, xe);
+                        out.v[e] = dequant(elem_fast(xe, p[e]).q, p[e]);
                     }
-                    if (bad) {
+                    if (!all_fast || guard_bad(guard)) {
 #pragma unroll
                         for (int e = 0; e < kCiVec; ++e) {
                             float xe = BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e];
@@ -190,14 +192,17 @@ __device__ __forceinline__ void ci_bwd_vec(const Vec4& vx, const Vec4& vg, const
                                            bool all_fast, Vec4& out, float (&te)[kCiVec], float (&tb)[kCiVec],
                                            float (&tdb)[kCiVec]) {
     float ve[kCiVec], vbz[kCiVec];
-    bool bad = !all_fast;
+    FastGuard guard;
+    guard_reset(guard);
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
         const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
         const float xe = RELU ? max_nan(xb, 0.0f) : xb;
         const float ge = vg.v[e];
-        const Elem el = elem_fast(xe, p[e], bad);
-        float d = dx_fast(ge, el.m, p[e], bad);
+        guard_note(guard, xe);
+        guard_note(guard, ge);
+        const Elem el = elem_fast(xe, p[e]);
+        float d = dx_fast(ge, el.m, p[e]);
         if (RELU) d = xb > 0.0f ? d : 0.0f;
         out.v[e] = d;
         if (WANT_DS) {
@@ -207,7 +212,7 @@ __device__ __forceinline__ void ci_bwd_vec(const Vec4& vx, const Vec4& vg, const
             vbz[e] = el.m ? 0.0f : ge;
         }
     }
-    if (bad) {  // rare: IEEE sequences for the whole vector
+    if (!all_fast || guard_bad(guard)) {  // rare: IEEE sequences for the whole vector
 #pragma unroll
         for (int e = 0; e < kCiVec; ++e) {
             const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];

@@ -177,24 +177,31 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // Fixed-order combine of per-CTA records [n_rec][width] (fp64): one CTA owns 8 consecutive entries; inside a warp the
 // low three lane bits select the entry and the high two a record phase, so one load instruction of a warp reads four
-// 64-byte segments and the 32 (warp, phase) pairs of the CTA walk the records 32 apart -- ~n_rec/32 dependent loads per
-// thread.  The phases are then added by two xor-shuffles and the eight warps through shared memory, always in the same
-// order.  Returns the sum for entry (base + (lane & 7)) in every thread with warp == 0 && lane < 8.
+// 64-byte segments and the 32 (warp, phase) pairs of the CTA walk the records 32 apart.  A thread issues ALL its loads
+// (up to 16 per pass: 512 records) before the first add, so the combine costs one memory round trip instead of one per
+// record (ncu: 5.5 us -> the latency of a single L2 read for a 296-record launch).  The phases are then added by two
+// xor-shuffles and the eight warps through shared memory, always in the same order.  Returns the sum for entry
+// (base + (lane & 7)) in every thread with warp == 0 && lane < 8.
 constexpr int kCombineEntries = 8;
+constexpr int kCombineDepth = 16;
 __device__ __forceinline__ double ci_combine8_sum(const double* __restrict__ records, size_t width, uint32_t n_rec,
                                                   size_t idx, bool valid, double (*s_part)[kCombineEntries]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t phase = (uint32_t)warp * 4u + (uint32_t)(lane >> 3);
-    double a0 = 0.0, a1 = 0.0;
-    if (valid) {
-        uint32_t r = phase;
-        for (; r + 32 < n_rec; r += 64) {
-            a0 += __ldcg(records + (size_t)r * width + idx);
-            a1 += __ldcg(records + (size_t)(r + 32) * width + idx);
+    double v = 0.0;
+    for (uint32_t r0 = phase; r0 < n_rec; r0 += 32u * kCombineDepth) {
+        double a[kCombineDepth];
+#pragma unroll
+        for (int k = 0; k < kCombineDepth; ++k) {
+            const uint32_t r = r0 + 32u * (uint32_t)k;
+            a[k] = (valid && r < n_rec) ? __ldcg(records + (size_t)r * width + idx) : 0.0;
         }
-        if (r < n_rec) a0 += __ldcg(records + (size_t)r * width + idx);
+#pragma unroll
+        for (int st = 1; st < kCombineDepth; st <<= 1)
+#pragma unroll
+            for (int k = 0; k + st < kCombineDepth; k += 2 * st) a[k] += a[k + st];
+        v += a[0];
     }
-    double v = a0 + a1;
     v += __longlong_as_double(__shfl_xor_sync(0xffffffffu, __double_as_longlong(v), 8));
     v += __longlong_as_double(__shfl_xor_sync(0xffffffffu, __double_as_longlong(v), 16));
     if (lane < kCombineEntries) s_part[warp][lane] = v;

@@ -192,41 +192,56 @@ __device__ __forceinline__ float dx_slow(float g, bool m, const QP& p) {
 //     q2 = RN(q1 + (x - q1*s)*r)                 -> correctly rounded (Markstein's theorem)
 // The residuals are exact as long as nothing under/overflows: guaranteed for 2^-60 <= |x| < 2^61 and
 // 2^-40 <= |s| <= 2^40.  x == 0 gives a zero whose sign is taken from q0 (= sign(x) xor sign(s)).
-// Anything else (denormal, huge, inf, NaN, odd scale) raises `bad`; the caller then recomputes the whole
-// vector with the IEEE sequence above, so the branch is per 8 elements and almost never taken.
+// Anything else (denormal, huge, inf, NaN, odd scale) fails the vector's FastGuard (below); the caller then recomputes
+// the whole vector with the IEEE sequence above, so the branch is per 4-8 elements and almost never taken.
 // dx = RN(RN(g*s) / s): g itself is a faithful quotient, so ONE correction step is exact:
 //     gd = RN(g*s);  rho = gd - g*s (exact FMA);  dx = RN(g + rho*r), sign taken from g.
 // tests/test_gpu_kernels.py::test_division_* check both against the IEEE division over ALL 2^32 inputs.
 constexpr float kFastLo = 8.673617379884035e-19f;  // 2^-60
 constexpr float kFastHi = 2.305843009213694e18f;   // 2^61
 
-__device__ __forceinline__ float div_fast(float x, const QP& p, bool& bad) {
+// The admissibility test is per VECTOR, not per element (three compares and a predicate merge per value made up a quarter
+// of the backward's instructions and all of them issue on the ALU pipe, the busiest one):
+//   hi = sum |v_i|          (FADD, FMA pipe)   hi < 2^61 implies every |v_i| < 2^61; NaN / inf make the test fail
+//   lo = min (2*bits_i - 1) (unsigned)         zero maps to 0xffffffff, 0 < |v| < 2^-60 to a key below kTinyKey
+// so "guard_ok" still guarantees 2^-60 <= |v| < 2^61 or v == 0 for every value noted -- the condition under which
+// div_fast / dx_fast are proven exact -- and only errs towards the slow path (values within 16x of 2^61).
+struct FastGuard {
+    float hi;
+    uint32_t lo;
+};
+constexpr uint32_t kTinyKey = 0x42ffffffu;  // 2 * bits(2^-60) - 1
+__device__ __forceinline__ void guard_reset(FastGuard& g) {
+    g.hi = 0.0f;
+    g.lo = 0xffffffffu;
+}
+__device__ __forceinline__ void guard_note(FastGuard& g, float v) {
+    g.hi = __fadd_rn(g.hi, fabsf(v));
+    g.lo = min(g.lo, 2u * __float_as_uint(v) - 1u);
+}
+__device__ __forceinline__ bool guard_bad(const FastGuard& g) { return !(g.hi < kFastHi) || (g.lo < kTinyKey); }
+
+__device__ __forceinline__ float div_fast(float x, const QP& p) {
     const float q0 = __fmul_rn(x, p.r);
     const float e0 = __fmaf_rn(-q0, p.s, x);
     const float q1 = __fmaf_rn(e0, p.r, q0);
     const float e1 = __fmaf_rn(-q1, p.s, x);
     const float q2 = __fmaf_rn(e1, p.r, q1);
-    const float ax = fabsf(x);
-    const bool in = (ax >= kFastLo) && (ax < kFastHi);
-    bad = bad || (!in && x != 0.0f);
     return copysignf(q2, q0);
 }
-__device__ __forceinline__ Elem elem_fast(float x, const QP& p, bool& bad) {
+__device__ __forceinline__ Elem elem_fast(float x, const QP& p) {
     Elem e;
-    e.v = div_fast(x, p, bad);
+    e.v = div_fast(x, p);
     e.t = __fadd_rn(e.v, p.z);
     const float tc = clamp_t(e.t, p);
     e.q = rintf(tc);
     e.m = (tc == e.t);  // clamped value unchanged <=> in range (false for NaN)
     return e;
 }
-__device__ __forceinline__ float dx_fast(float g, bool m, const QP& p, bool& bad) {
+__device__ __forceinline__ float dx_fast(float g, bool m, const QP& p) {
     const float gd = __fmul_rn(g, p.s);
     const float rho = __fmaf_rn(-g, p.s, gd);
     const float q = copysignf(__fmaf_rn(rho, p.r, g), g);
-    const float ag = fabsf(g);
-    const bool in = (ag >= kFastLo) && (ag < kFastHi);
-    bad = bad || (!in && g != 0.0f);
     return m ? q : p.zero_dx;
 }
 

@@ -644,16 +644,18 @@ __global__ void __launch_bounds__(kThreads) division_selftest_kernel(float s, in
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
         const float x = __uint_as_float((uint32_t)i);
-        bool bad = !p.fast;
+        FastGuard guard;
+        guard_reset(guard);
+        guard_note(guard, x);
         float a, b;
         if (mode == 0) {
-            a = div_fast(x, p, bad);
+            a = div_fast(x, p);
             b = __fdiv_rn(x, s);
         } else {
-            a = dx_fast(x, true, p, bad);
+            a = dx_fast(x, true, p);
             b = __fdiv_rn(__fmul_rn(x, s), s);
         }
-        if (bad) a = b;  // the kernels redo such vectors with the IEEE sequence
+        if (!p.fast || guard_bad(guard)) a = b;  // the kernels redo such vectors with the IEEE sequence
         const bool same = (__float_as_uint(a) == __float_as_uint(b)) || ((a != a) && (b != b));
         wrong += same ? 0u : 1u;
     }

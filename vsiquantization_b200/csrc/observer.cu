@@ -437,14 +437,27 @@ __global__ void __launch_bounds__(kThreads)
     pdl_wait();
     float mn = INFINITY, mx = -INFINITY;
     double sa = 0.0, s1 = 0.0, s2 = 0.0;
-    if (c < C) {
-        for (uint32_t r = phase; r < n_rec; r += 32) {
+    constexpr int kDepth = 7;  // records per pass: 35 independent loads in flight per thread, then the folds
+    for (uint32_t r0 = phase; r0 < n_rec; r0 += 32u * kDepth) {
+        double v[kDepth][kCiObsFields];
+#pragma unroll
+        for (int k = 0; k < kDepth; ++k) {
+            const uint32_t r = r0 + 32u * (uint32_t)k;
+            const bool ok = c < C && r < n_rec;
             const double* rec = records + (size_t)r * kCiObsFields * C + c;
-            mn = nanmin(mn, (float)__ldcg(rec));
-            mx = nanmax(mx, (float)__ldcg(rec + C));
-            sa += __ldcg(rec + 2 * C);
-            s1 += __ldcg(rec + 3 * C);
-            s2 += __ldcg(rec + 4 * C);
+            v[k][0] = ok ? __ldcg(rec) : (double)INFINITY;
+            v[k][1] = ok ? __ldcg(rec + C) : (double)-INFINITY;
+            v[k][2] = ok ? __ldcg(rec + 2 * C) : 0.0;
+            v[k][3] = ok ? __ldcg(rec + 3 * C) : 0.0;
+            v[k][4] = ok ? __ldcg(rec + 4 * C) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < kDepth; ++k) {
+            mn = nanmin(mn, (float)v[k][0]);
+            mx = nanmax(mx, (float)v[k][1]);
+            sa += v[k][2];
+            s1 += v[k][3];
+            s2 += v[k][4];
         }
     }
 #pragma unroll

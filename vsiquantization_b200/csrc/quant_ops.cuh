@@ -10,9 +10,9 @@ namespace vsiq {
 // ------------------------------------------------------------------------------------------ ops
 struct QuantOpBase : OpBase {
     QP p;
-    bool bad;
-    __device__ __forceinline__ void vec_begin() { bad = !p.fast; }
-    __device__ __forceinline__ bool vec_bad() const { return bad; }
+    FastGuard guard;  // admissibility of the current vector for the division-free arithmetic (common.cuh)
+    __device__ __forceinline__ void vec_begin() { guard_reset(guard); }
+    __device__ __forceinline__ bool vec_bad() const { return !p.fast || guard_bad(guard); }
 };
 
 // RELU = true fuses the preceding activation into the quantiser: the kernels see the conv output x, quantise
@@ -24,7 +24,9 @@ __device__ __forceinline__ float pre_act(float x) { return RELU ? max_nan(x, 0.0
 template <bool RELU>
 struct FwdOp : QuantOpBase {
     __device__ __forceinline__ void apply(const float (&a)[1], float (&o)[1]) {
-        o[0] = dequant(elem_fast(pre_act<RELU>(a[0]), p, bad).q, p);
+        const float x = pre_act<RELU>(a[0]);
+        guard_note(guard, x);
+        o[0] = dequant(elem_fast(x, p).q, p);
     }
     __device__ __forceinline__ void apply_slow(const float (&a)[1], float (&o)[1]) {
         o[0] = dequant(elem_slow(pre_act<RELU>(a[0]), p).q, p);
@@ -34,8 +36,11 @@ struct FwdOp : QuantOpBase {
 template <bool RELU>
 struct SteBwdOp : QuantOpBase {
     __device__ __forceinline__ void apply(const float (&a)[2], float (&o)[1]) {
-        const Elem e = elem_fast(pre_act<RELU>(a[0]), p, bad);
-        const float dx = dx_fast(a[1], e.m, p, bad);
+        const float x = pre_act<RELU>(a[0]);
+        guard_note(guard, x);
+        guard_note(guard, a[1]);
+        const Elem e = elem_fast(x, p);
+        const float dx = dx_fast(a[1], e.m, p);
         o[0] = (!RELU || a[0] > 0.0f) ? dx : 0.0f;
     }
     __device__ __forceinline__ void apply_slow(const float (&a)[2], float (&o)[1]) {
@@ -46,9 +51,11 @@ struct SteBwdOp : QuantOpBase {
 
 struct FwdBwdOp : QuantOpBase {
     __device__ __forceinline__ void apply(const float (&a)[2], float (&o)[2]) {
-        const Elem e = elem_fast(a[0], p, bad);
+        guard_note(guard, a[0]);
+        guard_note(guard, a[1]);
+        const Elem e = elem_fast(a[0], p);
         o[0] = dequant(e.q, p);
-        o[1] = dx_fast(a[1], e.m, p, bad);
+        o[1] = dx_fast(a[1], e.m, p);
     }
     __device__ __forceinline__ void apply_slow(const float (&a)[2], float (&o)[2]) {
         const Elem e = elem_slow(a[0], p);
@@ -63,7 +70,7 @@ struct LsqBwdOp : QuantOpBase {
     float b_acc;  // sum g over clamped-out elements
     float e_vec, b_vec;  // the current vector's share (committed by vec_done, discarded on a redo)
     __device__ __forceinline__ void vec_begin() {
-        bad = !p.fast;
+        guard_reset(guard);
         e_vec = 0.0f;
         b_vec = 0.0f;
     }
@@ -90,8 +97,11 @@ struct LsqBwdOp : QuantOpBase {
         }
     }
     __device__ __forceinline__ void apply(const float (&a)[2], float (&o)[1]) {
-        const Elem e = elem_fast(pre_act<RELU>(a[0]), p, bad);
-        if (MASK_MODE == VSIQ_MASK_ROUNDED) o[0] = dx_fast(a[1], e.m, p, bad);
+        const float x = pre_act<RELU>(a[0]);
+        guard_note(guard, x);
+        guard_note(guard, a[1]);
+        const Elem e = elem_fast(x, p);
+        if (MASK_MODE == VSIQ_MASK_ROUNDED) o[0] = dx_fast(a[1], e.m, p);
         accumulate(a[1], e, o);
         if (RELU) o[0] = a[0] > 0.0f ? o[0] : 0.0f;
     }
