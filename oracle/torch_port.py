@@ -51,3 +51,46 @@ def fwd_bwd(x, g, scale, zero_point, qmin, qmax, learn=False):
     y = fake_quant(x, scale, zero_point, qmin, qmax, learn)
     y.backward(g)
     return (y.detach(), x.grad, scale.grad) if learn else (y.detach(), x.grad)
+
+
+class EagerQuantizer:
+    """The reference's quantizer as a plugin object (torch eager on whatever device the tensors live on): per tensor it
+    is quantizers/uniform.py:34-56 verbatim in behaviour; with a multi-element scale it is the per-channel form of
+    quantizers/lsq_module.py:147-173,254-274,317-358 (qparams broadcast along ``ch_axis``, grad-scale
+    (qmax * numel / C) ** -0.5, learnable zero-point rounded and clamped with a straight-through gradient).
+    Used as the same-GPU checker of the model-scale parity tests and as benchmarks/yolo_qat.py's ``--quant-impl eager``
+    yardstick.  A float64 scale is rounded to float32 before use, like ATen does with the reference's 0-dim float64
+    Parameter."""
+
+    def __init__(self, num_bits=8, symmetric=True, ch_axis=None, grad_boost=1.0):
+        self.num_bits, self.symmetric = num_bits, symmetric
+        self.qmin, self.qmax = (-(2 ** (num_bits - 1)), 2 ** (num_bits - 1) - 1) if symmetric else (0, 2 ** num_bits - 1)
+        self.calib_grad_scale = 1
+        self.ch_axis = ch_axis
+        self.grad_boost = grad_boost
+
+    @classmethod
+    def like(cls, q):
+        e = cls(q.num_bits, q.symmetric, getattr(q, "ch_axis", None), getattr(q, "grad_boost", 1.0))
+        e.calib_grad_scale = q.calib_grad_scale
+        return e
+
+    def quantize(self, x, scale, zero_point, is_learning_scale=False):
+        C = scale.numel() if isinstance(scale, torch.Tensor) else 1
+        shape = [1] * x.dim()
+        if C > 1:
+            shape[self.ch_axis] = C
+        if isinstance(scale, torch.Tensor):
+            scale = scale.to(torch.float32).reshape(shape if C > 1 else ())
+        if isinstance(zero_point, torch.Tensor):
+            zero_point = zero_point.to(torch.float32).reshape(shape if C > 1 else ())
+        if is_learning_scale and isinstance(scale, torch.Tensor):
+            gs = (self.qmax * (x.numel() / C)) ** -0.5 * float(self.grad_boost)
+            cgs = self.calib_grad_scale
+            gs = gs * (cgs.sum() if isinstance(cgs, torch.Tensor) else cgs)
+            scale = _ScaleGrad.apply(scale, gs)
+            if not self.symmetric and isinstance(zero_point, torch.Tensor) and zero_point.is_floating_point():
+                zero_point = torch.clamp(_RoundSTE.apply(zero_point), self.qmin, self.qmax)
+                zero_point = _ScaleGrad.apply(zero_point, gs)
+        x_int = torch.clamp(_RoundSTE.apply(x / scale + zero_point), self.qmin, self.qmax)
+        return (x_int - zero_point) * scale

@@ -84,6 +84,24 @@ def run(native: bool, bits_w: int, bits_a: int):
     model.to(dev)  # the learnable scales become CUDA tensors (yolov8_qat.py:111)
     model.train()
     init = {n: [float(m.weight_quantizer.scale.detach()), float(m.activation_quantizer.scale.detach())] for n, m in fused}
+    # |terms| of every scale gradient's sums, gs * sum |g| (|q - z| + |x/s|): the yardstick its fp32 error is judged by
+    mass = {}
+    if native:
+        for n, m in fused:
+            for attr in ("weight_quantizer", "activation_quantizer"):
+                mgr = getattr(m, attr)
+                orig = mgr.quantizer.quantize
+
+                def wrapped(xq, scale, zp, learn=False, _orig=orig, _key=f"{n}.{attr}.scale", _q=mgr.quantizer):
+                    yq = _orig(xq, scale, zp, learn)
+                    if yq.requires_grad and _key not in mass:
+                        def grab(gq, xq=xq.detach(), yq=yq.detach(), scale=scale):
+                            s32 = float(scale.detach().float())
+                            gs = (_q.qmax * xq.numel()) ** -0.5
+                            mass[_key] = gs / abs(s32) * float((gq.double().abs() * (yq.double().abs() + xq.double().abs())).sum())
+                        yq.register_hook(grab)
+                    return yq
+                mgr.quantizer.quantize = wrapped
     acts = {}
     hooks = [m.register_forward_hook(lambda mod, i, o, n=n: acts.__setitem__(n, o.detach())) for n, m in fused]
     gx = torch.Generator().manual_seed(3)
@@ -102,7 +120,7 @@ def run(native: bool, bits_w: int, bits_a: int):
         opt.step()
     for h in hooks:
         h.remove()
-    return {"plugin_module": plug, "calibrated": calibrated, "init": init, "losses": losses, "first": first,
+    return {"mass": mass, "plugin_module": plug, "calibrated": calibrated, "init": init, "losses": losses, "first": first,
             "n_fused": len(fused), "scale_devices": sorted({str(m.weight_quantizer.scale.device) for _, m in fused})}
 
 
@@ -123,12 +141,13 @@ def compare(bits_w, bits_a):
         gb = fb["grads"][n]
         if n.endswith(("quantizer.scale", "quantizer.zero_point")):
             da, db = float(ga), float(gb)
-            sworst = max(sworst, abs(da - db) / max(abs(da), abs(db), 1e-12))
+            sworst = max(sworst, abs(da - db) / b["mass"][n])
         elif not np.array_equal(bits(ga), bits(gb)):
             wbad.append(n)
     res["weight_bias_grads_with_mismatch"] = wbad[:5]
     res["n_grads"] = len(fa["grads"])
-    res["scale_grad_worst_rel"] = sworst
+    res["scale_grad_worst_err_over_mass"] = sworst
+    res["n_scale_grads"] = len(b["mass"])
     return res
 
 

@@ -18,9 +18,9 @@ def test_reference_code_runs_the_native_plugins_bit_exact_on_the_gpu():
     the CUDA kernels through the registry: YOLOv8n, 57 fused layers, W8A8 and W4A8, calibration -> learnable scales ->
     three SGD steps.  Against the reference's own plugins on the same GPU (same cuDNN algorithms, CUDA-tensor scales):
     calibrated scales / zero-points and LSQ initialisations identical, every fused layer's output, the input gradient and
-    every weight / bias gradient bit-identical, scale gradients within 1e-3 relative (the reference sums them in fp32 in
-    ATen's reduction order; the kernels' sums are checked against the fp64 oracle in test_gpu_kernels.py), losses of the
-    three steps equal to 1e-6 relative."""
+    every weight / bias gradient bit-identical, every scale gradient within 1e-5 x the sum of |terms| of its reductions
+    (north_star's fp32 bar; the reference adds two fp32 full-tensor sums in ATen's order, the kernels' sums are checked
+    against the fp64 oracle in test_gpu_kernels.py), losses of the three steps equal to 1e-6 relative."""
     sys.path.insert(0, ROOT)
     from oracle import ref_shim
     if not ref_shim.available():
@@ -38,6 +38,7 @@ def test_reference_code_runs_the_native_plugins_bit_exact_on_the_gpu():
         assert r["layers_with_output_mismatch"] == [], r["layers_with_output_mismatch"]
         assert r["dx_equal"], "input gradient differs"
         assert r["weight_bias_grads_with_mismatch"] == [], r["weight_bias_grads_with_mismatch"]
-        assert r["scale_grad_worst_rel"] <= 1e-3, r["scale_grad_worst_rel"]
+        assert r["n_scale_grads"] == 114
+        assert r["scale_grad_worst_err_over_mass"] <= 1e-5, r["scale_grad_worst_err_over_mass"]
         for la, lb in zip(r["losses_reference"], r["losses_native"]):
             assert abs(la - lb) <= 1e-6 * abs(la), (r["losses_reference"], r["losses_native"])

@@ -13,6 +13,7 @@ for shp in shapes:
     x = torch.randn(shp, device="cuda").contiguous(memory_format=torch.channels_last)
     g = torch.randn(shp, device="cuda").contiguous(memory_format=torch.channels_last)
     y = torch.empty_like(x); n = x.numel()
+    gw = torch.randn(shp[0], 2 * C, shp[2], shp[3], device="cuda").contiguous(memory_format=torch.channels_last)[:, C:]  # pitched g
     fl = flush if n * 4 < (256 << 20) else None
     s_t = torch.tensor(0.02, device="cuda"); b = torch.randn(C, device="cuda")
     sc = torch.full((1, C, 1, 1), 0.02, device="cuda"); zc = torch.full((1, C, 1, 1), 3.3, device="cuda")
@@ -25,6 +26,7 @@ for shp in shapes:
         ("flat lsq pt", 12, lambda: ops.lsq_backward(x, g, s_t, 0, pt, 1e-3)),
         ("ci lsq pt+b", 12, lambda: ops.ci_backward(x, b, g, s_t, 0, pt, 1e-3)),
         ("ci lsq pc+b", 12, lambda: ops.ci_backward(x, b, g, sc, zc, pc, 1e-3, None, True, True, True)),
+        ("ci lsq pitched", 12, lambda: ops.ci_backward(x, b, gw, sc, zc, pc, 1e-3, None, True, True, True)),
         ("ci observe", 4, lambda: ops.observe(x, ch_axis=1)),
         ("sum(0,2,3)", 4, lambda: g.sum((0, 2, 3))),
     ]

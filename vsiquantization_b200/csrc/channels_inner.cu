@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 // input); the producer walks the CTA's step range (static split) or claims 16-step tiles from the atomic queue.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kCiStages = 3;
+constexpr int kCiMinPitchedRowBytes = 512;  // measured: 2 KB rows 42 vs 52 us, 512 B rows 132 vs 138, 256 B rows 93 vs 79
 constexpr uint32_t kCiDone = 0xffffffffu;
 constexpr uint32_t kCiTileEnd = 0x80000000u;  // the consumers fold their fp32 partials at tile ends (deterministic sums)
 
@@ -465,7 +466,7 @@ struct CiRing {
 template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
 __global__ void __launch_bounds__(kThreads + 32, 2)
     ci_bwd_tma_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ g,
-                      float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket) {
+                      float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket, int64_t g_pitch) {
     extern __shared__ __align__(128) unsigned char ci_smem[];  // kCiStages x [x unit | g unit]; later the flush scratch
     __shared__ CiRing ring;
     const int t = threadIdx.x;
@@ -482,44 +483,63 @@ __global__ void __launch_bounds__(kThreads + 32, 2)
     __syncthreads();
 
     if (t >= kThreads) {  // ---------------------------------------------------------------- producer warp
-        if (t == kThreads) {
-            pdl_launch_dependents();
-            unsigned int* counter = (unsigned int*)ws + 1;
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t s0 = 0, s1 = 0, tile = blockIdx.x;
-            if (geo.sched == kCiStatic) {
-                const uint64_t S = (uint64_t)geo.steps;
-                s0 = (uint32_t)(S * blockIdx.x / gridDim.x);
-                s1 = (uint32_t)(S * (blockIdx.x + 1) / gridDim.x);
-            }
-            for (;;) {
-                if (geo.sched != kCiStatic) {
-                    if (geo.sched == kCiDynamic) tile = atomicAdd(counter, 1u);
-                    if (tile >= geo.n_tiles) break;
-                    s0 = tile * (uint32_t)geo.tile_steps;
-                    s1 = s0 + geo.tile_steps < (uint32_t)geo.steps ? s0 + geo.tile_steps : (uint32_t)geo.steps;
-                    tile += gridDim.x;  // interleaved: the next tile of this CTA
+        // Lane 0 claims the work and owns the barriers; all 32 lanes issue copies when grad_output is pitched (one bulk
+        // copy per row of g: a channel slice of a wider NHWC tensor is contiguous only within a row).  Control flow is
+        // warp-uniform: the range comes from lane 0 by shuffle.
+        const int lane = t - kThreads;
+        const bool pitched = g_pitch != geo.channels;
+        const uint32_t row_bytes = (uint32_t)geo.channels * 4u;
+        if (lane == 0) pdl_launch_dependents();
+        unsigned int* counter = (unsigned int*)ws + 1;
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t s0 = 0, s1 = 0, tile = blockIdx.x;
+        if (geo.sched == kCiStatic) {
+            const uint64_t S = (uint64_t)geo.steps;
+            s0 = (uint32_t)(S * blockIdx.x / gridDim.x);
+            s1 = (uint32_t)(S * (blockIdx.x + 1) / gridDim.x);
+        }
+        for (;;) {
+            if (geo.sched != kCiStatic) {
+                if (geo.sched == kCiDynamic) {
+                    if (lane == 0) tile = atomicAdd(counter, 1u);
+                    tile = __shfl_sync(0xffffffffu, tile, 0);
                 }
-                for (uint32_t s = s0; s < s1; s += kCiUnroll) {
-                    const int64_t v0 = (int64_t)s * geo.threads;
-                    int64_t nv = (int64_t)((s + kCiUnroll < s1 ? s + kCiUnroll : s1) - s) * geo.threads;
-                    if (v0 + nv > geo.n_vec) nv = geo.n_vec - v0;
+                if (tile >= geo.n_tiles) break;
+                s0 = tile * (uint32_t)geo.tile_steps;
+                s1 = s0 + geo.tile_steps < (uint32_t)geo.steps ? s0 + geo.tile_steps : (uint32_t)geo.steps;
+                tile += gridDim.x;  // interleaved: the next tile of this CTA
+            }
+            for (uint32_t s = s0; s < s1; s += kCiUnroll) {
+                const int64_t v0 = (int64_t)s * geo.threads;
+                int64_t nv = (int64_t)((s + kCiUnroll < s1 ? s + kCiUnroll : s1) - s) * geo.threads;
+                if (v0 + nv > geo.n_vec) nv = geo.n_vec - v0;
+                const uint32_t bytes = (uint32_t)nv * 16u;
+                unsigned char* xs = ci_smem + (size_t)stage * 2 * unit_bytes;
+                if (lane == 0) {
                     mbar_wait(&ring.empty[stage], phase ^ 1u);  // the consumers have drained this stage
                     ring.vec0[stage] = v0;
                     ring.nvec[stage] = (uint32_t)nv | (s + kCiUnroll >= s1 ? kCiTileEnd : 0u);
-                    const uint32_t bytes = (uint32_t)nv * 16u;
-                    unsigned char* xs = ci_smem + (size_t)stage * 2 * unit_bytes;
                     mbar_arrive_expect_tx(&ring.full[stage], 2 * bytes);
                     bulk_load(xs, x + v0 * kCiVec, bytes, &ring.full[stage]);
-                    bulk_load(xs + unit_bytes, g + v0 * kCiVec, bytes, &ring.full[stage]);
-                    if (++stage == kCiStages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    if (!pitched) bulk_load(xs + unit_bytes, g + v0 * kCiVec, bytes, &ring.full[stage]);
                 }
-                if (geo.sched == kCiStatic) break;
+                if (pitched) {
+                    __syncwarp();  // the stage is free and its transaction count is armed
+                    const int64_t row0 = v0 / geo.groups;
+                    const int rows = (int)(nv / geo.groups);
+                    for (int r = lane; r < rows; r += 32)
+                        bulk_load(xs + unit_bytes + (size_t)r * row_bytes, g + (row0 + r) * g_pitch, row_bytes,
+                                  &ring.full[stage]);
+                }
+                if (++stage == kCiStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
+            if (geo.sched == kCiStatic) break;
+        }
+        if (lane == 0) {
             mbar_wait(&ring.empty[stage], phase ^ 1u);
             ring.nvec[stage] = kCiDone;
             mbar_arrive(&ring.full[stage]);
@@ -691,10 +711,11 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
     o.gs_dev = grad_scale_dev;
     const int width = 2 * (pcq ? (int)channels : 1) + (hb ? (int)channels : 0);
     const int use_ticket = width <= 64 ? 1 : 0;  // wider records: ci_finalize_kernel, one CTA per 8 entries
-    // dense grad_output: inputs staged through shared memory by bulk asynchronous copies (ci_bwd_tma_kernel); a pitched
-    // grad_output (channel slice of a wider NHWC tensor) keeps the direct-load kernel.  VSIQ_CI_TMA=0 forces the latter.
-    static const bool tma_enabled = []() { const char* e = getenv("VSIQ_CI_TMA"); return !(e && e[0] == '0'); }();
-    const bool use_tma = tma_enabled && g_row_pitch == channels;
+    // inputs staged through shared memory by bulk asynchronous copies (ci_bwd_tma_kernel); a pitched grad_output (channel
+    // slice of a wider NHWC tensor) is fetched row by row, rows of >= kCiMinPitchedRowBytes only (below that the copies
+    // are too small to pay and the direct-load kernel runs).  VSIQ_CI_TMA=0 forces the direct kernel, =2 the staged one.
+    static const int tma_mode = []() { const char* e = getenv("VSIQ_CI_TMA"); return e ? atoi(e) : 1; }();
+    const bool use_tma = tma_mode != 0 && (g_row_pitch == channels || tma_mode == 2 || channels * 4 >= kCiMinPitchedRowBytes);
     int cur_dev = 0;
     if (use_tma && cudaGetDevice(&cur_dev) != cudaSuccess) return VSIQ_ERR_NO_DEVICE;
     const size_t ring_bytes = (size_t)kCiStages * 2 * (size_t)geo.threads * kCiUnroll * 16;
@@ -705,7 +726,7 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
         if (use_tma) {                                                                                                     \
             if (cudaError_t ae = ci_set_smem_once<ci_bwd_tma_kernel<P, H, R, D>>(cur_dev, 3 * 2 * 16384)) return (int)ae;   \
             ci_bwd_tma_kernel<P, H, R, D><<<grid, kThreads + 32, dyn_smem, st>>>(x, bias, g, dx, geo, qpd, workspace, o,    \
-                                                                                use_ticket);                              \
+                                                                                use_ticket, g_row_pitch);                 \
         } else {                                                                                                           \
             ci_bwd_kernel<P, H, R, D><<<grid, kThreads, 0, st>>>(x, bias, g, dx, geo, qpd, workspace, o, use_ticket,        \
                                                                  g_row_pitch);                                            \
