@@ -35,6 +35,7 @@ def parse(argv=None):
     ap.add_argument("--channels-last", action="store_true",
                     help="NHWC weights / activations (cuDNN's native layout on sm_100); observers and the BN moments "
                          "pass walk that memory in place")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="autotuned (non-reproducible) cuDNN algorithms")
     return ap.parse_args(argv)
 
 
@@ -52,7 +53,10 @@ def run(args) -> dict:
     dev = torch.device("cuda", local)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.benchmark = True
+    # heuristic, deterministic cuDNN algorithms: a given batch then produces the same bits whichever rank runs it, which is
+    # what makes the activation digests comparable across world sizes (cudnn.benchmark picks per process and per run)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
+    torch.backends.cudnn.deterministic = not args.cudnn_benchmark
     from vsiquantization_b200 import _lib
     from vsiquantization_b200.modules.fuse import fuse_modules_unified
     from vsiquantization_b200.modules.fuse_config import FuseConfig, create_fuse_config_manager
@@ -108,15 +112,17 @@ def run(args) -> dict:
         dist.barrier()
     t_cal = time.perf_counter() - t0
     launches_cal = _lib.launch_count - l0
+    # post-sync scales: digested HERE -- the re-estimation pass below runs the model in calibration mode again, so (as in
+    # the reference, quantization_manager.py:55-71) the observers keep absorbing each rank's local batches afterwards
+    mgrs = quantization_managers(model)
+    hw = _digest((q.scale, q.zero_point) for n, q in mgrs if n.endswith("weight_quantizer"))
+    ha = _digest((q.scale, q.zero_point) for n, q in mgrs if n.endswith("activation_quantizer"))
     t0 = time.perf_counter()
     reestimate_BN_stats(model, mine, num_batches=len(mine), sync=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_bn = time.perf_counter() - t0
-    mgrs = quantization_managers(model)
-    hw = _digest((q.scale, q.zero_point) for n, q in mgrs if n.endswith("weight_quantizer"))
-    ha = _digest((q.scale, q.zero_point) for n, q in mgrs if n.endswith("activation_quantizer"))
     bn = [m.bn for m in model.modules() if hasattr(m, "bn")]
     hb = hashlib.sha256(b"".join(b.running_mean.detach().cpu().numpy().tobytes() + b.running_var.detach().cpu().numpy().tobytes()
                                  for b in bn)).hexdigest()
@@ -126,6 +132,8 @@ def run(args) -> dict:
         every = [torch.zeros_like(mine_d) for _ in range(world)]
         dist.all_gather(every, mine_d)
         agree = all(bool(torch.equal(e, every[0])) for e in every)
+        if not agree and rank == 0:
+            print("calibration: ranks disagree after the sync:", [e.tolist() for e in every], file=sys.stderr, flush=True)
     t = torch.tensor([t_cal, t_bn, sync_ms, t_fwd], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

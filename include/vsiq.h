@@ -105,6 +105,16 @@ int vsiq_device_info(int *sm_count, int *cc_major, int *cc_minor);
 int vsiq_fake_quant_fwd(const float *x, float *y, void *codes, const vsiq_layout *layout,
                         const vsiq_qparams *qp, vsiq_stream_t stream);
 
+/* ---- integer-code export ------------------------------------------------------------------
+ * codes[i] = clamp(rint(x / s + z), qmin, qmax) as integers -- what the reference computes as `x_int` and only ever keeps
+ * as a float tensor (quantizers/uniform.py:54,95); the on-wire format of a deployed / exported model (utils/util.py:356-374
+ * exports the fake-quantised floats).  code_bits: 16 (int16 / uint16), 8 (int8 / uint8) or 4 (two codes per byte, element
+ * 2k in the low nibble; needs an even `inner`); two's complement when qmin < 0, unsigned otherwise; [qmin, qmax] must fit.
+ * y (optional): the fake-quantised values from the same pass.  x (and y) 32-byte aligned, codes 16-byte aligned, else
+ * VSIQ_ERR_UNSUPPORTED.  NaN inputs get code 0.  Algorithmic traffic: 4 + code_bits/8 bytes per element (+4 with y). */
+int vsiq_quantize_codes(const float *x, float *y, void *codes, int code_bits, const vsiq_layout *layout,
+                        const vsiq_qparams *qp, vsiq_stream_t stream);
+
 /* ---- (3) STE backward ---------------------------------------------------------------------
  * dx = ((g * s) * m) / s,  m = [qmin <= rint(x/s+z) <= qmax]  -- the autograd graph of the forward
  * through RoundStraightThrough (quantizers/uniform.py:258-271) and torch.clamp; no qparam grads. */

@@ -218,6 +218,61 @@ def test_checkpoint_keeps_calibration_and_learned_qparams():
     assert not res.missing_keys and e.weight_quantizer.scale.item() == 0.0123
 
 
+def test_state_dict_holds_tensors_only_and_survives_an_ema_loop():
+    """Training engines walk state_dict() blindly: ultralytics' ModelEMA (the reference's qat_yolov11_ultralytics.py
+    driver builds one over the fused model) tests ``v.dtype.is_floating_point`` on every entry, and the reference's
+    load_partial_checkpoint reads ``.shape`` (utils/util.py:27-29, 401-405).  The extra state is one packed tensor."""
+    import copy
+    import torch
+    from vsiquantization_b200.quantizers.quantization_manager import QuantizationManager as M
+
+    class Layer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 4, 3)
+            self.weight_quantizer = M("UniformQuantizer", "MinMaxObserver", 8, True)
+            self.activation_quantizer = M("LSQQuantizer", "LSQObserver", 4, False)
+
+    a = Layer()
+    st = torch.zeros(1, 8, dtype=torch.float64)
+    st[0, :6] = torch.tensor([-1.5, 2.0, 2.0 / 127, 0.0, 2.0, 1.25], dtype=torch.float64)
+    a.weight_quantizer.observer.load_state(st)
+    a.weight_quantizer._calibrated = True
+    a.weight_quantizer._invalidate()
+    a.activation_quantizer.scale = 0.125          # host code set explicit values
+    a.activation_quantizer.zero_point = 3
+    a.activation_quantizer.quantizer.calib_grad_scale = torch.tensor([0.5, 2.0, 1.0])
+    sd = a.state_dict()
+    assert all(isinstance(v, torch.Tensor) for v in sd.values()), {k: type(v) for k, v in sd.items()}
+    # ultralytics ModelEMA.update
+    ema = copy.deepcopy(a).eval()
+    d = 0.9
+    msd = a.state_dict()
+    for k, v in ema.state_dict().items():
+        if v.dtype.is_floating_point:
+            v *= d
+            v += (1 - d) * msd[k].detach()
+    # the reference's load_partial_checkpoint
+    model_dict = Layer().state_dict()
+    filtered = {k: v for k, v in sd.items() if k in model_dict and v.shape == model_dict[k].shape}
+    assert "conv.weight" in filtered
+    # round trip keeps the Python types the reference's code expects
+    b = Layer()
+    assert not b.load_state_dict(sd, strict=True).missing_keys
+    assert isinstance(b.weight_quantizer.scale, float) and b.weight_quantizer.scale == a.weight_quantizer.scale
+    assert b.activation_quantizer.scale == 0.125 and isinstance(b.activation_quantizer.zero_point, int)
+    assert b.activation_quantizer.zero_point == 3
+    assert torch.equal(b.activation_quantizer.quantizer.calib_grad_scale, torch.tensor([0.5, 2.0, 1.0]))
+    # a checkpoint written with the former dict layout still loads
+    legacy = dict(sd)
+    legacy["weight_quantizer._extra_state"] = {"version": 1, "flags": {"is_quantize": False}, "calibrated": True,
+                                                "observer_state": st, "scale": None, "zero_point": None,
+                                                "calib_grad_scale": 1}
+    c = Layer()
+    c.load_state_dict(legacy, strict=True)
+    assert c.weight_quantizer.is_quantize is False and c.weight_quantizer.scale == a.weight_quantizer.scale
+
+
 def test_multi_tensor_plan_geometry_on_the_host():
     """vsiq_mt_plan is pure host code: tile prefix, per-tensor vs per-channel tiling, argument validation."""
     from vsiquantization_b200 import _lib

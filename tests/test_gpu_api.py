@@ -839,3 +839,41 @@ def test_yolov8n_end_to_end_against_reference_golden(monkeypatch):
         assert float(o.detach().abs().mean()) == pytest.approx(float(ref), rel=0.1)
     grads = torch.stack([torch.stack([m.weight_quantizer.scale.grad, m.activation_quantizer.scale.grad]) for _, m in layers])
     assert bool(torch.isfinite(grads).all()) and grads.dtype == torch.float64
+
+
+def test_reinitialising_a_learned_scale_updates_the_parameter_in_place():
+    """activate_learning_qparam(use_init=True) a second time (or deactivate_learning_qparam, whose use_init defaults to
+    True): the registered Parameter is re-initialised in place -- never shadowed by a plain attribute, never replaced by a
+    new object the optimizer does not know (the reference raises TypeError at this point)."""
+    from vsiquantization_b200.quantizers.quantization_manager import QuantizationManager as M
+    m = M("LSQQuantizer", "LSQObserver", 4, True)
+    m.is_learning_scale = False
+    x = torch.randn(4, 8, 16, 16, device="cuda")
+    m.quantize(x)
+    m.is_learning_scale = True
+    m.init_scaling_factor_for_learning()
+    m.make_learn_qparameter()
+    p = m.scale
+    assert isinstance(p, torch.nn.Parameter)
+    init = float(p.detach())
+    with torch.no_grad():
+        p.mul_(3.0)
+    m.init_scaling_factor_for_learning()          # re-initialise while learnable
+    m.make_learn_qparameter()
+    assert m.scale is p and m._parameters["scale"] is p and "scale" not in m.__dict__
+    assert float(p.detach()) == init
+
+
+def test_poking_observer_extrema_recomputes_the_qparams():
+    """observers/minmax.py:67-74 derives scale / zero-point from min_val / max_val on every call, so host code that sets
+    the extrema sees the new qparams immediately -- also through the owning manager's cached host view."""
+    from vsiquantization_b200.quantizers.quantization_manager import QuantizationManager as M
+    m = M("UniformQuantizer", "MinMaxObserver", 8, False)
+    m.is_learning_scale = False
+    m.quantize(torch.rand(1000, device="cuda") * 2 - 1)
+    s0, z0 = m.scale, m.zero_point
+    m.observer.min_val = -4.0
+    m.observer.max_val = 12.0
+    s1, z1 = m.observer.get_scale_zero_point()
+    assert s1 == (12.0 - -4.0) / (255 + 1e-8) and z1 == round(4.0 / (s1 + 1e-8))
+    assert (m.scale, m.zero_point) == (s1, z1) and (s1, z1) != (s0, z0)

@@ -510,3 +510,46 @@ def test_ci_observe_matches_nchw_observer(shape):
     s0, s1 = st0.cpu().numpy(), st1.cpu().numpy()
     assert np.array_equal(s0[:, :5], s1[:, :5], equal_nan=True)  # running extrema, scale, zero-point, call count
     np.testing.assert_allclose(s1[:, 5:], s0[:, 5:], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,sym", [(8, True), (8, False), (4, True), (4, False), (16, True), (12, False), (3, True)])
+@pytest.mark.parametrize("shape,ch_axis", [(((1 << 16) + 24,), None), ((37, 1030), 0), ((3, 6, 50, 38), 1), ((5, 8), None)])
+def test_integer_code_export(ops, bits, sym, shape, ch_axis):
+    """vsiq_quantize_codes: codes equal the oracle's x_int exactly in every width (int4 packed two per byte, int8, int16),
+    signed and unsigned, per tensor and per channel, ragged rows; y from the same pass is the forward's y bit for bit;
+    wider-than-8-bit ranges are never wrapped into bytes."""
+    rng = np.random.default_rng(bits * 7 + len(shape))
+    x = (rng.standard_normal(shape) * 3).astype(np.float32)
+    x.reshape(-1)[::97] = np.nan
+    x.reshape(-1)[1::113] = 1e30
+    qmin, qmax = (-(1 << (bits - 1)), (1 << (bits - 1)) - 1) if sym else (0, (1 << bits) - 1)
+    C = 1 if ch_axis is None else shape[ch_axis]
+    s = (rng.uniform(0.5, 2.0, C) * 6.0 / (qmax - qmin)).astype(np.float32)
+    z = np.zeros(C, np.float32) if sym else np.rint(rng.uniform(qmax / 3, qmax / 2, C)).astype(np.float32)
+    spec = ops.QSpec(qmin, qmax, ch_axis=ch_axis)
+    xt = dev(x)
+    st, zt = (float(s[0]), float(z[0])) if ch_axis is None else (dev(s), dev(z))
+    y_o, c_o = oracle.fake_quant_fwd(x, s if ch_axis is not None else s[0], z if ch_axis is not None else z[0], qmin, qmax,
+                                     ch_axis=ch_axis, want_codes=True)
+    want = np.where(np.isnan(c_o), 0, c_o).astype(np.int64)
+    for code_bits in sorted({4 if bits <= 4 else None, 8 if bits <= 8 else None, 16} - {None}):
+        y, codes = ops.quantize_codes(xt, st, zt, spec, code_bits)
+        assert bits_equal(y.cpu().numpy(), y_o), (code_bits, first_mismatch(y.cpu().numpy(), y_o))
+        c = codes.cpu().numpy()
+        if code_bits == 4:
+            assert c.dtype == np.uint8 and c.shape == shape[:-1] + (shape[-1] // 2,)
+            lo, hi = (c & 0xf).astype(np.int64), (c >> 4).astype(np.int64)
+            if sym:
+                lo, hi = np.where(lo > 7, lo - 16, lo), np.where(hi > 7, hi - 16, hi)
+            got = np.stack([lo, hi], axis=-1).reshape(shape)
+        else:
+            got = c.astype(np.int64)
+            assert c.shape == shape and c.dtype.itemsize * 8 == code_bits and (c.dtype.kind == "i") == sym
+        assert np.array_equal(got, want), code_bits
+    # the default width never wraps: 8 bits when the range fits, else 16
+    y2, c2 = ops.fake_quant_forward(xt, st, zt, spec, want_codes=True)
+    assert c2.dtype.itemsize == (1 if bits <= 8 else 2) and np.array_equal(c2.cpu().numpy().astype(np.int64), want)
+    if bits > 8:
+        with pytest.raises(Exception):
+            ops.quantize_codes(xt, st, zt, spec, 8)

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "vsiq_error_string": (ctypes.c_char_p, [c_int]),
     "vsiq_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "vsiq_fake_quant_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Layout), ctypes.POINTER(QParams), c_void_p]),
+    "vsiq_quantize_codes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(Layout), ctypes.POINTER(QParams), c_void_p]),
     "vsiq_fake_quant_bwd_ste": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Layout), ctypes.POINTER(QParams), c_void_p]),
     "vsiq_fake_quant_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Layout), ctypes.POINTER(QParams), c_void_p]),
     "vsiq_lsq_bwd_workspace_bytes": (c_size_t, [ctypes.POINTER(Layout)]),

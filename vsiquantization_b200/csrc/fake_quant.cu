@@ -56,18 +56,111 @@ __global__ void __launch_bounds__(kThreads) fq_fwd_bwd_kernel(const float* __res
     run_elementwise<GROUP, V, FwdBwdOp, 2, 2>(in, out, tiles, qpd);
 }
 
-// integer-code export (deployment path, not the training hot loop): 4-byte loads, 1-byte stores
-__global__ void __launch_bounds__(kThreads) fq_codes_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                            int8_t* __restrict__ codes, int64_t n, int64_t inner,
-                                                            int64_t channels, QPDev qpd) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int64_t c = channels == 1 ? 0 : (i / inner) % channels;
-        const QP p = load_qp(qpd, c);
-        const float q = elem_slow(ld_stream1(x + i), p).q;
-        if (y) y[i] = dequant(q, p);
-        const int qi = (q == q) ? (int)q : 0;  // NaN has no code; emit 0
-        codes[i] = (int8_t)(qi & 0xff);
+// Integer-code export (the deployment / ONNX path: the reference only ever holds the codes as floats, uniform.py:54).
+// Same tiles as the forward; a thread turns one 256-bit load into 8 codes and stores them as ONE word: 8 x int4 in 32 bits
+// (low nibble = even element), 8 x int8 in 64 bits, 8 x int16 in 128 bits; the fake-quantised values ride along as a
+// 256-bit store when wanted.  Ragged heads / tails go element by element (byte by byte for int4: rows hold an even number
+// of elements, so a byte never straddles two channels).  Roofline: HBM, 4.5 / 5 / 6 B per element (+4 with y).
+template <int BITS>
+struct CodePack;
+template <>
+struct CodePack<4> {
+    __device__ static __forceinline__ void store8(void* codes, int64_t i, const int (&q)[8]) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w |= ((uint32_t)q[e] & 0xfu) << (4 * e);
+        *reinterpret_cast<uint32_t*>((uint8_t*)codes + (i >> 1)) = w;
+    }
+};
+template <>
+struct CodePack<8> {
+    __device__ static __forceinline__ void store8(void* codes, int64_t i, const int (&q)[8]) {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            lo |= ((uint32_t)q[e] & 0xffu) << (8 * e);
+            hi |= ((uint32_t)q[e + 4] & 0xffu) << (8 * e);
+        }
+        *reinterpret_cast<uint2*>((uint8_t*)codes + i) = make_uint2(lo, hi);
+    }
+};
+template <>
+struct CodePack<16> {
+    __device__ static __forceinline__ void store8(void* codes, int64_t i, const int (&q)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = ((uint32_t)q[2 * e] & 0xffffu) | (((uint32_t)q[2 * e + 1] & 0xffffu) << 16);
+        *reinterpret_cast<uint4*>((uint16_t*)codes + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+__device__ __forceinline__ int code_of(float q) { return (q == q) ? (int)q : 0; }  // NaN has no code: emit 0
+
+template <int BITS>
+__device__ __forceinline__ void code_store1(void* codes, int64_t i, int q) {
+    if (BITS == 8) ((uint8_t*)codes)[i] = (uint8_t)(q & 0xff);
+    if (BITS == 16) ((uint16_t*)codes)[i] = (uint16_t)(q & 0xffff);
+}
+
+template <int BITS, bool WANT_Y>
+__global__ void __launch_bounds__(kThreads)
+    fq_codes_kernel(const float* __restrict__ x, float* __restrict__ y, void* __restrict__ codes, Tiles tiles, QPDev qpd) {
+    const int tid = threadIdx.x;
+    int64_t cur_channel = -1;
+    QP p;
+    for (uint32_t t = blockIdx.x; t < tiles.n_tiles; t += gridDim.x) {
+        const TileCursor<kThreads> c = tile_at<kThreads>(tiles, t);
+        if (c.channel != cur_channel) {
+            p = load_qp(qpd, c.channel);
+            cur_channel = c.channel;
+        }
+        const int64_t off = c.offset;
+        int head = (int)((kVec - (off & (kVec - 1))) & (kVec - 1));
+        head = head < c.len ? head : c.len;
+        const int nvec = (c.len - head) / kVec;
+        const int tail0 = head + nvec * kVec;
+        // ---- ragged head and tail: IEEE sequence, one element (int4: one byte = two elements) per thread
+        const int ragged = head + (c.len - tail0);
+        const int per = BITS == 4 ? 2 : 1;
+        for (int k = tid * per; k < ragged; k += kThreads * per) {
+            const int i0 = k < head ? k : tail0 + (k - head);
+            int q2[2] = {0, 0};
+#pragma unroll
+            for (int u = 0; u < per; ++u) {
+                const float q = elem_slow(ld_stream1(x + off + i0 + u), p).q;
+                if (WANT_Y) y[off + i0 + u] = dequant(q, p);
+                q2[u] = code_of(q);
+            }
+            if (BITS == 4)
+                ((uint8_t*)codes)[(off + i0) >> 1] = (uint8_t)((q2[0] & 0xf) | ((q2[1] & 0xf) << 4));
+            else
+                code_store1<BITS>(codes, off + i0, q2[0]);
+        }
+        // ---- vector body
+        for (int v = tid; v < nvec; v += kThreads) {
+            const int64_t i = off + head + (int64_t)v * kVec;
+            const Vec<kVec> vin = ld_stream(x + i, (Vec<kVec>*)nullptr);
+            float q[kVec];
+            FastGuard guard;
+            guard_reset(guard);
+#pragma unroll
+            for (int e = 0; e < kVec; ++e) {
+                guard_note(guard, vin.v[e]);
+                q[e] = elem_fast(vin.v[e], p).q;
+            }
+            if (!p.fast || guard_bad(guard)) {
+#pragma unroll
+                for (int e = 0; e < kVec; ++e) q[e] = elem_slow(vin.v[e], p).q;
+            }
+            int qi[kVec];
+            Vec<kVec> vy;
+#pragma unroll
+            for (int e = 0; e < kVec; ++e) {
+                qi[e] = code_of(q[e]);
+                if (WANT_Y) vy.v[e] = dequant(q[e], p);
+            }
+            CodePack<BITS>::store8(codes, i, qi);
+            if (WANT_Y) st_stream(y + i, vy);
+        }
     }
 }
 
@@ -396,15 +489,8 @@ extern "C" int vsiq_fake_quant_fwd(const float* x, float* y, void* codes, const 
     if (n == 0) return VSIQ_OK;
     if (!x || (!y && !codes)) return VSIQ_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (codes) {
-        if (qp->pre_op != VSIQ_PRE_NONE) return VSIQ_ERR_UNSUPPORTED;
-        if (qp->qmin < -128 || qp->qmax > 255 || (qp->qmin < 0 && qp->qmax > 127)) return VSIQ_ERR_UNSUPPORTED;
-        int64_t blocks = (n + kThreads - 1) / kThreads;
-        int grid = (int)(blocks > (1 << 20) ? (1 << 20) : blocks);
-        if (grid < 0) return -grid;
-        fq_codes_kernel<<<grid, kThreads, 0, st>>>(x, y, (int8_t*)codes, n, layout->inner, layout->channels, qpd);
-        return (int)cudaGetLastError();
-    }
+    if (codes)  // int8 (qmin < 0) / uint8 codes: the 8-bit form of vsiq_quantize_codes
+        return vsiq_quantize_codes(x, y, codes, 8, layout, qp, stream);
     const bool warp_group = layout->inner < kWarpGroupMaxInner;
     const bool vec8 = aligned32(x) && aligned32(y);
     Tiles tiles;
@@ -421,6 +507,39 @@ extern "C" int vsiq_fake_quant_fwd(const float* x, float* y, void* codes, const 
     }
     VSIQ_DISPATCH_GROUP_VEC(warp_group, vec8, CALL);
 #undef CALL
+    return (int)cudaGetLastError();
+}
+
+extern "C" int vsiq_quantize_codes(const float* x, float* y, void* codes, int code_bits, const vsiq_layout* layout,
+                                   const vsiq_qparams* qp, vsiq_stream_t stream) {
+    if (int e = check_layout(layout)) return e;
+    QPDev qpd;
+    if (int e = fill_qp(qp, &qpd)) return e;
+    if (code_bits != 4 && code_bits != 8 && code_bits != 16) return VSIQ_ERR_INVALID_ARG;
+    const int64_t n = layout->outer * layout->channels * layout->inner;
+    if (n == 0) return VSIQ_OK;
+    if (!x || !codes) return VSIQ_ERR_INVALID_ARG;
+    if (qp->pre_op != VSIQ_PRE_NONE) return VSIQ_ERR_UNSUPPORTED;
+    // the integer range must fit the code width: two's complement when qmin < 0, unsigned otherwise
+    const int64_t lo = qp->qmin < 0 ? -(int64_t(1) << (code_bits - 1)) : 0;
+    const int64_t hi = qp->qmin < 0 ? (int64_t(1) << (code_bits - 1)) - 1 : (int64_t(1) << code_bits) - 1;
+    if (qp->qmin < lo || qp->qmax > hi) return VSIQ_ERR_UNSUPPORTED;
+    if (code_bits == 4 && (layout->inner & 1)) return VSIQ_ERR_UNSUPPORTED;  // a byte must not straddle two rows
+    // 256-bit loads of x need a 32-byte aligned base; the packed stores then are aligned as well when codes (and y) are
+    const uintptr_t amask = reinterpret_cast<uintptr_t>(x) | (y ? reinterpret_cast<uintptr_t>(y) : 0);
+    if ((amask & 31u) || (reinterpret_cast<uintptr_t>(codes) & 15u)) return VSIQ_ERR_UNSUPPORTED;
+    Tiles tiles;
+    if (!make_tiles<kThreads>(layout->outer, layout->channels, layout->inner, &tiles)) return VSIQ_ERR_INVALID_ARG;
+    const int grid = launch_grid(tiles.n_tiles);
+    if (grid < 0) return -grid;
+    cudaStream_t st = (cudaStream_t)stream;
+#define C(B)                                                                                   \
+    {                                                                                          \
+        if (y) fq_codes_kernel<B, true><<<grid, kThreads, 0, st>>>(x, y, codes, tiles, qpd);    \
+        else fq_codes_kernel<B, false><<<grid, kThreads, 0, st>>>(x, y, codes, tiles, qpd);     \
+    }
+    if (code_bits == 4) C(4) else if (code_bits == 8) C(8) else C(16)
+#undef C
     return (int)cudaGetLastError();
 }
 

@@ -40,6 +40,7 @@ class MinMaxObserver(BaseObserver):
         self._host = None                            # cached host copy of the state
         self.last_stats: Optional[torch.Tensor] = None
         self.last_count = 0
+        self._on_change = None                       # set by the owning QuantizationManager (cache invalidation)
 
     # -- device state -----------------------------------------------------------------------------
     def bind_state(self, state: torch.Tensor) -> None:
@@ -112,7 +113,14 @@ class MinMaxObserver(BaseObserver):
                 raise RuntimeError("vsiquantization_b200 needs a CUDA device: there is no CPU fallback")
             self._state = ops.new_observer_state(1, torch.device("cuda"))
         self._state[:, col] = torch.as_tensor(v, dtype=torch.float64)
+        # scale / zero-point follow the extrema on every read in the reference (observers/minmax.py:67-74): recompute the
+        # cached columns now and let the owning manager drop its host copies
+        n = self._state.shape[0]
+        ops.qparams_from_minmax(self._state, torch.full((n,), int(self.num_bits), dtype=torch.int32),
+                                torch.full((n,), int(bool(self.symmetric)), dtype=torch.int32), float(self.eps))
         self._host = None
+        if self._on_change is not None:
+            self._on_change()
 
     # -- reference interface ------------------------------------------------------------------------
     def observe(self, x):

@@ -180,10 +180,56 @@ def _out_like(x: torch.Tensor, out: Optional[torch.Tensor], name: str) -> torch.
     return out
 
 
+def code_bits_for(spec: QSpec) -> int:
+    """Smallest supported code width (8 or 16 bits) that holds [qmin, qmax]; 4-bit packing is opt-in (quantize_codes)."""
+    for bits in (8, 16):
+        lo, hi = (-(1 << (bits - 1)), (1 << (bits - 1)) - 1) if spec.qmin < 0 else (0, (1 << bits) - 1)
+        if spec.qmin >= lo and spec.qmax <= hi:
+            return bits
+    raise ValueError(f"integer range [{spec.qmin}, {spec.qmax}] does not fit 16-bit codes")
+
+
+def quantize_codes(x: torch.Tensor, scale, zero_point, spec: QSpec, code_bits: Optional[int] = None, want_y: bool = True):
+    """(y or None, integer codes) in one pass: codes = clamp(rint(x/s + z), qmin, qmax)  [uniform.py:54,95 keeps them as
+    floats].  code_bits 8 / 16 -> int8 / uint8 / int16 / uint16 tensors shaped like x; 4 -> uint8 tensor with HALF the last
+    dimension, two codes per byte (element 2k in the low nibble, two's complement when qmin < 0)."""
+    if spec.pre_relu:
+        raise ValueError("code export has no fused activation")
+    x = _dense_for(x, "x", spec.ch_axis)
+    if not x.is_contiguous():
+        x = x.contiguous()  # codes are laid out in logical (row-major) order
+    if x.data_ptr() % 32:
+        x = x.clone()
+    bits = code_bits_for(spec) if code_bits is None else int(code_bits)
+    outer, C, inner = layout_of(x.shape, spec.ch_axis)
+    lay = Layout(outer, C, inner)
+    keep: list = []
+    with torch.cuda.device(x.device):
+        qp = _make_qparams(spec, scale, zero_point, max(C, 1), x.device, keep)
+        y = torch.empty_like(x) if want_y else None
+        if bits == 4:
+            if x.dim() == 0 or x.shape[-1] % 2:
+                raise ValueError("int4 packing needs an even last dimension")
+            codes = torch.empty(x.shape[:-1] + (x.shape[-1] // 2,), dtype=torch.uint8, device=x.device)
+        else:
+            signed = spec.qmin < 0
+            dt = {(8, True): torch.int8, (8, False): torch.uint8, (16, True): torch.int16, (16, False): torch.uint16}[(bits, signed)]
+            codes = torch.empty(x.shape, dtype=dt, device=x.device)
+        check(lib.vsiq_quantize_codes(x.data_ptr(), y.data_ptr() if want_y else None, codes.data_ptr(), bits,
+                                      ctypes.byref(lay), ctypes.byref(qp), _stream_ptr()), "vsiq_quantize_codes")
+        _count_launch()
+    return y, codes
+
+
 def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_codes: bool = False,
                        out: Optional[torch.Tensor] = None):
-    """y = (clamp(rint(x/s + z), qmin, qmax) - z) * s  [reference: quantizers/uniform.py:54-55,95]."""
-    if spec.ch_axis == 1 and not want_codes and ci_supported(x):
+    """y = (clamp(rint(x/s + z), qmin, qmax) - z) * s  [reference: quantizers/uniform.py:54-55,95].
+    want_codes: also the integer codes, int8 / uint8 when the range fits 8 bits, else int16 / uint16 (never wrapped)."""
+    if want_codes:
+        if out is not None:
+            raise ValueError("want_codes allocates its own outputs")
+        return quantize_codes(x, scale, zero_point, spec)
+    if spec.ch_axis == 1 and ci_supported(x):
         return ci_forward(x, None, scale, zero_point, spec, out=out)  # per-channel qparams on NHWC memory, no conversion
     x = _dense_for(x, "x", spec.ch_axis)
     outer, C, inner = layout_of(x.shape, spec.ch_axis)
@@ -192,13 +238,10 @@ def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_cod
     with torch.cuda.device(x.device):
         qp = _make_qparams(spec, scale, zero_point, max(C, 1), x.device, keep)
         y = _out_like(x, out, "out")
-        codes = None
-        if want_codes:
-            codes = torch.empty(x.shape, dtype=torch.int8 if spec.qmin < 0 else torch.uint8, device=x.device)
-        check(lib.vsiq_fake_quant_fwd(x.data_ptr(), y.data_ptr(), codes.data_ptr() if want_codes else None,
-                                      ctypes.byref(lay), ctypes.byref(qp), _stream_ptr()), "vsiq_fake_quant_fwd")
+        check(lib.vsiq_fake_quant_fwd(x.data_ptr(), y.data_ptr(), None, ctypes.byref(lay), ctypes.byref(qp), _stream_ptr()),
+              "vsiq_fake_quant_fwd")
         _count_launch()
-    return (y, codes) if want_codes else y
+    return y
 
 
 def fake_quant_backward_ste(x: torch.Tensor, g: torch.Tensor, scale, zero_point, spec: QSpec,

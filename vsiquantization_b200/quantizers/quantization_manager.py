@@ -54,6 +54,8 @@ class QuantizationManager(nn.Module):
             self.quantizer.ch_axis = ch_axis
             self.observer.ch_axis = ch_axis
         self.ch_axis = ch_axis
+        if hasattr(self.observer, "_on_change"):
+            self.observer._on_change = self._invalidate  # host code poking min_val / max_val drops the cached qparams
         self.bits_width = bits_width
         self.param_dtype = param_dtype  # the reference's learned scale is a 0-dim float64 Parameter
         self.scale = 1
@@ -103,26 +105,79 @@ class QuantizationManager(nn.Module):
         return out
 
     # ---- checkpointing --------------------------------------------------------------------------------------
+    # state_dict() must hold TENSORS only: training engines walk it blindly (ultralytics' ModelEMA tests
+    # ``v.dtype.is_floating_point`` on every entry, the reference's load_partial_checkpoint reads ``.shape``,
+    # utils/util.py:27-29, 401-405).  The extra state is therefore ONE packed float64 vector:
+    #   [magic, version, is_observer_qparam, is_learning_scale, is_quantize, calibrated, C,
+    #    scale kind, scale numel, zero_point kind, zero_point numel, calib_grad_scale kind, calib_grad_scale numel,
+    #    observer state (C x 8) ..., scale ..., zero_point ..., calib_grad_scale ...]
+    # kind: 0 absent (a learned Parameter: an ordinary state_dict entry), 1 Python int, 2 Python float, 3 0-dim tensor,
+    # 4 1-D tensor; +10 when the tensor was float32 (else float64).
+    _MAGIC, _HEADER = 20477.0, 13
+
+    @staticmethod
+    def _pack_value(v):
+        if v is None or isinstance(v, nn.Parameter):
+            return 0, []
+        if isinstance(v, torch.Tensor):
+            t = v.detach().to("cpu", torch.float64)
+            kind = (3 if t.dim() == 0 else 4) + (10 if v.dtype == torch.float32 else 0)
+            return kind, t.reshape(-1).tolist()
+        if isinstance(v, bool) or isinstance(v, int):
+            return 1, [float(v)]
+        return 2, [float(v)]
+
+    @staticmethod
+    def _unpack_value(kind: int, vals):
+        if kind == 0:
+            return None
+        if kind == 1:
+            return int(vals[0])
+        if kind == 2:
+            return float(vals[0])
+        dtype = torch.float32 if kind >= 10 else torch.float64
+        t = torch.tensor(vals, dtype=torch.float64).to(dtype)
+        return t.reshape(()) if kind % 10 == 3 else t
+
     def get_extra_state(self):
-        """Everything state_dict() would otherwise lose: mode flags, the observer's running state, fixed qparams."""
-        def host(v):
-            if isinstance(v, nn.Parameter):
-                return None  # learned qparams are ordinary state_dict entries
-            if isinstance(v, torch.Tensor):
-                return v.detach().cpu()
-            return v
+        """Everything state_dict() would otherwise lose -- mode flags, the observer's running state, fixed qparams,
+        calib_grad_scale -- as one float64 tensor (layout above)."""
         st = getattr(self.observer, "state", None)
-        return {"version": 1,
-                "flags": {"is_observer_qparam": bool(self.is_observer_qparam), "is_learning_scale": bool(self.is_learning_scale),
-                          "is_quantize": bool(self.is_quantize)},
-                "calibrated": bool(self._calibrated),
-                "observer_state": st.detach().cpu() if isinstance(st, torch.Tensor) else None,
-                "scale": host(self.__dict__.get("scale")), "zero_point": host(self.__dict__.get("zero_point")),
-                "calib_grad_scale": host(getattr(self.quantizer, "calib_grad_scale", 1))}
+        st = st.detach().to("cpu", torch.float64) if isinstance(st, torch.Tensor) else None
+        C = st.shape[0] if st is not None else 0
+        parts = [self._pack_value(self.__dict__.get("scale")), self._pack_value(self.__dict__.get("zero_point")),
+                 self._pack_value(getattr(self.quantizer, "calib_grad_scale", 1))]
+        head = [self._MAGIC, 2.0, float(bool(self.is_observer_qparam)), float(bool(self.is_learning_scale)),
+                float(bool(self.is_quantize)), float(bool(self._calibrated)), float(C)]
+        for kind, vals in parts:
+            head += [float(kind), float(len(vals))]
+        body = st.reshape(-1).tolist() if st is not None else []
+        for _, vals in parts:
+            body += vals
+        return torch.tensor(head + body, dtype=torch.float64)
+
+    def _decode_extra_state(self, t: torch.Tensor):
+        v = t.detach().to("cpu", torch.float64).reshape(-1).tolist()
+        if len(v) < self._HEADER or v[0] != self._MAGIC:
+            raise ValueError("unrecognised QuantizationManager extra state")
+        C = int(v[6])
+        kinds = [(int(v[7 + 2 * i]), int(v[8 + 2 * i])) for i in range(3)]
+        off = self._HEADER
+        st = torch.tensor(v[off:off + 8 * C], dtype=torch.float64).reshape(C, 8) if C else None
+        off += 8 * C
+        vals = []
+        for kind, n in kinds:
+            vals.append(self._unpack_value(kind, v[off:off + n]))
+            off += n
+        return {"flags": {"is_observer_qparam": bool(v[2]), "is_learning_scale": bool(v[3]), "is_quantize": bool(v[4])},
+                "calibrated": bool(v[5]), "observer_state": st, "scale": vals[0], "zero_point": vals[1],
+                "calib_grad_scale": vals[2]}
 
     def set_extra_state(self, state) -> None:
-        if not state:
+        if state is None or (isinstance(state, dict) and not state):
             return
+        if isinstance(state, torch.Tensor):
+            state = self._decode_extra_state(state)  # dicts: checkpoints written before the packed layout
         for k, v in state.get("flags", {}).items():
             setattr(self, k, v)
         st = state.get("observer_state")
@@ -215,9 +270,18 @@ class QuantizationManager(nn.Module):
         out = torch.empty(st.shape[0], dtype=self.param_dtype, device=st.device)
         self.observer.lsq_init_scale(self.bits_width, out)
         self._calibrated = False
+        if "scale" in self._parameters:
+            # already learnable (a second activate_learning_qparam / deactivate_learning_qparam): re-initialise the
+            # registered Parameter IN PLACE -- a plain attribute of the same name would shadow it, the optimizer would keep
+            # training an orphan (the reference raises TypeError here: nn.Module refuses a non-Parameter for that name)
+            p = self._parameters["scale"]
+            with torch.no_grad():
+                p.copy_(out.reshape(p.shape).to(device=p.device, dtype=p.dtype))
+            return
         self.__dict__.pop("zero_point", None)
         self.__dict__["scale"] = out.reshape(()) if out.numel() == 1 else out
-        self.__dict__["zero_point"] = self._current_zero_point()
+        if "zero_point" not in self._parameters:
+            self.__dict__["zero_point"] = self._current_zero_point()
 
     def _current_zero_point(self):
         st = self.observer.state

@@ -136,13 +136,16 @@ class UniformQuantizer(BaseQuantizer):
         spec = self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu)
         return ops.FakeQuantEpilogue.apply(x, bias, s_arg, z_arg, spec, gs_host, gs_dev)
 
-    def quantize_codes(self, x, scale, zero_point):
-        """(fake-quantised tensor, integer codes as int8/uint8) -- the reference keeps codes as floats (uniform.py:54)."""
+    def quantize_codes(self, x, scale, zero_point, code_bits: Optional[int] = None):
+        """(fake-quantised tensor, integer codes) -- the reference keeps codes as floats (uniform.py:54).  int8 / uint8
+        when the range fits 8 bits, int16 / uint16 otherwise; ``code_bits=4`` packs two codes per byte (W4 deployment)."""
         x = _as_cuda(x)
         ch_axis = self._resolve_axis(x, scale)
         zp_round = isinstance(zero_point, torch.Tensor) and not self.symmetric and zero_point.is_floating_point() \
             and zero_point.requires_grad
-        return ops.fake_quant_forward(x.detach(), scale, zero_point, self._spec(ch_axis, zp_round), want_codes=True)
+        s = scale.detach() if isinstance(scale, torch.Tensor) else scale
+        z = zero_point.detach() if isinstance(zero_point, torch.Tensor) else zero_point
+        return ops.quantize_codes(x.detach(), s, z, self._spec(ch_axis, zp_round), code_bits)
 
 
 @register_class
