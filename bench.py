@@ -389,7 +389,8 @@ def yolo_section(args, world):
            "fake_quant_frac_of_floor": fq.get("fraction_of_hbm_floor"), "fake_quant_kernels": fq.get("kernels"),
            "device_ms_per_step": fq.get("device_ms_per_step"), "fake_quant_gb_per_step": fq.get("algorithmic_gb_per_step_per_gpu"),
            "loss": r["loss"], "ms_per_step_by_rank": r.get("ms_per_step_by_rank"), "peak_mem_gb": r["peak_mem_gb"],
-           "fused_layers": r["fused_layers"], "prefetch": r["prefetch"], "weight_bank": r["weight_bank"]}
+           "fused_layers": r["fused_layers"], "prefetch": r["prefetch"], "weight_bank": r["weight_bank"],
+           "slow_paths": r.get("slow_paths")}
     if fq.get("profile_error"):
         out["profile_error"] = fq["profile_error"]
     return out

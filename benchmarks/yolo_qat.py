@@ -290,6 +290,8 @@ def run(args) -> dict:
         return float(loss.item())  # device -> host read of the step's result
 
     bucket_params = set(bucket.params) if bucket is not None else set()
+    from vsiquantization_b200 import ops as _ops
+    _ops.slow_path_counters(reset=True)  # from here on: warm-up / capture / timed steps only
     graphed = None
     if args.cuda_graph:
         # world > 1: no DDP wrapper -- the graphed step all-reduces one flat gradient buffer inside the captured graph
@@ -396,7 +398,10 @@ def run(args) -> dict:
            "h2d_bytes_per_step": args.batch * 3 * args.imgsz * args.imgsz, "d2h_bytes_per_step": 4,
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
            "h2d_ms": h2d_ms, "allreduce_ms": (sorted(ar_ms)[len(ar_ms) // 2] if ar_ms else None),
-           "allreduce_alone": ar_alone, "ms_per_step_by_rank": spread, "ms_per_step_this_rank": mine / args.steps}
+           "allreduce_alone": ar_alone, "ms_per_step_by_rank": spread, "ms_per_step_this_rank": mine / args.steps,
+           # copies / scalar instantiations the wrappers fell back to while the step was executed eagerly (warm-up, graph
+           # capture, and -- without a graph -- the timed steps): all zero means every tensor took a fast path
+           "slow_paths": _ops.slow_path_counters()}
     peak = 6531.9
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])

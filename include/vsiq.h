@@ -14,7 +14,8 @@
  *     (fp32 unless stated) owned by the caller, except in the *_host entry.
  *   - every call is asynchronous on the given stream (a cudaStream_t passed as
  *     void*), allocates nothing (scratch comes in as `workspace`), keeps no
- *     global mutable state and is re-entrant across streams and devices.
+ *     global mutable state (beyond mutex-guarded, write-once per-device caches of
+ *     device attributes and kernel attributes) and is re-entrant across streams and devices.
  *     Workspaces must not be shared by calls running concurrently on
  *     different streams.  A workspace must be zero-filled once when it is
  *     allocated; every call leaves it zero-filled where it needs it to be.
@@ -95,6 +96,15 @@ int vsiq_version(void);
 const char *vsiq_error_string(int code);
 /* SM count and compute capability of the current device (VSIQ_ERR_NO_DEVICE without one). */
 int vsiq_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* Workspaces.  The reducing entry points (observer, LSQ backward, NHWC kernels, multi-tensor backward) take a caller-owned
+ * scratch buffer.  Its first 256 bytes hold a ticket and a tile counter that must be ZERO when a call starts; every call
+ * leaves them zero when its kernels complete (zero-fill the buffer once after allocating it).  If a call is abandoned --
+ * the library returned an error, the stream was destroyed, a capture was invalidated -- clear the header before the
+ * buffer is used again: vsiq_workspace_reset enqueues that (asynchronous, 256 bytes) on `stream`.  A non-zero header
+ * makes the next launch skip work silently; the Python host side resets on every reported error and offers
+ * VSIQ_WS_PARANOID=1 (reset before every use) for debugging. */
+int vsiq_workspace_reset(void *workspace, size_t workspace_bytes, vsiq_stream_t stream);
 
 /* ---- (3) fake-quant forward ---------------------------------------------------------------
  * y = (clamp(rint(x / s + z), qmin, qmax) - z) * s
@@ -232,6 +242,16 @@ int vsiq_ci_lsq_bwd(const float *x, const float *bias, const float *g, float *dx
                     void *dzp, int dzp_dtype, float *dbias, int64_t rows, int64_t channels, const vsiq_qparams *qp,
                     int64_t qp_channels, double grad_scale_host, const float *grad_scale_dev, int64_t g_row_pitch,
                     void *workspace, size_t workspace_bytes, vsiq_stream_t stream);
+
+/* BatchNorm normalisation of a channel-innermost tensor with GIVEN moments, optionally followed by ReLU:
+ *   y = act((x - mean[c]) / sqrt(var[c] + eps) * gamma[c] + beta[c])      (computed as x * a[c] + b[c], one FMA)
+ * the second half of each layer of reestimate_BN_stats (utils/estimate_bn.py:79-91 runs the BN in training mode, i.e. with
+ * the batch mean and the BIASED batch variance; modules/fused.py:131-134 then applies the ReLU) once vsiq_ci_observe +
+ * vsiq_bn_moments_finalize have produced the moments: one read and one write instead of ATen's batch_norm and relu
+ * passes.  gamma / beta may be NULL (1 / 0).  Within 2 ulp of ATen's op order (same bar as north_star's BN tolerance). */
+int vsiq_ci_bn_normalize(const float *x, const float *mean, const float *var, const float *gamma, const float *beta,
+                         float eps, float *y, int64_t rows, int64_t channels, int relu, void *workspace,
+                         size_t workspace_bytes, vsiq_stream_t stream);
 
 /* Per-channel observer on a channel-innermost tensor [rows, channels]: the same outputs as vsiq_observe with
  * layout {outer = N, channels, inner = H*W} on the NCHW-permuted tensor (stats[c] / state[c]; min / max exact, sums to

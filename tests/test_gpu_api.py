@@ -284,8 +284,29 @@ def test_bn_reestimate_api_matches_golden():
     from vsiquantization_b200.utils.estimate_bn import _make_hook
     layer.running_mean_sum = torch.zeros(C, device="cuda")
     layer.running_var_sum = torch.zeros(C, device="cuda")
-    got = _make_hook({"sync": False, "weight": 1.0, "local_images": 1.0, "global_images": 1.0})(layer, x)
+    hook = _make_hook({"sync": False, "weight": 1.0, "local_images": 1.0, "global_images": 1.0})
+    got = hook(layer, x)
     assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+    # channels_last: normalise + ReLU as ONE pass of the vsiq_ci_bn_normalize kernel (no ATen batch_norm / relu)
+    from vsiquantization_b200 import _lib, ops
+    xw = torch.randn(6, 8, 12, 12, device="cuda").contiguous(memory_format=torch.channels_last) * 3 + 0.5
+    bn8 = torch.nn.BatchNorm2d(8, eps=0.001).cuda()
+    with torch.no_grad():
+        bn8.weight.copy_(torch.rand(8) + 0.5)
+        bn8.bias.copy_(torch.randn(8) * 0.2)
+    wide = ConvBnReLU(torch.nn.Conv2d(3, 8, 3, bias=False), bn8, torch.nn.ReLU(), "MinMaxObserver", "UniformQuantizer",
+                      "MinMaxObserver", "UniformQuantizer", True, True, False, 8, 8).cuda()
+    wide.running_mean_sum = torch.zeros(8, device="cuda")
+    wide.running_var_sum = torch.zeros(8, device="cuda")
+    n0 = _lib.launch_count
+    got_cl = hook(wide, xw, act="relu")
+    assert _lib.launch_count - n0 == 4          # NHWC observer (2 launches) + moments finalize + normalise/ReLU
+    ref_cl = torch.relu(torch.nn.functional.batch_norm(xw, None, None, bn8.weight, bn8.bias, True, 1.0, bn8.eps))
+    assert got_cl.is_contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(got_cl, ref_cl, rtol=2e-6, atol=2e-6)
+    y_plain = ops.ci_bn_normalize(xw, xw.mean((0, 2, 3)), xw.var((0, 2, 3), unbiased=False), None, None, 1e-5, relu=False)
+    ref_plain = torch.nn.functional.batch_norm(xw, None, None, None, None, True, 1.0, 1e-5)
+    assert torch.allclose(y_plain, ref_plain, rtol=2e-6, atol=2e-6)
 
 
 def test_fused_layer_variants_forward_backward():
@@ -877,3 +898,45 @@ def test_poking_observer_extrema_recomputes_the_qparams():
     s1, z1 = m.observer.get_scale_zero_point()
     assert s1 == (12.0 - -4.0) / (255 + 1e-8) and z1 == round(4.0 / (s1 + 1e-8))
     assert (m.scale, m.zero_point) == (s1, z1) and (s1, z1) != (s0, z0)
+
+
+def test_workspace_header_is_cleared_after_an_error_and_on_request():
+    """include/vsiq.h, "Workspaces": a ticket / tile counter left behind by an abandoned call makes the next reducing
+    launch skip work silently.  The host side clears the header whenever the library reports an error, and on request."""
+    from vsiquantization_b200 import _lib, ops
+    x = torch.randn(64, 32, 40, 40, device="cuda").contiguous(memory_format=torch.channels_last)
+    g = torch.randn_like(x)
+    spec = ops.QSpec(-128, 127, pre_relu=True)
+    b = torch.randn(32, device="cuda")
+    s = torch.tensor(0.02, device="cuda")
+    good = [t.clone() for t in ops.ci_backward(x, b, g, s, 0, spec, 1e-3) if t is not None]
+    ws = ops._workspace(256, x.device)
+    # a launch that never finished: non-zero ticket and tile counter
+    ws[:8] = torch.tensor([3, 0, 0, 0, 200, 0, 0, 0], dtype=torch.uint8, device="cuda")
+    with pytest.raises(_lib.VsiqError):
+        _lib.check(-1, "simulated failure")          # any reported error resets every cached workspace header
+    assert int(ws[:256].sum()) == 0 and ops.slow_path_counters()["workspace_resets"] >= 1
+    again = [t for t in ops.ci_backward(x, b, g, s, 0, spec, 1e-3) if t is not None]
+    for a, c in zip(good, again):
+        assert torch.equal(a, c)
+    ws[:8] = 9
+    assert ops.reset_workspaces() >= 1 and int(ws[:256].sum()) == 0
+    st = ops.observe(x, ch_axis=1)
+    assert torch.equal(st[:, 0], x.amin((0, 2, 3)).double()) and torch.equal(st[:, 1], x.amax((0, 2, 3)).double())
+
+
+def test_slow_path_counters_flag_layout_conversions():
+    """C % 4 != 0 (or C > 1024) per-channel activations cannot use the NHWC kernels and are converted: that detour is counted
+    so a benchmark can show it took none."""
+    from vsiquantization_b200 import ops
+    ops.slow_path_counters(reset=True)
+    x = torch.randn(2, 6, 8, 8, device="cuda").contiguous(memory_format=torch.channels_last)   # C = 6: not a multiple of 4
+    s = torch.full((6,), 0.05, device="cuda")
+    ops.fake_quant_forward(x, s, torch.zeros(6, device="cuda"), ops.QSpec(-128, 127, ch_axis=1))
+    c = ops.slow_path_counters()
+    assert c["layout_conversion_copies"] == 1 and c["layout_conversion_elements"] == x.numel()
+    y = torch.randn(2, 8, 8, 8, device="cuda").contiguous(memory_format=torch.channels_last)
+    ops.fake_quant_forward(y, torch.full((8,), 0.05, device="cuda"), torch.zeros(8, device="cuda"), ops.QSpec(-128, 127, ch_axis=1))
+    assert ops.slow_path_counters()["layout_conversion_copies"] == 1     # C = 8 walks NHWC memory in place
+    ops.fake_quant_forward(torch.randn(1001, device="cuda")[1:], 0.05, 0, ops.QSpec(-128, 127))
+    assert ops.slow_path_counters()["unaligned_scalar_launches"] == 1

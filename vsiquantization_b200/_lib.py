@@ -61,6 +61,7 @@ _SIGNATURES = {
     "vsiq_version": (c_int, []),
     "vsiq_error_string": (ctypes.c_char_p, [c_int]),
     "vsiq_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+    "vsiq_workspace_reset": (c_int, [c_void_p, c_size_t, c_void_p]),
     "vsiq_fake_quant_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Layout), ctypes.POINTER(QParams), c_void_p]),
     "vsiq_quantize_codes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(Layout), ctypes.POINTER(QParams), c_void_p]),
     "vsiq_fake_quant_bwd_ste": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(Layout), ctypes.POINTER(QParams), c_void_p]),
@@ -89,6 +90,7 @@ _SIGNATURES = {
     "vsiq_ci_lsq_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                 c_int64, c_int64, ctypes.POINTER(QParams), c_int64, c_double, c_void_p, c_int64, c_void_p,
                                 c_size_t, c_void_p]),
+    "vsiq_ci_bn_normalize": (c_int, [c_void_p] * 5 + [c_float, c_void_p, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "vsiq_ci_observe_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "vsiq_ci_observe": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_size_t,
                                 c_void_p]),
@@ -125,7 +127,17 @@ lib = _load()
 launch_count = 0
 
 
+# hook run before a library error is raised (ops.py clears the workspace headers: a failed launch must not leave a ticket
+# or tile counter behind for the next one)
+on_error = None
+
+
 def check(code: int, what: str = "") -> None:
     if code != 0:
+        if on_error is not None:
+            try:
+                on_error()
+            except Exception:
+                pass
         msg = lib.vsiq_error_string(code)
         raise VsiqError(f"{what or 'libvsiq'} failed: {msg.decode() if msg else code} (code {code})")

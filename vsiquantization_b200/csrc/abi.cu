@@ -129,6 +129,11 @@ int fill_qp(const vsiq_qparams* in, QPDev* out) {
 
 extern "C" int vsiq_version(void) { return VSIQ_VERSION; }
 
+extern "C" int vsiq_workspace_reset(void* workspace, size_t workspace_bytes, vsiq_stream_t stream) {
+    if (!workspace || workspace_bytes < vsiq::kWsHeader) return VSIQ_ERR_WORKSPACE;
+    return (int)cudaMemsetAsync(workspace, 0, vsiq::kWsHeader, (cudaStream_t)stream);
+}
+
 extern "C" const char* vsiq_error_string(int code) {
     switch (code) {
         case VSIQ_OK: return "ok";

@@ -185,6 +185,60 @@ __global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: 
     if (geo.sched == kCiDynamic) ci_leave(ws);
 }
 
+// ------------------------------------------------------------------------------ BatchNorm normalise (+ ReLU)
+// y = act(x * a[c] + b[c]),  a = gamma / sqrt(var + eps),  b = beta - mean * a: what training-mode BatchNorm computes for
+// a layer that kept its BN (is_fuse_bn=False) once the batch moments are known -- the second half of every layer of
+// reestimate_BN_stats (utils/estimate_bn.py:79-91: bn in training mode, then modules/fused.py:131-134 applies the ReLU).
+// One read and one write instead of ATen's batch_norm pass plus a separate ReLU pass.
+template <bool RELU>
+__global__ void __launch_bounds__(kThreads, 3)
+    ci_affine_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ y,
+                     CiGeom geo, void* ws) {
+    const int t = threadIdx.x;
+    const bool active = t < geo.threads;
+    const int c0 = (t % geo.groups) * kCiVec;
+    constexpr int kU = 2 * kCiUnroll;
+    __shared__ uint32_t s_tile[2];
+    CiSched sc;
+    CiRange r = ci_sched_first(geo, sc, ws, s_tile, t);
+    float a[kCiVec], b[kCiVec];
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        const int c = active ? c0 + e : 0;
+        const float g = gamma ? __ldg(gamma + c) : 1.0f;
+        a[e] = __fdiv_rn(g, __fsqrt_rn(__fadd_rn(__ldg(var + c), eps)));
+        b[e] = __fsub_rn(beta ? __ldg(beta + c) : 0.0f, __fmul_rn(__ldg(mean + c), a[e]));
+    }
+    const int64_t stride = (int64_t)geo.threads * kCiVec;
+    const int64_t dy = y - x;
+    for (;;) {
+        if (active) {
+            const float* xp = x + ((int64_t)r.s0 * geo.threads + t) * kCiVec;
+#pragma unroll 1
+            for (uint32_t s = r.s0; s < r.s1; s += kU, xp += kU * stride) {
+                Vec4 vin[kU];
+#pragma unroll
+                for (int j = 0; j < kU; ++j)
+                    if (s + j < r.s1) vin[j] = ld4(xp + j * stride);
+#pragma unroll
+                for (int j = 0; j < kU; ++j) {
+                    if (s + j >= r.s1) continue;
+                    Vec4 out;
+#pragma unroll
+                    for (int e = 0; e < kCiVec; ++e) {
+                        const float v = __fmaf_rn(vin[j].v[e], a[e], b[e]);
+                        out.v[e] = RELU ? max_nan(v, 0.0f) : v;
+                    }
+                    st4(const_cast<float*>(xp) + j * stride + dy, out);
+                }
+            }
+        }
+        if (!ci_sched_next(geo, sc, s_tile, t, r)) break;
+    }
+    if (geo.sched == kCiDynamic) ci_leave(ws);
+}
+
 // --------------------------------------------------------------------------------------------- backward
 // The element arithmetic of one vector (four channels): dx, and the LSQ terms when WANT_DS.
 template <bool BIAS, bool RELU, bool WANT_DS>
@@ -667,6 +721,26 @@ extern "C" int vsiq_ci_fake_quant_fwd(const float* x, const float* bias, float* 
     if (pcq) { if (hb) { if (relu) F(true, true, true); else F(true, true, false); } else { if (relu) F(true, false, true); else F(true, false, false); } }
     else     { if (hb) { if (relu) F(false, true, true); else F(false, true, false); } else { if (relu) F(false, false, true); else F(false, false, false); } }
 #undef F
+    return (int)cudaGetLastError();
+}
+
+extern "C" int vsiq_ci_bn_normalize(const float* x, const float* mean, const float* var, const float* gamma,
+                                    const float* beta, float eps, float* y, int64_t rows, int64_t channels, int relu,
+                                    void* workspace, size_t workspace_bytes, vsiq_stream_t stream) {
+    if (rows == 0) return VSIQ_OK;
+    if (!x || !y || !mean || !var) return VSIQ_ERR_INVALID_ARG;
+    CiGeom geo;
+    if (!make_ci_geom(rows, channels, &geo)) return VSIQ_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return VSIQ_ERR_UNSUPPORTED;
+    DeviceProps dp;
+    if (int e = get_device_props(&dp)) return e;
+    const int grid = ci_pick_grid(&geo, dp.sm_count, 3, 2 * kCiUnroll);
+    if (geo.sched == kCiDynamic && (!workspace || workspace_bytes < kWsHeader)) return VSIQ_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (relu)
+        ci_affine_kernel<true><<<grid, kThreads, 0, st>>>(x, mean, var, gamma, beta, eps, y, geo, workspace);
+    else
+        ci_affine_kernel<false><<<grid, kThreads, 0, st>>>(x, mean, var, gamma, beta, eps, y, geo, workspace);
     return (int)cudaGetLastError();
 }
 

@@ -89,6 +89,9 @@ class ConvBnReLU(_ConvBase):
         return x
 
     def run_forward_core(self, x, weights, bias):
+        if not self.is_fuse_bn and self._bn_reestimate is not None:
+            # BN re-estimation: the hook normalises with the batch moments and applies the activation in the same pass
+            return self._bn_reestimate(self, self._conv(x, weights, bias), act="relu" if self.is_relu else "silu")
         x = self._pre_activation(x, weights, bias)
         # the reference applies SiLU when relu is not an nn.ReLU -- including relu=None (ConvBn overrides this)
         return F.relu(x) if self.is_relu else F.silu(x)

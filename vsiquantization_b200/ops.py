@@ -6,6 +6,7 @@ used for device memory, streams and autograd bookkeeping only; all arithmetic ha
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple, Union
 
@@ -34,6 +35,31 @@ def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+# Slow-path bookkeeping: every time a wrapper has to COPY a tensor before the kernels can walk it (a layout conversion the
+# fast paths avoid) or hands the kernels a pointer that forces the scalar (V = 1) instantiation, a counter moves.  Benchmarks
+# read them (slow_path_counters()) to show that the measured step took none of these detours.
+_slow = {"layout_conversion_copies": 0, "layout_conversion_elements": 0, "grad_layout_copies": 0,
+         "unaligned_scalar_launches": 0, "workspace_resets": 0}
+
+
+def slow_path_counters(reset: bool = False) -> dict:
+    out = dict(_slow)
+    if reset:
+        for k in _slow:
+            _slow[k] = 0
+    return out
+
+
+def _note_conversion(t: torch.Tensor) -> None:
+    _slow["layout_conversion_copies"] += 1
+    _slow["layout_conversion_elements"] += t.numel()
+
+
+def _note_alignment(*tensors) -> None:
+    if any(t is not None and t.data_ptr() % 32 for t in tensors):
+        _slow["unaligned_scalar_launches"] += 1
+
+
 def _dense_for(t: torch.Tensor, name: str, ch_axis: Optional[int]) -> torch.Tensor:
     """CUDA fp32 tensor the kernels can walk WITHOUT a copy.
 
@@ -54,6 +80,7 @@ def _dense_for(t: torch.Tensor, name: str, ch_axis: Optional[int]) -> torch.Tens
             return t
         if t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d):
             return t
+    _note_conversion(t)  # e.g. per-channel activation quantisation of an NHWC tensor with C % 4 != 0 or C > 1024
     return t.contiguous()
 
 
@@ -67,6 +94,7 @@ def _match_layout(g: torch.Tensor, x: torch.Tensor, name: str) -> torch.Tensor:
         return g
     out = torch.empty_like(x)  # preserve_format: x's strides
     out.copy_(g)
+    _slow["grad_layout_copies"] += 1
     return out
 
 
@@ -88,16 +116,39 @@ def layout_of(shape, ch_axis: Optional[int]) -> Tuple[int, int, int]:
 
 
 _workspaces = {}
+_WS_PARANOID = os.environ.get("VSIQ_WS_PARANOID", "0") not in ("", "0")
 
 
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    """Zero-initialised scratch, one per (device, stream); kernels leave it zeroed."""
+    """Zero-initialised scratch, one per (device, stream).  The reducing kernels keep a ticket and a tile counter in its
+    256-byte header and leave both zero when they finish; a launch that never completed would leave them non-zero and
+    the NEXT launch would silently skip work, so the header is cleared again (vsiq_workspace_reset, asynchronous on the
+    stream) whenever a library call fails (`check`), on request (reset_workspaces), and -- with VSIQ_WS_PARANOID=1 -- before
+    every use (a debugging aid: one extra memset node per reducing launch)."""
     key = (device.index, _stream_ptr())
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
+    elif _WS_PARANOID:
+        lib.vsiq_workspace_reset(ws.data_ptr(), ws.numel(), _stream_ptr())
+        _slow["workspace_resets"] += 1
     return ws
+
+
+def reset_workspaces() -> int:
+    """Clear the header of every cached workspace (each on the stream it belongs to); returns how many were reset.
+    Called automatically when a library call reports an error."""
+    n = 0
+    for (dev_index, stream_ptr), ws in list(_workspaces.items()):
+        with torch.cuda.device(dev_index):
+            lib.vsiq_workspace_reset(ws.data_ptr(), ws.numel(), stream_ptr)
+        n += 1
+    _slow["workspace_resets"] += n
+    return n
+
+
+_lib.on_error = reset_workspaces
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -238,6 +289,7 @@ def fake_quant_forward(x: torch.Tensor, scale, zero_point, spec: QSpec, want_cod
     with torch.cuda.device(x.device):
         qp = _make_qparams(spec, scale, zero_point, max(C, 1), x.device, keep)
         y = _out_like(x, out, "out")
+        _note_alignment(x, y)
         check(lib.vsiq_fake_quant_fwd(x.data_ptr(), y.data_ptr(), None, ctypes.byref(lay), ctypes.byref(qp), _stream_ptr()),
               "vsiq_fake_quant_fwd")
         _count_launch()
@@ -257,6 +309,7 @@ def fake_quant_backward_ste(x: torch.Tensor, g: torch.Tensor, scale, zero_point,
     with torch.cuda.device(x.device):
         qp = _make_qparams(spec, scale, zero_point, C, x.device, keep)
         dx = _out_like(x, out, "out")
+        _note_alignment(x, g, dx)
         check(lib.vsiq_fake_quant_bwd_ste(x.data_ptr(), g.data_ptr(), dx.data_ptr(), ctypes.byref(lay),
                                           ctypes.byref(qp), _stream_ptr()), "vsiq_fake_quant_bwd_ste")
         _count_launch()
@@ -305,6 +358,7 @@ def lsq_backward(x, g, scale, zero_point, spec: QSpec, grad_scale: float, grad_s
             raise ValueError("gradient outputs must have one entry per channel")
         nbytes = lib.vsiq_lsq_bwd_workspace_bytes(ctypes.byref(lay))
         ws = _workspace(nbytes, x.device)
+        _note_alignment(x, g, dx)
         gsd = None
         if grad_scale_dev is not None:
             gsd = grad_scale_dev.detach().to(device=x.device, dtype=torch.float32).contiguous()
@@ -539,6 +593,26 @@ def bn_moments_finalize(stats: torch.Tensor, count: float, mean_sum=None, var_su
               "vsiq_bn_moments_finalize")
         _count_launch()
     return m, vb, vu
+
+
+def ci_bn_normalize(x: torch.Tensor, mean, var, gamma, beta, eps: float, relu: bool = False) -> torch.Tensor:
+    """act((x - mean) / sqrt(var + eps) * gamma + beta) on a channels_last tensor in one pass (vsiq_ci_bn_normalize):
+    training-mode BatchNorm's normalisation with known batch moments, ReLU folded in (estimate_bn.py:79-91, fused.py:131-134)."""
+    if not ci_supported(x):
+        raise ValueError("ci_bn_normalize needs a float32 CUDA channels_last tensor with C % 4 == 0 and C <= 1024")
+    N, C, H, W = x.shape
+    f = lambda t: None if t is None else t.detach().to(device=x.device, dtype=torch.float32).contiguous()  # noqa: E731
+    mean, var, gamma, beta = f(mean), f(var), f(gamma), f(beta)
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        ws = _workspace(256, x.device)
+        check(lib.vsiq_ci_bn_normalize(x.data_ptr(), mean.data_ptr(), var.data_ptr(),
+                                       gamma.data_ptr() if gamma is not None else None,
+                                       beta.data_ptr() if beta is not None else None, float(eps), y.data_ptr(),
+                                       N * H * W, C, int(bool(relu)), ws.data_ptr(), ws.numel(), _stream_ptr()),
+              "vsiq_ci_bn_normalize")
+        _count_launch()
+    return y
 
 
 def bn_reestimate_finish(mean_sum, var_sum, batch_count: int, running_mean, running_var) -> None:

@@ -42,22 +42,29 @@ def _make_hook(ctx: dict):
     """ctx carries the per-iteration facts the hook needs: ``sync`` (all-reduce the sums), ``weight`` (0.0 when this rank
     only replays a batch to keep the collectives aligned), ``local_images`` / ``global_images`` (this rank's and all
     ranks' image count of the iteration -- the global per-channel element count follows without a per-layer sync)."""
-    def hook(module: ConvBnReLU, x: torch.Tensor) -> torch.Tensor:
+    def hook(module: ConvBnReLU, x: torch.Tensor, act=None) -> torch.Tensor:
+        """Moments of this batch -> running sums; returns training-mode BN of x, with ``act`` ("relu" / "silu" / None)
+        applied (the layer hands its activation over so that normalise + ReLU are one pass on channels_last tensors)."""
         bn = module.bn
         stats = ops.observe(x, ch_axis=1)                      # [C,5]: .., sum x, sum x^2  -- one read of x
         count = float(x.numel() // x.shape[1])
         if ctx["sync"]:
-            sums = stats[:, 2:].contiguous()  # NCCL wants a dense buffer
             if ctx["weight"] != 1.0:
-                sums.mul_(ctx["weight"])
-            torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM)
-            stats[:, 2:] = sums
+                stats.mul_(ctx["weight"])
+            # the whole [C,5] block in place, one collective and no staging copies (the min / max columns come back as
+            # sums and are not used by the moments)
+            torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.SUM)
             count = count / ctx["local_images"] * ctx["global_images"]  # ranks may hold different batch sizes
         mean, var_b, _ = ops.bn_moments_finalize(stats, count, module.running_mean_sum, module.running_var_sum)
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         # training-mode BN normalises with the batch mean and the BIASED batch variance
-        return F.batch_norm(x, mean, var_b, bn.weight, bn.bias, False, 0.0, bn.eps)
+        if act in (None, "relu") and ops.ci_supported(x):
+            return ops.ci_bn_normalize(x, mean, var_b, bn.weight, bn.bias, bn.eps, relu=act == "relu")
+        y = F.batch_norm(x, mean, var_b, bn.weight, bn.bias, False, 0.0, bn.eps)
+        if act == "relu":
+            return F.relu(y)
+        return F.silu(y) if act == "silu" else y
     return hook
 
 
