@@ -57,7 +57,13 @@ enum { VSIQ_F32 = 0, VSIQ_F64 = 1 };
 
 /* activation fused in front of the quantiser (fwd, STE bwd, LSQ bwd): the fused layer's F.relu (modules/fused.py:133)
  * followed by quantize_activation (quantizers/fake_quantize.py:49-50) becomes one pass over the conv output */
-enum { VSIQ_PRE_NONE = 0, VSIQ_PRE_RELU = 1 };
+enum {
+    VSIQ_PRE_NONE = 0,
+    VSIQ_PRE_RELU = 1,
+    /* SiLU, x / (1 + exp(-x)) and its derivative in ATen-CUDA's operation order: the channel-innermost entry points only
+     * (vsiq_ci_fake_quant_fwd / vsiq_ci_lsq_bwd); everything else returns VSIQ_ERR_UNSUPPORTED for it. */
+    VSIQ_PRE_SILU = 2
+};
 
 /* mask semantics of the LSQ backward */
 enum {
@@ -88,7 +94,7 @@ typedef struct vsiq_qparams {
     int32_t zp_learned;
     int32_t qmin;
     int32_t qmax;
-    int32_t pre_op; /* VSIQ_PRE_NONE, or VSIQ_PRE_RELU: quantise relu(x) and apply relu's backward mask [x > 0] too */
+    int32_t pre_op; /* VSIQ_PRE_NONE, or VSIQ_PRE_RELU / VSIQ_PRE_SILU: quantise act(x) and chain act's derivative in the backward */
 } vsiq_qparams;
 
 /* ---- library ---------------------------------------------------------------------------- */

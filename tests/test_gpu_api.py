@@ -940,3 +940,62 @@ def test_slow_path_counters_flag_layout_conversions():
     assert ops.slow_path_counters()["layout_conversion_copies"] == 1     # C = 8 walks NHWC memory in place
     ops.fake_quant_forward(torch.randn(1001, device="cuda")[1:], 0.05, 0, ops.QSpec(-128, 127))
     assert ops.slow_path_counters()["unaligned_scalar_launches"] == 1
+
+
+@pytest.mark.parametrize("learn", [False, True], ids=["fixed", "lsq"])
+def test_fused_silu_epilogue_matches_aten_silu_then_quant(learn, monkeypatch):
+    """ConvBnReLU built with nn.SiLU (the reference applies F.silu whenever ``relu`` is not an nn.ReLU, fused.py:81,133):
+    on channels_last the bias add, SiLU and the output quantiser run as ONE kernel pass each way.  The bar is the same
+    GPU's ATen composition F.silu(conv + b) -> quantiser: bit-identical forward (x / (1 + exp(-x)) with the same exp and
+    division), gradients to 1e-6 of their scale (ATen's silu_backward contracts its multiply-adds at nvcc's discretion).
+    torch-CPU's vectorised exp differs in the last bits, so against CPU results SiLU layers agree to exp rounding only."""
+    from vsiquantization_b200 import _lib
+    from vsiquantization_b200.modules.fused import ConvBnReLU
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    torch.manual_seed(5)
+    cv, bn = torch.nn.Conv2d(8, 16, 3, padding=1, bias=False), torch.nn.BatchNorm2d(16)
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.1)
+        bn.running_var.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.2)
+    layer = ConvBnReLU(cv, bn, torch.nn.SiLU(), "LSQObserver", "LSQQuantizer", "LSQObserver", "LSQQuantizer", True, False,
+                       True, 8, 8).cuda().to(memory_format=torch.channels_last)
+    assert layer.is_relu is False and layer._has_act
+    x = torch.randn(4, 8, 20, 20, device="cuda").contiguous(memory_format=torch.channels_last)
+    from vsiquantization_b200.utils.quantize_manager import activate_learning_qparam, activate_quantizer, calibrate_qat_model
+    calibrate_qat_model(layer, [x], lambda m, loader, dev: [m(b) for b in loader])
+    if learn:
+        activate_learning_qparam(layer, use_init=True)
+    else:
+        for q in (layer.weight_quantizer, layer.activation_quantizer):
+            q.is_learning_scale = False
+            q.is_observer_qparam = False
+    activate_quantizer(layer)
+    layer.train()
+
+    def run(fused):
+        layer.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        n0 = _lib.launch_count
+        if fused:
+            y = layer(xi)
+        else:  # the same arithmetic spelled out with ATen's silu between the conv and the quantiser
+            w, b = layer.get_weight_bias()
+            pre = layer._conv(xi, layer.quantize_weights(w), None) + b.view(1, -1, 1, 1)
+            y = layer.quantize_activation(torch.nn.functional.silu(pre))
+        launches = _lib.launch_count - n0
+        (y * torch.linspace(-1, 1, y.numel(), device="cuda").view_as(y)).sum().backward()
+        grads = {n: p.grad.detach().clone() for n, p in layer.named_parameters() if p.grad is not None}
+        return y.detach(), xi.grad.detach(), grads, launches
+
+    y1, dx1, g1, n1 = run(True)
+    y0, dx0, g0, n0 = run(False)
+    assert n1 == 2 and n0 == 2          # weight quantiser + ONE epilogue launch (vs weight + activation quantiser after ATen's silu)
+    assert torch.equal(y1, y0), "fused SiLU epilogue differs from F.silu -> quantiser"
+    scale = float(dx0.abs().max())
+    assert float((dx1 - dx0).abs().max()) <= 1e-6 * scale
+    assert set(g1) == set(g0)
+    for n in g0:
+        tol = 2e-5 if n.endswith(("scale", "zero_point", "bias")) else 1e-6
+        assert float((g1[n].double() - g0[n].double()).abs().max()) <= tol * float(g0[n].abs().max() + 1e-12), n

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("VSIQ_LIB") or os.path.join(_HERE, "libvsiq.so")  # VS
 
 F32, F64 = 0, 1
 MASK_ROUNDED, MASK_FUNLSQ = 0, 1
-PRE_NONE, PRE_RELU = 0, 1
+PRE_NONE, PRE_RELU, PRE_SILU = 0, 1, 2
 STATS_WIDTH, STATE_WIDTH = 5, 8
 
 c_void_p, c_int, c_int64, c_float, c_double, c_size_t = (

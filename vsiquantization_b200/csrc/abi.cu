@@ -102,7 +102,7 @@ int check_layout(const vsiq_layout* l) {
 int fill_qp(const vsiq_qparams* in, QPDev* out) {
     if (!in) return VSIQ_ERR_INVALID_ARG;
     if (in->qmin >= in->qmax) return VSIQ_ERR_INVALID_ARG;
-    if (in->pre_op != VSIQ_PRE_NONE && in->pre_op != VSIQ_PRE_RELU) return VSIQ_ERR_INVALID_ARG;
+    if (in->pre_op != VSIQ_PRE_NONE && in->pre_op != VSIQ_PRE_RELU && in->pre_op != VSIQ_PRE_SILU) return VSIQ_ERR_INVALID_ARG;
     if ((in->scale_dtype != VSIQ_F32 && in->scale_dtype != VSIQ_F64) ||
         (in->zp_dtype != VSIQ_F32 && in->zp_dtype != VSIQ_F64))
         return VSIQ_ERR_INVALID_ARG;

@@ -124,7 +124,7 @@ __device__ __forceinline__ void ci_leave(void* ws) {
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-template <bool PCQ, bool BIAS, bool RELU>
+template <bool PCQ, bool BIAS, int ACT>
 __global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: measured 5.84 -> 6.39 TB/s on [64,32,320,320]
     ci_fwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y, CiGeom geo,
                   QPDev qpd, void* ws) {
@@ -163,16 +163,14 @@ __global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: 
                     guard_reset(guard);
 #pragma unroll
                     for (int e = 0; e < kCiVec; ++e) {
-                        float xe = BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e];
-                        if (RELU) xe = max_nan(xe, 0.0f);
+                        const float xe = act_fwd<ACT>(BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e]);
                         guard_note(guard, xe);
                         out.v[e] = dequant(elem_fast(xe, p[e]).q, p[e]);
                     }
                     if (!all_fast || guard_bad(guard)) {
 #pragma unroll
                         for (int e = 0; e < kCiVec; ++e) {
-                            float xe = BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e];
-                            if (RELU) xe = max_nan(xe, 0.0f);
+                            const float xe = act_fwd<ACT>(BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e]);
                             out.v[e] = dequant(elem_slow(xe, p[e]).q, p[e]);
                         }
                     }
@@ -241,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 
 // --------------------------------------------------------------------------------------------- backward
 // The element arithmetic of one vector (four channels): dx, and the LSQ terms when WANT_DS.
-template <bool BIAS, bool RELU, bool WANT_DS>
+template <bool BIAS, int ACT, bool WANT_DS>
 __device__ __forceinline__ void ci_bwd_vec(const Vec4& vx, const Vec4& vg, const QP (&p)[kCiVec], const float (&bv)[kCiVec],
                                            bool all_fast, Vec4& out, float (&te)[kCiVec], float (&tb)[kCiVec],
                                            float (&tdb)[kCiVec]) {
@@ -251,14 +249,12 @@ __device__ __forceinline__ void ci_bwd_vec(const Vec4& vx, const Vec4& vg, const
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
         const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
-        const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+        const float xe = act_fwd<ACT>(xb);
         const float ge = vg.v[e];
         guard_note(guard, xe);
         guard_note(guard, ge);
         const Elem el = elem_fast(xe, p[e]);
-        float d = dx_fast(ge, el.m, p[e]);
-        if (RELU) d = xb > 0.0f ? d : 0.0f;
-        out.v[e] = d;
+        out.v[e] = act_bwd<ACT>(xb, dx_fast(ge, el.m, p[e]));
         if (WANT_DS) {
             const float dd = __fsub_rn(el.q, p[e].z);
             const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
@@ -270,12 +266,10 @@ __device__ __forceinline__ void ci_bwd_vec(const Vec4& vx, const Vec4& vg, const
 #pragma unroll
         for (int e = 0; e < kCiVec; ++e) {
             const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
-            const float xe = RELU ? max_nan(xb, 0.0f) : xb;
+            const float xe = act_fwd<ACT>(xb);
             const float ge = vg.v[e];
             const Elem el = elem_slow(xe, p[e]);
-            float d = dx_slow(ge, el.m, p[e]);
-            if (RELU) d = xb > 0.0f ? d : 0.0f;
-            out.v[e] = d;
+            out.v[e] = act_bwd<ACT>(xb, dx_slow(ge, el.m, p[e]));
             if (WANT_DS) {
                 const float dd = __fsub_rn(el.q, p[e].z);
                 const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
@@ -388,7 +382,7 @@ __device__ __forceinline__ void ci_bwd_flush(const double (&acc_e)[kCiVec], cons
 
 // Direct-load backward: used when grad_output is pitched (a channel slice of a wider NHWC tensor, which is what the
 // backward of torch.cat hands out: row r of g starts at g + r * g_pitch) or when VSIQ_CI_TMA=0.
-template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
+template <bool PCQ, bool BIAS, int ACT, bool WANT_DS>
 __global__ void __launch_bounds__(kThreads, 2)
     ci_bwd_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ g,
                   float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket, int64_t g_pitch) {
@@ -440,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                 for (int j = 0; j < kCiUnroll; ++j) {
                     if (s + j >= r.s1) continue;
                     Vec4 out;
-                    ci_bwd_vec<BIAS, RELU, WANT_DS>(vx[j], vg[j], p, bv, all_fast, out, te, tb, tdb);
+                    ci_bwd_vec<BIAS, ACT, WANT_DS>(vx[j], vg[j], p, bv, all_fast, out, te, tb, tdb);
                     st4(const_cast<float*>(xp) + j * stride + ddx, out);
                 }
                 if ((++it & (kCiBatches - 1)) == 0 || s + kCiUnroll >= r.s1) {
@@ -517,7 +511,7 @@ struct CiRing {
     int64_t vec0[kCiStages];   // its first vector
 };
 
-template <bool PCQ, bool BIAS, bool RELU, bool WANT_DS>
+template <bool PCQ, bool BIAS, int ACT, bool WANT_DS>
 __global__ void __launch_bounds__(kThreads + 32, 2)
     ci_bwd_tma_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ g,
                       float* __restrict__ dx, CiGeom geo, QPDev qpd, void* ws, CiOut o, int use_ticket, int64_t g_pitch) {
@@ -638,7 +632,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2)
                 const Vec4 vx = lds4(xs + (size_t)u * kCiVec);
                 const Vec4 vg = lds4(gs + (size_t)u * kCiVec);
                 Vec4 out;
-                ci_bwd_vec<BIAS, RELU, WANT_DS>(vx, vg, p, bv, all_fast, out, te, tb, tdb);
+                ci_bwd_vec<BIAS, ACT, WANT_DS>(vx, vg, p, bv, all_fast, out, te, tb, tdb);
                 st4(dx + (v0 + u) * kCiVec, out);
             }
         }
@@ -716,10 +710,12 @@ extern "C" int vsiq_ci_fake_quant_fwd(const float* x, const float* bias, float* 
     const int grid = ci_pick_grid(&geo, dp.sm_count, 3, 2 * kCiUnroll);
     if (geo.sched == kCiDynamic && (!workspace || workspace_bytes < kWsHeader)) return VSIQ_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool pcq = qp_channels == channels && channels > 1, relu = qp->pre_op == VSIQ_PRE_RELU, hb = bias != nullptr;
-#define F(P, B, R) ci_fwd_kernel<P, B, R><<<grid, kThreads, 0, st>>>(x, bias, y, geo, qpd, workspace)
-    if (pcq) { if (hb) { if (relu) F(true, true, true); else F(true, true, false); } else { if (relu) F(true, false, true); else F(true, false, false); } }
-    else     { if (hb) { if (relu) F(false, true, true); else F(false, true, false); } else { if (relu) F(false, false, true); else F(false, false, false); } }
+    const bool pcq = qp_channels == channels && channels > 1, hb = bias != nullptr;
+    const int act = qp->pre_op;  // VSIQ_PRE_* == kAct*
+#define F(P, B, A) ci_fwd_kernel<P, B, A><<<grid, kThreads, 0, st>>>(x, bias, y, geo, qpd, workspace)
+#define F2(P, B) { if (act == kActRelu) F(P, B, kActRelu); else if (act == kActSilu) F(P, B, kActSilu); else F(P, B, kActNone); }
+    if (pcq) { if (hb) F2(true, true) else F2(true, false) } else { if (hb) F2(false, true) else F2(false, false) }
+#undef F2
 #undef F
     return (int)cudaGetLastError();
 }
@@ -773,7 +769,8 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
     DeviceProps dp;
     if (int e = get_device_props(&dp)) return e;
     const int grid = ci_pick_grid(&geo, dp.sm_count, 2, kCiUnroll);
-    const bool pcq = qp_channels == channels && channels > 1, relu = qp->pre_op == VSIQ_PRE_RELU, hb = bias != nullptr;
+    const bool pcq = qp_channels == channels && channels > 1, hb = bias != nullptr;
+    const int act = qp->pre_op;  // VSIQ_PRE_* == kAct*
     const bool want_ds = dscale != nullptr;
     CiOut o;
     o.dscale = dscale;
@@ -807,7 +804,7 @@ extern "C" int vsiq_ci_lsq_bwd(const float* x, const float* bias, const float* g
         }                                                                                                                  \
     }
 #define B3(P, H, R) { if (want_ds) B(P, H, R, true) else B(P, H, R, false) }
-#define B2(P, H) { if (relu) B3(P, H, true) else B3(P, H, false) }
+#define B2(P, H) { if (act == kActRelu) B3(P, H, kActRelu) else if (act == kActSilu) B3(P, H, kActSilu) else B3(P, H, kActNone) }
     if (pcq) { if (hb) B2(true, true) else B2(true, false) } else { if (hb) B2(false, true) else B2(false, false) }
 #undef B2
 #undef B3

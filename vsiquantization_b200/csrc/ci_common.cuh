@@ -130,6 +130,28 @@ __device__ __forceinline__ bool ci_sched_next(const CiGeom& geo, CiSched& sc, ui
     return true;
 }
 
+// Activation fused in front of the quantiser (the fused layer's F.relu / F.silu, modules/fused.py:133).  SiLU follows
+// ATen's CUDA kernels operation by operation (ActivationSiluKernel.cu: x / (1 + exp(-x)); backward
+// dy * s * (1 + x * (1 - s)) with s = 1 / (1 + exp(-x)), the inner multiply-add contracted as nvcc does), so the fused
+// epilogue reproduces F.silu followed by the quantiser ON THE SAME GPU; torch-CPU's vectorised exp differs in the last
+// bits, so against the reference's CPU results SiLU layers agree to rounding of exp, not bit for bit.
+enum { kActNone = 0, kActRelu = 1, kActSilu = 2 };
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float x) {
+    if (ACT == kActRelu) return max_nan(x, 0.0f);
+    if (ACT == kActSilu) return __fdiv_rn(x, __fadd_rn(1.0f, expf(-x)));
+    return x;
+}
+template <int ACT>
+__device__ __forceinline__ float act_bwd(float x, float d) {
+    if (ACT == kActRelu) return x > 0.0f ? d : 0.0f;
+    if (ACT == kActSilu) {
+        const float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+        return __fmul_rn(__fmul_rn(d, s), __fmaf_rn(x, __fsub_rn(1.0f, s), 1.0f));
+    }
+    return d;
+}
+
 struct Vec4 {
     float v[4];
 };

@@ -489,6 +489,7 @@ extern "C" int vsiq_fake_quant_fwd(const float* x, float* y, void* codes, const 
     if (n == 0) return VSIQ_OK;
     if (!x || (!y && !codes)) return VSIQ_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (qp->pre_op == VSIQ_PRE_SILU) return VSIQ_ERR_UNSUPPORTED;  // SiLU: channel-innermost entry points only
     if (codes)  // int8 (qmin < 0) / uint8 codes: the 8-bit form of vsiq_quantize_codes
         return vsiq_quantize_codes(x, y, codes, 8, layout, qp, stream);
     const bool warp_group = layout->inner < kWarpGroupMaxInner;
@@ -548,6 +549,7 @@ extern "C" int vsiq_fake_quant_bwd_ste(const float* x, const float* g, float* dx
     if (int e = check_layout(layout)) return e;
     QPDev qpd;
     if (int e = fill_qp(qp, &qpd)) return e;
+    if (qp->pre_op == VSIQ_PRE_SILU) return VSIQ_ERR_UNSUPPORTED;
     if (layout->outer * layout->channels * layout->inner == 0) return VSIQ_OK;
     if (!x || !g || !dx) return VSIQ_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -619,6 +621,7 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
         return VSIQ_ERR_INVALID_ARG;
     QPDev qpd;
     if (int e = fill_qp(qp, &qpd)) return e;
+    if (qp->pre_op == VSIQ_PRE_SILU) return VSIQ_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < vsiq_lsq_bwd_workspace_bytes(layout)) return VSIQ_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (layout->outer * layout->channels * layout->inner == 0) {

@@ -97,10 +97,14 @@ class ConvBnReLU(_ConvBase):
         return F.relu(x) if self.is_relu else F.silu(x)
 
     def forward(self, x):
-        """fake_quantize.py:43-51 with the ReLU folded into the output quantiser when that is possible."""
-        if not (self.fuse_relu_into_quant and self.is_relu and self._has_act and self.quantize_out
+        """fake_quantize.py:43-51 with the activation folded into the output quantiser when that is possible: ReLU in
+        every layout, SiLU (what the reference applies whenever ``relu`` is not an nn.ReLU, fused.py:81,133) on
+        channels_last tensors."""
+        act = "relu" if self.is_relu else "silu"
+        if not (self.fuse_relu_into_quant and self._has_act and self.quantize_out
                 and type(self).run_forward_core is ConvBnReLU.run_forward_core
-                and self.activation_quantizer.can_fuse_relu()):
+                and self.activation_quantizer.can_fuse_relu()
+                and not (self._bn_reestimate is not None and not self.is_fuse_bn)):
             return super().forward(x)
         if self.quantize_inp:
             x = self.quantize_activation(x)
@@ -110,9 +114,9 @@ class ConvBnReLU(_ConvBase):
                 and x.is_contiguous(memory_format=torch.channels_last)):
             pre = self._conv(x, weights, None)  # bias-free conv; the epilogue adds the bias and returns its gradient
             if ops.ci_supported(pre):
-                return self.activation_quantizer.quantize(pre, pre_relu=True, bias=bias)
-            return self.activation_quantizer.quantize(pre + bias.view(1, -1, 1, 1), pre_relu=True)
-        return self.activation_quantizer.quantize(self._pre_activation(x, weights, bias), pre_relu=True)
+                return self.activation_quantizer.quantize(pre, pre_act=act, bias=bias)
+            return self.activation_quantizer.quantize(pre + bias.view(1, -1, 1, 1), pre_act=act)
+        return self.activation_quantizer.quantize(self._pre_activation(x, weights, bias), pre_act=act)
 
 
 class ConvBn(ConvBnReLU):

@@ -168,13 +168,14 @@ class QSpec:
     zp_learned: bool = False
     mask_mode: int = _lib.MASK_ROUNDED
     pre_relu: bool = False  # quantise relu(x); the backward also applies relu's mask (one pass instead of two)
+    pre_silu: bool = False  # quantise silu(x) (ATen-CUDA's op order); channels_last tensors only (ci_forward / ci_backward)
 
 
 def _make_qparams(spec: QSpec, scale, zero_point, channels: int, device: torch.device, keep: list) -> QParams:
     qp = QParams()
     qp.qmin, qp.qmax = int(spec.qmin), int(spec.qmax)
     qp.zp_learned = 1 if spec.zp_learned else 0
-    qp.pre_op = _lib.PRE_RELU if spec.pre_relu else _lib.PRE_NONE
+    qp.pre_op = _lib.PRE_SILU if spec.pre_silu else (_lib.PRE_RELU if spec.pre_relu else _lib.PRE_NONE)
     qp.scale_dtype = qp.zp_dtype = F32
     if isinstance(scale, torch.Tensor):
         s = scale.detach()
@@ -244,7 +245,7 @@ def quantize_codes(x: torch.Tensor, scale, zero_point, spec: QSpec, code_bits: O
     """(y or None, integer codes) in one pass: codes = clamp(rint(x/s + z), qmin, qmax)  [uniform.py:54,95 keeps them as
     floats].  code_bits 8 / 16 -> int8 / uint8 / int16 / uint16 tensors shaped like x; 4 -> uint8 tensor with HALF the last
     dimension, two codes per byte (element 2k in the low nibble, two's complement when qmin < 0)."""
-    if spec.pre_relu:
+    if spec.pre_relu or spec.pre_silu:
         raise ValueError("code export has no fused activation")
     x = _dense_for(x, "x", spec.ch_axis)
     if not x.is_contiguous():
@@ -735,22 +736,25 @@ class FakeQuantEpilogue(torch.autograd.Function):
         ctx.zp_is_tensor = isinstance(zero_point, torch.Tensor)
         ctx.scale_const = None if ctx.scale_is_tensor else scale
         ctx.zp_const = None if ctx.zp_is_tensor else zero_point
-        saved = [x, bias] + ([scale] if ctx.scale_is_tensor else []) + ([zero_point] if ctx.zp_is_tensor else [])
+        ctx.has_bias = bias is not None
+        saved = [x] + ([bias] if ctx.has_bias else []) + ([scale] if ctx.scale_is_tensor else []) + \
+            ([zero_point] if ctx.zp_is_tensor else [])
         ctx.save_for_backward(*saved)
         return ci_forward(x, bias, scale, zero_point, spec)
 
     @staticmethod
     def backward(ctx, g):
         saved = list(ctx.saved_tensors)
-        x, bias = saved[0], saved[1]
-        k = 2
+        x = saved[0]
+        bias = saved[1] if ctx.has_bias else None
+        k = 2 if ctx.has_bias else 1
         scale = saved[k] if ctx.scale_is_tensor else ctx.scale_const
         k += 1 if ctx.scale_is_tensor else 0
         zp = saved[k] if ctx.zp_is_tensor else ctx.zp_const
         want_ds = ctx.scale_is_tensor and ctx.needs_input_grad[2]
         want_dz = want_ds and ctx.zp_is_tensor and ctx.needs_input_grad[3]
         dx, ds, dz, db = ci_backward(x, bias, g, scale, zp, ctx.spec, ctx.grad_scale, ctx.grad_scale_dev, want_ds, want_dz,
-                                     ctx.needs_input_grad[1], scale.dtype if ctx.scale_is_tensor else torch.float32,
+                                     ctx.has_bias and ctx.needs_input_grad[1], scale.dtype if ctx.scale_is_tensor else torch.float32,
                                      zp.dtype if ctx.zp_is_tensor else torch.float32)
         ds = ds.view(scale.shape).to(scale.device) if want_ds else None
         dz = dz.view(zp.shape).to(zp.device) if want_dz else None

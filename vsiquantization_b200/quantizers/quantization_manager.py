@@ -227,22 +227,34 @@ class QuantizationManager(nn.Module):
         collecting = (not self.is_learning_scale) and self.is_observer_qparam
         return bool(self.is_quantize and not collecting and getattr(self.quantizer, "supports_pre_relu", False))
 
-    def quantize(self, x, pre_relu: bool = False, bias=None):
-        """collect (if calibrating) then fake-quantise (if enabled) -- :73-90.  ``pre_relu``: x is the pre-activation
-        and relu is applied here -- fused into the quantiser kernels when quantising, as a plain F.relu otherwise.
-        ``bias`` (with pre_relu, channels_last x): the conv bias is added in the same pass and its gradient comes out of
-        the backward kernel."""
+    def can_fuse_act(self, act, x=None) -> bool:
+        """Same question for either activation: "relu" everywhere, "silu" on tensors the NHWC kernels can walk."""
+        if act == "relu":
+            return self.can_fuse_relu()
+        if act == "silu":
+            from .. import ops
+            return bool(self.can_fuse_relu() and getattr(self.quantizer, "supports_pre_silu", False)
+                        and x is not None and ops.ci_supported(x))
+        return False
+
+    def quantize(self, x, pre_relu: bool = False, bias=None, pre_act=None):
+        """collect (if calibrating) then fake-quantise (if enabled) -- :73-90.  ``pre_act`` ("relu" / "silu"; ``pre_relu``
+        is the older spelling of "relu"): x is the pre-activation and the activation is applied here -- fused into the
+        quantiser kernels when quantising, as a plain F.relu / F.silu otherwise.  ``bias`` (with an activation,
+        channels_last x): the conv bias is added in the same pass and its gradient comes out of the backward kernel."""
+        act = pre_act or ("relu" if pre_relu else None)
         banked = self.__dict__.get("_banked")
         if banked is not None:  # bank.WeightBank already fake-quantised this weight in its multi-tensor launch
             self.__dict__["_banked"] = None
-            if banked[0] is x and not pre_relu:
+            if banked[0] is x and act is None:
                 return banked[1]
-        if pre_relu:
-            if not self.can_fuse_relu():
+        if act is not None:
+            if not self.can_fuse_act(act, x):
                 if bias is not None:
                     x = x + bias.view(1, -1, 1, 1)
-                return self.quantize(torch.nn.functional.relu(x))
-            kw = {"pre_relu": True}
+                fn = torch.nn.functional.relu if act == "relu" else torch.nn.functional.silu
+                return self.quantize(fn(x))
+            kw = {"pre_act": act}
             if bias is not None:
                 kw["bias"] = bias
             if "scale" in self._parameters or "zero_point" in self._parameters or not self._calibrated \

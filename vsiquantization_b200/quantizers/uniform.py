@@ -66,14 +66,15 @@ class UniformQuantizer(BaseQuantizer):
         raise ValueError("per-channel scale: set quantizer.ch_axis or pass a broadcast-shaped scale")
 
     supports_pre_relu = True  # quantize(..., pre_relu=True) fuses the preceding ReLU into the kernels
+    supports_pre_silu = True  # quantize(..., pre_act="silu") fuses SiLU on channels_last tensors (ops.ci_supported)
 
-    def _spec(self, ch_axis, zp_learned=False, pre_relu=False) -> ops.QSpec:
+    def _spec(self, ch_axis, zp_learned=False, pre_relu=False, pre_silu=False) -> ops.QSpec:
         mode = _lib.MASK_FUNLSQ if self.mask_mode == "funlsq" else _lib.MASK_ROUNDED
         return ops.QSpec(self.qmin, self.qmax, ch_axis=ch_axis, zp_learned=zp_learned, mask_mode=mode,
-                         pre_relu=pre_relu)
+                         pre_relu=pre_relu, pre_silu=pre_silu)
 
     # -- the plugin entry point ------------------------------------------------------------------------
-    def quantize(self, x, scale, zero_point, is_learning_scale=False, pre_relu=False, bias=None):
+    def quantize(self, x, scale, zero_point, is_learning_scale=False, pre_relu=False, bias=None, pre_act=None):
         """Fake-quantise x (uniform.py:34-56); with ``pre_relu`` quantise relu(x) in the same pass (the fused layer's
         F.relu, modules/fused.py:133, folded into the kernel; gradients include relu's mask).
 
@@ -81,12 +82,18 @@ class UniformQuantizer(BaseQuantizer):
         0-dim fp64, on any device).  zero_point: Python int, or a float tensor / nn.Parameter (learnable: the forward
         uses clamp(round(z)), uniform.py:98-102).  The result is autograd-connected to x and to every qparam that
         requires grad."""
+        if pre_act not in (None, "relu", "silu"):
+            raise ValueError("pre_act must be None, 'relu' or 'silu'")
+        pre_relu = bool(pre_relu) or pre_act == "relu"
+        pre_silu = pre_act == "silu"
         if not x.is_cuda:
-            y = self.quantize(_as_cuda(x), scale, zero_point, is_learning_scale, pre_relu, bias)
+            y = self.quantize(_as_cuda(x), scale, zero_point, is_learning_scale, pre_relu, bias, "silu" if pre_silu else None)
             return y.to(x.device)
         ch_axis = self._resolve_axis(x, scale)
-        if bias is not None:
-            return self._quantize_epilogue(x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis)
+        if bias is not None or pre_silu:
+            # SiLU (x / (1 + exp(-x)), the fused layer's F.silu of modules/fused.py:133) exists in the channels_last
+            # epilogue kernels only
+            return self._quantize_epilogue(x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis, pre_silu)
         scale_learn = isinstance(scale, torch.Tensor) and scale.requires_grad and torch.is_grad_enabled()
         zp_tensor = isinstance(zero_point, torch.Tensor)
         # the reference rounds / clamps a tensor zero-point only on the asymmetric learning path (uniform.py:50-52)
@@ -112,10 +119,10 @@ class UniformQuantizer(BaseQuantizer):
         return ops.FakeQuantLearned.apply(x, scale, zp_arg, self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu),
                                           gs_host, gs_dev)
 
-    def _quantize_epilogue(self, x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis):
+    def _quantize_epilogue(self, x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis, pre_silu=False):
         """fq(act(x + bias)) on a channels_last conv output (ops.FakeQuantEpilogue); bias gradient from the same pass."""
         if not ops.ci_supported(x):
-            raise ValueError("bias fusion needs a channels_last float32 CUDA tensor with C % 4 == 0 and C <= 1024")
+            raise ValueError("bias / SiLU fusion needs a channels_last float32 CUDA tensor with C % 4 == 0 and C <= 1024")
         if self.mask_mode == "funlsq":
             raise ValueError("mask_mode='funlsq' has no fused-bias form")
         zp_tensor = isinstance(zero_point, torch.Tensor)
@@ -133,7 +140,7 @@ class UniformQuantizer(BaseQuantizer):
                 gs_host *= float(cgs)
         s_arg = scale if scale_learn else (scale.detach() if isinstance(scale, torch.Tensor) else scale)
         z_arg = zero_point if zp_learn else (zero_point.detach() if zp_tensor else zero_point)
-        spec = self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu)
+        spec = self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu, pre_silu=pre_silu)
         return ops.FakeQuantEpilogue.apply(x, bias, s_arg, z_arg, spec, gs_host, gs_dev)
 
     def quantize_codes(self, x, scale, zero_point, code_bits: Optional[int] = None):
