@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: 
         all_fast = all_fast && p[e].fast;
         bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
     }
+    const uint32_t seed = guard_seed(all_fast);
     const int64_t stride = (int64_t)geo.threads * kCiVec;  // floats between a thread's consecutive vectors
     const int64_t dy = y - x;
     for (;;) {
@@ -160,14 +161,14 @@ __global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: 
                     if (s + j >= r.s1) continue;
                     Vec4 out;
                     FastGuard guard;
-                    guard_reset(guard);
+                    guard_reset(guard, seed);
 #pragma unroll
                     for (int e = 0; e < kCiVec; ++e) {
                         const float xe = act_fwd<ACT>(BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e]);
                         guard_note(guard, xe);
                         out.v[e] = dequant(elem_fast(xe, p[e]).q, p[e]);
                     }
-                    if (!all_fast || guard_bad(guard)) {
+                    if (guard_bad(guard)) {
 #pragma unroll
                         for (int e = 0; e < kCiVec; ++e) {
                             const float xe = act_fwd<ACT>(BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e]);
@@ -241,11 +242,11 @@ __global__ void __launch_bounds__(kThreads, 3)
 // The element arithmetic of one vector (four channels): dx, and the LSQ terms when WANT_DS.
 template <bool BIAS, int ACT, bool WANT_DS>
 __device__ __forceinline__ void ci_bwd_vec(const Vec4& vx, const Vec4& vg, const QP (&p)[kCiVec], const float (&bv)[kCiVec],
-                                           bool all_fast, Vec4& out, float (&te)[kCiVec], float (&tb)[kCiVec],
+                                           uint32_t seed, Vec4& out, float (&te)[kCiVec], float (&tb)[kCiVec],
                                            float (&tdb)[kCiVec]) {
     float ve[kCiVec], vbz[kCiVec];
     FastGuard guard;
-    guard_reset(guard);
+    guard_reset(guard, seed);
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
         const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
@@ -256,13 +257,14 @@ __device__ __forceinline__ void ci_bwd_vec(const Vec4& vx, const Vec4& vg, const
         const Elem el = elem_fast(xe, p[e]);
         out.v[e] = act_bwd<ACT>(xb, dx_fast(ge, el.m, p[e]));
         if (WANT_DS) {
-            const float dd = __fsub_rn(el.q, p[e].z);
-            const float mv = __fmul_rn(el.v, el.m ? 1.0f : 0.0f);
-            ve[e] = ge * (dd - mv);
+            // g * ((q - z) - m * v): v is finite on this path, so the masked product is a predicated subtraction
+            float dd = __fsub_rn(el.q, p[e].z);
+            if (el.m) dd = __fsub_rn(dd, el.v);
+            ve[e] = __fmul_rn(ge, dd);
             vbz[e] = el.m ? 0.0f : ge;
         }
     }
-    if (!all_fast || guard_bad(guard)) {  // rare: IEEE sequences for the whole vector
+    if (guard_bad(guard)) {  // rare: IEEE sequences for the whole vector
 #pragma unroll
         for (int e = 0; e < kCiVec; ++e) {
             const float xb = BIAS ? __fadd_rn(vx.v[e], bv[e]) : vx.v[e];
@@ -403,6 +405,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         all_fast = all_fast && p[e].fast;
         bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
     }
+    const uint32_t seed = guard_seed(all_fast);
     double acc_e[kCiVec], acc_b[kCiVec], acc_db[kCiVec];
     float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials, folded into the fp64 sums every 16 vectors
 #pragma unroll
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                 for (int j = 0; j < kCiUnroll; ++j) {
                     if (s + j >= r.s1) continue;
                     Vec4 out;
-                    ci_bwd_vec<BIAS, ACT, WANT_DS>(vx[j], vg[j], p, bv, all_fast, out, te, tb, tdb);
+                    ci_bwd_vec<BIAS, ACT, WANT_DS>(vx[j], vg[j], p, bv, seed, out, te, tb, tdb);
                     st4(const_cast<float*>(xp) + j * stride + ddx, out);
                 }
                 if ((++it & (kCiBatches - 1)) == 0 || s + kCiUnroll >= r.s1) {
@@ -607,6 +610,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2)
         all_fast = all_fast && p[e].fast;
         bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
     }
+    const uint32_t seed = guard_seed(all_fast);
     double acc_e[kCiVec], acc_b[kCiVec], acc_db[kCiVec];
     float te[kCiVec], tb[kCiVec], tdb[kCiVec];  // fp32 partials, folded into the fp64 sums every kCiBatches units
 #pragma unroll
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2)
                 const Vec4 vx = lds4(xs + (size_t)u * kCiVec);
                 const Vec4 vg = lds4(gs + (size_t)u * kCiVec);
                 Vec4 out;
-                ci_bwd_vec<BIAS, ACT, WANT_DS>(vx, vg, p, bv, all_fast, out, te, tb, tdb);
+                ci_bwd_vec<BIAS, ACT, WANT_DS>(vx, vg, p, bv, seed, out, te, tb, tdb);
                 st4(dx + (v0 + u) * kCiVec, out);
             }
         }

@@ -211,10 +211,12 @@ struct FastGuard {
     uint32_t lo;
 };
 constexpr uint32_t kTinyKey = 0x42ffffffu;  // 2 * bits(2^-60) - 1
-__device__ __forceinline__ void guard_reset(FastGuard& g) {
+__device__ __forceinline__ void guard_reset(FastGuard& g, uint32_t lo0 = 0xffffffffu) {
     g.hi = 0.0f;
-    g.lo = 0xffffffffu;
+    g.lo = lo0;  // 0 here poisons the guard: the way an out-of-range SCALE forces the IEEE path without a second test
 }
+// loop-invariant seed for guard_reset: all-ones when every scale of this thread admits the fast arithmetic
+__device__ __forceinline__ uint32_t guard_seed(bool all_fast) { return all_fast ? 0xffffffffu : 0u; }
 __device__ __forceinline__ void guard_note(FastGuard& g, float v) {
     g.hi = __fadd_rn(g.hi, fabsf(v));
     g.lo = min(g.lo, 2u * __float_as_uint(v) - 1u);

@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(kThreads)
             const Vec<kVec> vin = ld_stream(x + i, (Vec<kVec>*)nullptr);
             float q[kVec];
             FastGuard guard;
-            guard_reset(guard);
+            guard_reset(guard, guard_seed(p.fast));
 #pragma unroll
             for (int e = 0; e < kVec; ++e) {
                 guard_note(guard, vin.v[e]);
                 q[e] = elem_fast(vin.v[e], p).q;
             }
-            if (!p.fast || guard_bad(guard)) {
+            if (guard_bad(guard)) {
 #pragma unroll
                 for (int e = 0; e < kVec; ++e) q[e] = elem_slow(vin.v[e], p).q;
             }

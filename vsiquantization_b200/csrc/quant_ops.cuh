@@ -11,8 +11,8 @@ namespace vsiq {
 struct QuantOpBase : OpBase {
     QP p;
     FastGuard guard;  // admissibility of the current vector for the division-free arithmetic (common.cuh)
-    __device__ __forceinline__ void vec_begin() { guard_reset(guard); }
-    __device__ __forceinline__ bool vec_bad() const { return !p.fast || guard_bad(guard); }
+    __device__ __forceinline__ void vec_begin() { guard_reset(guard, guard_seed(p.fast)); }
+    __device__ __forceinline__ bool vec_bad() const { return guard_bad(guard); }
 };
 
 // RELU = true fuses the preceding activation into the quantiser: the kernels see the conv output x, quantise
@@ -70,7 +70,7 @@ struct LsqBwdOp : QuantOpBase {
     float b_acc;  // sum g over clamped-out elements
     float e_vec, b_vec;  // the current vector's share (committed by vec_done, discarded on a redo)
     __device__ __forceinline__ void vec_begin() {
-        guard_reset(guard);
+        guard_reset(guard, guard_seed(p.fast));
         e_vec = 0.0f;
         b_vec = 0.0f;
     }
