@@ -86,6 +86,15 @@ int ci_tile_override() {
     return v;
 }
 
+int pc_chunk_override() {
+    static const int v = []() {
+        const char* e = getenv("VSIQ_PC_CHUNK");
+        const int n = e ? atoi(e) : 0;
+        return n >= 2048 && n <= (1 << 20) ? (n / 2048) * 2048 : 0;
+    }();
+    return v;
+}
+
 bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 int check_layout(const vsiq_layout* l) {

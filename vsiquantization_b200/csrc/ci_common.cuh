@@ -164,39 +164,6 @@ __device__ __forceinline__ void st4(float* p, const Vec4& r) {
     asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
 }
 
-// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
-// A reducing kernel that leaves wide per-CTA records is followed by a small combine kernel on the same stream.  The
-// combine kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs become resident while the
-// streaming kernel is still running (the streaming kernel signals launch_dependents in its prologue) and park in
-// griddepcontrol.wait, which returns once the streaming grid has completed and its writes are visible.  The ~5 us
-// launch-and-drain bubble of a plain back-to-back launch shrinks to the wake-up latency.  Both instructions are no-ops
-// when the kernel was launched without the attribute.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    // the legacy default stream takes no programmatic dependencies: plain stream order there
-    const bool legacy = st == nullptr || st == cudaStreamLegacy;
-    cfg.numAttrs = (pdl_enabled() && !legacy) ? 1 : 0;
-    cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-    if (err == cudaErrorInvalidValue && cfg.numAttrs) {  // attribute refused (driver / stream kind): launch without it
-        (void)cudaGetLastError();
-        cfg.numAttrs = 0;
-        err = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-    }
-    return err;
-}
-
 // Fixed-order combine of per-CTA records [n_rec][width] (fp64): one CTA owns 8 consecutive entries; inside a warp the
 // low three lane bits select the entry and the high two a record phase, so one load instruction of a warp reads four
 // 64-byte segments and the 32 (warp, phase) pairs of the CTA walk the records 32 apart.  A thread issues ALL its loads

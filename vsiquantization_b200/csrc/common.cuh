@@ -522,12 +522,22 @@ struct PcGeom {
     uint32_t k;       // CTAs per channel
     int chunk;        // elements per unit
 };
+int pc_chunk_override();  // VSIQ_PC_CHUNK (abi.cu)
 inline bool make_pc_geom(int64_t outer, int64_t channels, int64_t inner, bool warp_group, int sm_count, PcGeom* g) {
     if (outer <= 0 || channels <= 1 || inner <= 0) return false;
     g->outer = outer;
     g->channels = channels;
     g->inner = inner;
-    const int64_t chunk = warp_group ? inner : 16384;
+    // 16384-element units; halved (down to 4096) while the whole problem is only a wave or two of CTAs, so that mid-size
+    // tensors (2^22 .. 2^24 elements) are not dealt out as 2.3 waves of fat CTAs with an idle tail
+    int64_t chunk = warp_group ? inner : 16384;
+    if (!warp_group) {
+        const int64_t ov = pc_chunk_override();
+        if (ov > 0)
+            chunk = ov;
+        else
+            while (chunk > 4096 && channels * outer * ((inner + chunk - 1) / chunk) < (int64_t)sm_count * 3 * 6) chunk >>= 1;
+    }
     const int64_t chunks = (inner + chunk - 1) / chunk;
     const int64_t units = outer * chunks;
     if (units >= (int64_t(1) << 31) || chunk >= (int64_t(1) << 31)) return false;
@@ -537,7 +547,7 @@ inline bool make_pc_geom(int64_t outer, int64_t channels, int64_t inner, bool wa
     const int64_t per_cta = warp_group ? kWarps : 1;  // units a CTA works on concurrently
     int64_t k = ((int64_t)sm_count * 8 + channels - 1) / channels;
     const int64_t kmax = (units + per_cta - 1) / per_cta;
-    if (k > kmax) k = kmax;
+    if (k > kmax || kmax <= 4) k = kmax;  // a handful of units per channel: one CTA each (k < kmax would pair them unevenly)
     if (k < 1) k = 1;
     g->k = (uint32_t)k;
     if (channels * k >= (int64_t(1) << 31)) return false;
@@ -579,7 +589,41 @@ bool aligned32(const void* p);
 bool pdl_enabled();         // programmatic dependent launch for the combine kernels (VSIQ_PDL=0 disables; A/B knob)
 int ci_sched_override();    // VSIQ_CI_SCHED=static|dynamic|interleaved -> 0 | 1 | 2, else -1 (automatic)
 int ci_tile_override();     // VSIQ_CI_TILE=<steps per tile>, else 0 (automatic)
+int pc_chunk_override();    // VSIQ_PC_CHUNK=<elements per unit of the NCHW per-channel schedule>, else 0 (automatic)
 int check_layout(const vsiq_layout* l);
 int fill_qp(const vsiq_qparams* in, QPDev* out);
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL)
+// ---------------------------------------------------------------------------------------------
+// A reducing kernel that leaves wide per-CTA records is followed by a small combine kernel on the same stream.  The
+// combine kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs become resident while the
+// streaming kernel is still running (the streaming kernel signals launch_dependents in its prologue) and park in
+// griddepcontrol.wait, which returns once the streaming grid has completed and its writes are visible.  The ~5 us
+// launch-and-drain bubble of a plain back-to-back launch shrinks to the wake-up latency.  Both instructions are no-ops
+// when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (err == cudaErrorInvalidValue && cfg.numAttrs) {  // attribute refused (driver / stream kind): launch without it
+        (void)cudaGetLastError();
+        cfg.numAttrs = 0;
+        err = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    }
+    return err;
+}
 
 }  // namespace vsiq

@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(kThreads, 3)  // <= 85 registers: three CTAs p
     lsq_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, Tiles tiles,
                    QPDev qpd, void* ws, LsqOut o, int64_t outer, int use_ticket) {
     __shared__ double s_red[kWarps][2];
+    pdl_launch_dependents();
     const float* const in[2] = {x, g};
     float* const out[1] = {dx};
     double* partials = ws_partials(ws);
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(kThreads, 3)  // <= 85 registers: three CTAs p
     lsq_bwd_pc_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, PcGeom geo,
                       QPDev qpd, void* ws, LsqOut o, int use_ticket) {
     __shared__ double s_red[kWarps][2];
+    pdl_launch_dependents();
     const float* const in[2] = {x, g};
     float* const out[1] = {dx};
     double* partials = ws_partials(ws);
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(kThreads)
     lsq_finalize_kernel(Tiles tiles, QPDev qpd, const void* ws, LsqOut o, int64_t outer) {
     __shared__ double s_red[kWarps][2];
     const double* partials = (const double*)((const char*)ws + kWsHeader);
+    pdl_wait();  // launched as a programmatic dependent of the streaming kernel: its records are complete from here on
     if (MODE == 0) {
         for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < tiles.channels; c += (int64_t)gridDim.x * kThreads)
             lsq_combine_thread(partials, tiles, outer, c, o, qpd);
@@ -606,7 +609,7 @@ extern "C" size_t vsiq_lsq_bwd_workspace_bytes(const vsiq_layout* layout) {
     if (make_tiles<kThreads>(layout->outer, layout->channels, layout->inner, &tc)) slots = tc.n_tiles;
     if (layout->inner < kWarpGroupMaxInner && make_tiles<32>(layout->outer, layout->channels, layout->inner, &tw))
         slots = tw.n_tiles > slots ? tw.n_tiles : slots;
-    return kWsHeader + slots * 2 * sizeof(double);
+    return kWsHeader + 2 * slots * 2 * sizeof(double);  // x2: the per-channel schedule may use 4096-element units
 }
 
 extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dscale, int dscale_dtype, void* dzp,
@@ -658,21 +661,21 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
             return VSIQ_ERR_INVALID_ARG;                                                                       \
         int grid = launch_grid(ctas_for_tiles<G>(tiles.n_tiles));                                              \
         if (grid < 0) return -grid;                                                                            \
-        const int use_ticket = tiles.n_tiles <= kTicketMaxRecords ? 1 : 0;                                     \
+        const int use_ticket = (grid <= dprops.sm_count * 4 && tiles.n_tiles <= kTicketMaxRecords) ? 1 : 0;             \
         lsq_bwd_kernel<G, V, M, Z, R><<<grid, kThreads, 0, st>>>(x, g, dx, tiles, qpd, workspace, lo,          \
                                                               layout->outer, use_ticket);                      \
         if (!use_ticket) {                                                                                     \
             const int64_t items = layout->outer * (int64_t)tiles.chunks;                                       \
             if (items <= kThreadCombineMaxItems) {                                                             \
                 int64_t fg = (layout->channels + kThreads - 1) / kThreads;                                     \
-                lsq_finalize_kernel<0><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, qpd, workspace, lo, \
+                launch_pdl(lsq_finalize_kernel<0>, dim3((unsigned)(fg < 4096 ? fg : 4096)), dim3(kThreads), 0, st, tiles, qpd, workspace, lo, \
                                                                                           layout->outer);      \
             } else if (items >= 512) {                                                                         \
                 int fgrid = (int)(layout->channels < 1024 ? layout->channels : 1024);                          \
-                lsq_finalize_kernel<2><<<fgrid, kThreads, 0, st>>>(tiles, qpd, workspace, lo, layout->outer);  \
+                launch_pdl(lsq_finalize_kernel<2>, dim3((unsigned)fgrid), dim3(kThreads), 0, st, tiles, qpd, workspace, lo, layout->outer);  \
             } else {                                                                                           \
                 int64_t fg = (layout->channels + kWarps - 1) / kWarps;                                         \
-                lsq_finalize_kernel<1><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, qpd, workspace, lo, \
+                launch_pdl(lsq_finalize_kernel<1>, dim3((unsigned)(fg < 4096 ? fg : 4096)), dim3(kThreads), 0, st, tiles, qpd, workspace, lo, \
                                                                                           layout->outer);      \
             }                                                                                                  \
         }                                                                                                      \
@@ -684,7 +687,8 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
         make_pc_geom(layout->outer, layout->channels, layout->inner, warp_group, dprops.sm_count, &pc) &&
         (size_t)pc.channels * pc.k * 2 * sizeof(double) + kWsHeader <= workspace_bytes) {
         const int grid = (int)(pc.channels * pc.k);
-        const int use_ticket = (uint32_t)grid <= kTicketMaxRecords ? 1 : 0;
+        // one partial wave: the last CTA combines; more: no ticket, no fence -- the combine kernel is a programmatic dependent
+        const int use_ticket = grid <= dprops.sm_count * 4 ? 1 : 0;
         const bool relu = qp->pre_op == VSIQ_PRE_RELU;
 #define PC(G, V, Z, R) lsq_bwd_pc_kernel<G, V, Z, R><<<grid, kThreads, 0, st>>>(x, g, dx, pc, qpd, workspace, lo, use_ticket)
 #define PC2(G, V, Z) { if (relu) PC(G, V, Z, true); else PC(G, V, Z, false); }
@@ -703,10 +707,10 @@ extern "C" int vsiq_lsq_bwd(const float* x, const float* g, float* dx, void* dsc
             rec.tile = 0;
             if (pc.k <= kThreadCombineMaxItems) {
                 int64_t fg = (pc.channels + kThreads - 1) / kThreads;
-                lsq_finalize_kernel<0><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(rec, qpd, workspace, lo, 1);
+                launch_pdl(lsq_finalize_kernel<0>, dim3((unsigned)(fg < 4096 ? fg : 4096)), dim3(kThreads), 0, st, rec, qpd, workspace, lo, 1);
             } else {
                 int64_t fg = (pc.channels + kWarps - 1) / kWarps;
-                lsq_finalize_kernel<1><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(rec, qpd, workspace, lo, 1);
+                launch_pdl(lsq_finalize_kernel<1>, dim3((unsigned)(fg < 4096 ? fg : 4096)), dim3(kThreads), 0, st, rec, qpd, workspace, lo, 1);
             }
         }
         return (int)cudaGetLastError();

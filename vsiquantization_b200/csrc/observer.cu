@@ -208,6 +208,7 @@ template <int GROUP, int V>
 __global__ void __launch_bounds__(kThreads)
     observe_kernel(const float* __restrict__ x, Tiles tiles, int64_t outer, void* ws, ObserveOut o, int use_ticket) {
     __shared__ double s_red[kWarps][kPartialWidth];
+    pdl_launch_dependents();
     const float* const in[1] = {x};
     float* const out[1] = {nullptr};
     double* partials = ws_partials(ws);
@@ -275,6 +276,7 @@ template <int GROUP, int V>
 __global__ void __launch_bounds__(kThreads)
     observe_pc_kernel(const float* __restrict__ x, PcGeom geo, void* ws, ObserveOut o, int use_ticket) {
     __shared__ double s_red[kWarps][kPartialWidth];
+    pdl_launch_dependents();
     const float* const in[1] = {x};
     float* const out[1] = {nullptr};
     double* partials = ws_partials(ws);
@@ -497,6 +499,7 @@ __global__ void __launch_bounds__(kThreads)
     observe_finalize_kernel(Tiles tiles, int64_t outer, const void* ws, ObserveOut o) {
     __shared__ double s_red[kWarps][kPartialWidth];
     const double* partials = (const double*)((const char*)ws + kWsHeader);
+    pdl_wait();  // a programmatic dependent of the streaming kernel
     if (MODE == 0) {
         for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < tiles.channels; c += (int64_t)gridDim.x * kThreads)
             observe_combine<1>(partials, tiles, outer, c, o, s_red);
@@ -573,7 +576,7 @@ extern "C" size_t vsiq_observe_workspace_bytes(const vsiq_layout* layout) {
     if (make_tiles<kThreads>(layout->outer, layout->channels, layout->inner, &tc)) slots = tc.n_tiles;
     if (layout->inner < kWarpGroupMaxInner && make_tiles<32>(layout->outer, layout->channels, layout->inner, &tw))
         slots = tw.n_tiles > slots ? tw.n_tiles : slots;
-    return kWsHeader + slots * kPartialWidth * sizeof(double);
+    return kWsHeader + 2 * slots * kPartialWidth * sizeof(double);  // x2: the per-channel schedule may use 4096-element units
 }
 
 extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* stats, double* state, int bits,
@@ -607,7 +610,7 @@ extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* s
         make_pc_geom(layout->outer, layout->channels, layout->inner, warp_group, dprops.sm_count, &pc) &&
         (size_t)pc.channels * pc.k * kPartialWidth * sizeof(double) + kWsHeader <= workspace_bytes) {
         const int grid = (int)(pc.channels * pc.k);
-        const int use_ticket = (uint32_t)grid <= kTicketMaxRecords ? 1 : 0;
+        const int use_ticket = grid <= dprops.sm_count * 4 ? 1 : 0;  // else: combine kernel as a programmatic dependent
         if (warp_group) {
             if (vec8) observe_pc_kernel<32, 8><<<grid, kThreads, 0, st>>>(x, pc, workspace, oo, use_ticket);
             else observe_pc_kernel<32, 1><<<grid, kThreads, 0, st>>>(x, pc, workspace, oo, use_ticket);
@@ -625,10 +628,10 @@ extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* s
             recs.tile = 0;
             if (pc.k <= kThreadCombineMaxItems) {
                 int64_t fg = (pc.channels + kThreads - 1) / kThreads;
-                observe_finalize_kernel<0><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(recs, 1, workspace, oo);
+                launch_pdl(observe_finalize_kernel<0>, dim3((unsigned)(fg < 4096 ? fg : 4096)), dim3(kThreads), 0, st, recs, 1, workspace, oo);
             } else {
                 int64_t fg = (pc.channels + kWarps - 1) / kWarps;
-                observe_finalize_kernel<1><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(recs, 1, workspace, oo);
+                launch_pdl(observe_finalize_kernel<1>, dim3((unsigned)(fg < 4096 ? fg : 4096)), dim3(kThreads), 0, st, recs, 1, workspace, oo);
             }
         }
         return (int)cudaGetLastError();
@@ -657,20 +660,20 @@ extern "C" int vsiq_observe(const float* x, const vsiq_layout* layout, double* s
         uint32_t want = G == kThreads ? tiles.n_tiles : (tiles.n_tiles + kWarps - 1) / kWarps;                  \
         int grid = launch_grid(want);                                                                           \
         if (grid < 0) return -grid;                                                                             \
-        const int use_ticket = tiles.n_tiles <= kTicketMaxRecords ? 1 : 0;                                      \
+        const int use_ticket = (grid <= dprops.sm_count * 4 && tiles.n_tiles <= kTicketMaxRecords) ? 1 : 0;              \
         observe_kernel<G, V><<<grid, kThreads, 0, st>>>(x, tiles, layout->outer, workspace, oo, use_ticket);    \
         if (!use_ticket) {                                                                                      \
             const int64_t items = layout->outer * (int64_t)tiles.chunks;                                        \
             if (items <= kThreadCombineMaxItems) {                                                              \
                 int64_t fg = (layout->channels + kThreads - 1) / kThreads;                                      \
-                observe_finalize_kernel<0><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, layout->outer, \
+                launch_pdl(observe_finalize_kernel<0>, dim3((unsigned)(fg < 4096 ? fg : 4096)), dim3(kThreads), 0, st, tiles, layout->outer, \
                                                                                               workspace, oo);   \
             } else if (items >= 512) {                                                                          \
                 int fgrid = (int)(layout->channels < 1024 ? layout->channels : 1024);                           \
-                observe_finalize_kernel<2><<<fgrid, kThreads, 0, st>>>(tiles, layout->outer, workspace, oo);    \
+                launch_pdl(observe_finalize_kernel<2>, dim3((unsigned)fgrid), dim3(kThreads), 0, st, tiles, layout->outer, workspace, oo);    \
             } else {                                                                                            \
                 int64_t fg = (layout->channels + kWarps - 1) / kWarps;                                          \
-                observe_finalize_kernel<1><<<(int)(fg < 4096 ? fg : 4096), kThreads, 0, st>>>(tiles, layout->outer, \
+                launch_pdl(observe_finalize_kernel<1>, dim3((unsigned)(fg < 4096 ? fg : 4096)), dim3(kThreads), 0, st, tiles, layout->outer, \
                                                                                               workspace, oo);   \
             }                                                                                                   \
         }                                                                                                       \
