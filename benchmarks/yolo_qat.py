@@ -7,8 +7,9 @@ QAT layers, synthetic data, one process per GPU.
 Every step copies its uint8 image batch from pinned host memory, runs forward / backward / (flat qparam-gradient
 all-reduce) / SGD step and reads the loss back to the host: the number is end to end.  Loss = sum over the three
 heads of mean(out^2) (the reference's ComputeLoss needs box targets; the detection loss is out of scope).
-`--quant-impl eager` swaps the two plugins for torch-eager restatements of the reference's op sequence on the SAME
-GPU -- the GPU-vs-GPU yardstick of SURVEY 8(d) -- everything else (fused layers, manager, cuDNN convs) unchanged.
+`--quant-impl eager` swaps every quantizer plugin object for the torch-eager restatement of the reference's op sequence
+on the SAME GPU after calibration -- the GPU-vs-GPU yardstick of SURVEY 8(d) -- everything else (fused layers, manager,
+calibrated parameters, cuDNN convs) unchanged.
 """
 from __future__ import annotations
 
@@ -26,74 +27,20 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def install_eager_plugins():
-    """Reference-composition plugins (torch eager on the current device) under the reference's registry names."""
-    from oracle import torch_port
-    from vsiquantization_b200.utils.registry import CLASS_REGISTRY
-
-    class EagerUniformQuantizer:
-        def __init__(self, num_bits=8, symmetric=True):
-            self.num_bits, self.symmetric = num_bits, symmetric
-            self.qmin, self.qmax = (-(2 ** (num_bits - 1)), 2 ** (num_bits - 1) - 1) if symmetric else (0, 2 ** num_bits - 1)
-            self.calib_grad_scale = 1
-            self.ch_axis = None
-
-        def quantize(self, x, scale, zero_point, is_learning_scale=False):
-            if is_learning_scale and isinstance(scale, torch.Tensor):
-                gs = (self.qmax * x.numel()) ** -0.5 * self.calib_grad_scale
-                scale = torch_port._ScaleGrad.apply(scale, gs)
-                if not self.symmetric and isinstance(zero_point, torch.Tensor):
-                    zero_point = torch.clamp(torch_port._RoundSTE.apply(zero_point), self.qmin, self.qmax)
-                    zero_point = torch_port._ScaleGrad.apply(zero_point, gs)
-            x_int = torch.clamp(torch_port._RoundSTE.apply(x / scale + zero_point), self.qmin, self.qmax)
-            return (x_int - zero_point) * scale
-
-    class EagerMinMaxObserver:
-        """observers/minmax.py:25-88 verbatim in behaviour: two reductions + two .item() syncs per call."""
-
-        def __init__(self, symmetric=True, num_bits=8, eps=1e-8):
-            self.symmetric, self.num_bits, self.eps = symmetric, num_bits, eps
-            self.min_val = self.max_val = 0
-            self.ch_axis = None
-            self.state = None
-            self._abs = []
-
-        def observe(self, x):
-            mn, mx = x.min().item(), x.max().item()
-            self._abs.append(x.abs().mean().item())
-            self.last_stats, self.last_count = None, x.numel()
-            self.min_val, self.max_val = min(self.min_val, mn), max(self.max_val, mx)
-
-        def get_scale_zero_point(self):
-            if self.symmetric:
-                return max(abs(self.min_val), abs(self.max_val)) / (2 ** (self.num_bits - 1) - 1 + self.eps), 0
-            s = (self.max_val - self.min_val) / (2 ** self.num_bits - 1 + self.eps)
-            return s, round(-self.min_val / (s + self.eps))
-
-        def forward(self, x):
-            self.observe(x)
-            return self.get_scale_zero_point()
-
-    CLASS_REGISTRY["UniformQuantizer"] = EagerUniformQuantizer
-    CLASS_REGISTRY["LSQQuantizer"] = EagerUniformQuantizer
-    CLASS_REGISTRY["MinMaxObserver"] = EagerMinMaxObserver
-    CLASS_REGISTRY["LSQObserver"] = EagerMinMaxObserver
-
-
-def _eager_manager_patch():
-    """The eager observers keep host floats; give the manager the reference's host-side calibration / LSQ init."""
-    import numpy as np
-    from vsiquantization_b200.quantizers.quantization_manager import QuantizationManager as M
-
-    def collect(self, x):
-        if not self.is_learning_scale and self.is_observer_qparam:
-            self.scale, self.zero_point = self.observer.forward(x.detach())
-
-    def init(self):
-        if self.observer._abs:
-            self.scale = float(2 * np.mean(self.observer._abs) / np.sqrt(2 ** (self.bits_width - 1) - 1))
-
-    M.collect_qparameter, M.init_scaling_factor_for_learning = collect, init
+def swap_in_eager_quantizers(model) -> int:
+    """The GPU-vs-GPU yardstick: same fused layers, same calibrated / initialised parameters, same cuDNN convolutions --
+    only the quantizer plugin objects are replaced by the reference's eager composition (oracle/torch_port.EagerQuantizer:
+    quantizers/uniform.py:34-56 per tensor, the per-channel form of quantizers/lsq_module.py:147-173 otherwise): six ATen
+    kernels forward and ~14 backward per quantiser instead of one each.  Returns the number of quantisers swapped."""
+    from oracle.torch_port import EagerQuantizer
+    n = 0
+    for mod in model.modules():
+        for attr in ("weight_quantizer", "activation_quantizer"):
+            mgr = getattr(mod, attr, None)
+            if mgr is not None and hasattr(mgr, "quantizer"):
+                mgr.quantizer = EagerQuantizer.like(mgr.quantizer)
+                n += 1
+    return n
 
 
 def kernel_time_profile(step, n_steps: int):
@@ -175,7 +122,7 @@ def build_model(args, device):
     calibrate_qat_model(model, calib, data_calib, device)
     torch.cuda.synchronize()
     calib_s = time.perf_counter() - t0
-    if dist.is_initialized() and args.quant_impl == "native":
+    if dist.is_initialized():
         from vsiquantization_b200.parallel import sync_observers
         sync_observers(model)
     activate_learning_qparam(model, use_init=True)
@@ -193,12 +140,10 @@ def run(args) -> dict:
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=device)
     torch.backends.cudnn.benchmark = True
-    if args.quant_impl == "eager":
-        import vsiquantization_b200.quantizers.quantization_manager  # noqa: F401  (registers the native plugins first)
-        install_eager_plugins()
-        _eager_manager_patch()
     from vsiquantization_b200 import _lib
     model, n_fused, calib_s = build_model(args, device)
+    if args.quant_impl == "eager":
+        swap_in_eager_quantizers(model)
     model.train()
     if args.channels_last:
         model.to(memory_format=torch.channels_last)
@@ -370,7 +315,7 @@ def run(args) -> dict:
     # competes with it, against its duration inside the step (which includes waiting for the slowest rank)
     ar_alone = None
     if world > 1:
-        nbytes = graphed.allreduce_bytes if graphed is not None else sum(p.numel() * p.element_size() for p in model.parameters())
+        nbytes = getattr(graphed, "allreduce_bytes", 0) or sum(p.numel() * p.element_size() for p in model.parameters())
         buf = torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
         for _ in range(3):
             dist.all_reduce(buf)

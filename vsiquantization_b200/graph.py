@@ -24,6 +24,12 @@ from typing import Callable
 import torch
 
 
+import os as _os
+
+# measurement knob only (benchmarks: what does the step cost without its collective?) -- training without it is wrong
+_SKIP_ALLREDUCE = _os.environ.get("VSIQ_DEBUG_SKIP_ALLREDUCE", "0") not in ("", "0")
+
+
 class GraphedQATStep:
     def __init__(self, model, optimizer, loss_fn: Callable, example_input: torch.Tensor, warmup: int = 3,
                  post_backward: Callable = None, group=None, average: bool = False):
@@ -62,7 +68,7 @@ class GraphedQATStep:
     def _fwd_bwd_step(self):
         loss = self.loss_fn(self.model(self.static_input))
         loss.backward()
-        if self.world > 1:
+        if self.world > 1 and not _SKIP_ALLREDUCE:
             self._all_reduce_grads()
         if self.post_backward is not None:
             self.post_backward()
@@ -101,7 +107,7 @@ class GraphedQATStep:
             return None
         try:
             return float(self._ar_events[0].elapsed_time(self._ar_events[1]))
-        except RuntimeError:
+        except (RuntimeError, ValueError):  # never recorded (single process, or the collective was skipped)
             return None
 
     def _eager_step(self):
