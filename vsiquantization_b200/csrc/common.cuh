@@ -545,6 +545,9 @@ inline bool make_pc_geom(int64_t outer, int64_t channels, int64_t inner, bool wa
     g->chunks = (uint32_t)chunks;
     g->units = (uint32_t)units;
     const int64_t per_cta = warp_group ? kWarps : 1;  // units a CTA works on concurrently
+    // thousands of short rows with fewer units per channel than a CTA has warps ([4096, 1024] weights): a CTA per channel
+    // would leave 7 of 8 warps idle -- the warp-per-tile schedule (one warp per row, eight rows per CTA) is the right one
+    if (warp_group && units < kWarps) return false;
     int64_t k = ((int64_t)sm_count * 8 + channels - 1) / channels;
     const int64_t kmax = (units + per_cta - 1) / per_cta;
     if (k > kmax || kmax <= 4) k = kmax;  // a handful of units per channel: one CTA each (k < kmax would pair them unevenly)
