@@ -35,27 +35,48 @@ struct CiOut {
 };
 
 // Record layout per CTA (doubles): [E: nq][B: nq][DB: C]   with nq = C (per-channel qparams) or 1 (per tensor)
-__device__ __forceinline__ void ci_store(const CiOut& o, const QPDev& qpd, bool pcq, bool bias, int C, int idx, double v) {
+// What an entry's store needs besides the combined sum: the gradient scale and, for a zero-point entry, its channel's
+// step size and range test.  Loaded separately so that the combine kernel can fetch it BEFORE it waits for the
+// streaming grid (these values do not depend on it).
+struct CiEntryParams {
+    double gs;
+    float s;
+    bool cz;
+};
+__device__ __forceinline__ CiEntryParams ci_entry_params(const CiOut& o, const QPDev& qpd, bool pcq, int C, int idx) {
+    const int nq = pcq ? C : 1;
+    CiEntryParams e;
+    e.gs = o.gs_host * (o.gs_dev ? (double)__ldg(o.gs_dev) : 1.0);
+    e.s = 0.0f;
+    e.cz = true;
+    if (idx >= nq && idx < 2 * nq && o.dzp) {
+        const QP p = load_qp(qpd, idx - nq);
+        const float zr = rintf(p.zf);
+        e.s = p.s;
+        e.cz = qpd.zp_learned ? ((zr >= p.lo) && (zr <= p.hi)) : true;
+    }
+    return e;
+}
+__device__ __forceinline__ void ci_store(const CiOut& o, const CiEntryParams& e, bool pcq, bool bias, int C, int idx, double v) {
     // idx addresses the record: [0,nq) E, [nq,2nq) B, [2nq, 2nq+C) DB
     const int nq = pcq ? C : 1;
-    const double gs = o.gs_host * (o.gs_dev ? (double)__ldg(o.gs_dev) : 1.0);
     if (idx < nq) {
         if (o.dscale) {
-            const double ds = gs * v;
+            const double ds = e.gs * v;
             if (o.ds_f64) ((double*)o.dscale)[idx] = ds; else ((float*)o.dscale)[idx] = (float)ds;
         }
     } else if (idx < 2 * nq) {
         if (o.dzp) {
             const int c = idx - nq;
-            const QP p = load_qp(qpd, c);
-            const float zr = rintf(p.zf);
-            const bool cz = qpd.zp_learned ? ((zr >= p.lo) && (zr <= p.hi)) : true;
-            const double dz = cz ? -gs * (double)p.s * v : 0.0;
+            const double dz = e.cz ? -e.gs * (double)e.s * v : 0.0;  // sum (g*s)*(m-1) = -s * sum over clamped g
             if (o.dz_f64) ((double*)o.dzp)[c] = dz; else ((float*)o.dzp)[c] = (float)dz;
         }
     } else if (bias && o.dbias) {
         o.dbias[idx - 2 * nq] = (float)v;
     }
+}
+__device__ __forceinline__ void ci_store(const CiOut& o, const QPDev& qpd, bool pcq, bool bias, int C, int idx, double v) {
+    ci_store(o, ci_entry_params(o, qpd, pcq, C, idx), pcq, bias, C, idx, v);
 }
 
 // CTA-wide barrier over the first kThreads threads: plain __syncthreads() for 256-thread CTAs, named barrier 1 when a
@@ -106,9 +127,11 @@ __global__ void __launch_bounds__(kThreads)
     __shared__ double s_part[kWarps][kCombineEntries];
     const double* records = (const double*)((const char*)ws + kWsHeader);
     const int idx = blockIdx.x * kCombineEntries + (threadIdx.x & 7);
+    CiEntryParams ep = {};
+    if (threadIdx.x < kCombineEntries && idx < width) ep = ci_entry_params(o, qpd, pcq != 0, C, idx);  // before the wait
     pdl_wait();  // the streaming grid has completed and its records are visible
     const double v = ci_combine8_sum(records, (size_t)width, n_rec, (size_t)idx, idx < width, s_part);
-    if (threadIdx.x < kCombineEntries && idx < width) ci_store(o, qpd, pcq != 0, bias != 0, C, idx, v);
+    if (threadIdx.x < kCombineEntries && idx < width) ci_store(o, ep, pcq != 0, bias != 0, C, idx, v);
 }
 
 // The last CTA to leave resets the ticket (and the tile counter of the dynamic schedule) for the next launch.

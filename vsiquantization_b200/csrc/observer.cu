@@ -18,22 +18,20 @@ namespace vsiq {
 constexpr int kPartialWidth = 6;  // min, max, sum|x|, sum x, sum x^2, nan flag
 
 struct StatsOp : OpBase {
-    float mn, mx;
-    bool bad;            // saw a NaN
+    float mn, mx;        // NaN-propagating extrema (FMNMX.NAN): a NaN input sticks, exactly torch.min / torch.max -- one
+                         // instruction each instead of a compare, a predicate merge and a plain min / max
     float fa, f1, f2;    // fp32 partials of the current vector (<= 8 elements)
     double sa, s1, s2;   // fp64 running sums of this thread
     __device__ __forceinline__ void reset() {
         mn = INFINITY;
         mx = -INFINITY;
-        bad = false;
         fa = f1 = f2 = 0.0f;
         sa = s1 = s2 = 0.0;
     }
     __device__ __forceinline__ void apply(const float (&a)[1], float (&)[1]) {
         const float x = a[0];
-        bad = bad || (x != x);
-        mn = fminf(mn, x);
-        mx = fmaxf(mx, x);
+        mn = min_nan(mn, x);
+        mx = max_nan(mx, x);
         fa += fabsf(x);
         f1 += x;
         f2 = fmaf(x, x, f2);
@@ -52,8 +50,8 @@ template <int GROUP>
 __device__ __forceinline__ void stats_group_reduce(StatsOp& op, double (&out)[kPartialWidth],
                                                    double (*s_red)[kPartialWidth]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float mn = warp_min(op.bad ? NAN : op.mn);
-    float mx = warp_max(op.bad ? NAN : op.mx);
+    float mn = warp_min(op.mn);
+    float mx = warp_max(op.mx);
     double sa = warp_sum(op.sa), s1 = warp_sum(op.s1), s2 = warp_sum(op.s2);
     if (GROUP == 32) {
         out[0] = (double)mn;
@@ -335,15 +333,13 @@ __global__ void __launch_bounds__(kThreads, 3)
     const int t = threadIdx.x;
     const bool active = t < geo.threads;
     pdl_launch_dependents();
-    float mn[kCiVec], mx[kCiVec];
-    bool nan[kCiVec];
+    float mn[kCiVec], mx[kCiVec];  // NaN-propagating (FMNMX.NAN): a NaN in the channel sticks, like torch.min / torch.max
     // the fp64 running sums live in this thread's column of shared memory (touched once per 16 vectors; keeps the kernel
     // at 80 registers = 3 CTAs per SM without spilling)
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
         mn[e] = INFINITY;
         mx[e] = -INFINITY;
-        nan[e] = false;
         s_acc[2 * kCiVec + e][t] = 0.0;
         s_acc[3 * kCiVec + e][t] = 0.0;
         s_acc[4 * kCiVec + e][t] = 0.0;
@@ -372,9 +368,8 @@ __global__ void __launch_bounds__(kThreads, 3)
 #pragma unroll
                     for (int e = 0; e < kCiVec; ++e) {
                         const float xv = vin[j].v[e];
-                        nan[e] = nan[e] || (xv != xv);
-                        mn[e] = fminf(mn[e], xv);
-                        mx[e] = fmaxf(mx[e], xv);
+                        mn[e] = min_nan(mn[e], xv);
+                        mx[e] = max_nan(mx[e], xv);
                         fa[e] += fabsf(xv);
                         f1[e] += xv;
                         f2[e] = fmaf(xv, xv, f2[e]);
@@ -396,8 +391,8 @@ __global__ void __launch_bounds__(kThreads, 3)
     // ---- one record per CTA: fixed-order reduction over the threads that share a channel group
 #pragma unroll
     for (int e = 0; e < kCiVec; ++e) {
-        s_acc[0 * kCiVec + e][t] = active ? (double)(nan[e] ? NAN : mn[e]) : (double)INFINITY;
-        s_acc[1 * kCiVec + e][t] = active ? (double)(nan[e] ? NAN : mx[e]) : (double)-INFINITY;  // sums: already in place
+        s_acc[0 * kCiVec + e][t] = active ? (double)mn[e] : (double)INFINITY;
+        s_acc[1 * kCiVec + e][t] = active ? (double)mx[e] : (double)-INFINITY;  // sums: already in place
     }
     __syncthreads();
     const int C = geo.channels;
@@ -436,6 +431,8 @@ __global__ void __launch_bounds__(kThreads)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kCombineEntries + (lane & 7);
     const uint32_t phase = (uint32_t)warp * 4u + (uint32_t)(lane >> 3);
+    if (o.state && warp == 0 && lane < kCombineEntries && c < C)  // pull the running state towards L2 while waiting
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(o.state + (size_t)c * VSIQ_STATE_WIDTH));
     pdl_wait();
     float mn = INFINITY, mx = -INFINITY;
     double sa = 0.0, s1 = 0.0, s2 = 0.0;
