@@ -328,6 +328,37 @@ def size_sweep(dev, log2ns, peak, iters: int = 10):
     return rows
 
 
+def code_export_bench(dev, log2n: int, peak: float, iters: int = 10):
+    """Integer-code export (vsiq_quantize_codes) over 2^log2n elements: packed int4 (4.5 B/element) and int8 (5 B/element),
+    codes only, CUDA events, median of `iters`."""
+    import torch
+    from vsiquantization_b200 import ops
+    n = 1 << log2n
+    torch.manual_seed(0)
+    x = torch.randn(n, device=dev)
+    out = {}
+    for name, bits, spec, scale, zp, bpe in (("int8", 8, ops.QSpec(-128, 127), SCALE, 0, 5.0),
+                                             ("int4_packed", 4, ops.QSpec(0, 15), 3.0 / 7, 8, 4.5)):
+        for _ in range(3):
+            ops.quantize_codes(x, scale, zp, spec, bits, want_y=False)
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.quantize_codes(x, scale, zp, spec, bits, want_y=False)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        med = ts[len(ts) // 2]
+        gbs = bpe * n / (med * 1e-3) / 1e9
+        out[name] = {"ms": round(med, 5), "bytes_per_element": bpe, "gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4),
+                     "note": "includes the allocation of the code tensor by the caching allocator"}
+    out["elements"] = n
+    return out
+
+
 # ---------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -591,6 +622,10 @@ def run_native(args):
         line["sweep"] = size_sweep(dev, args.sweep_log2n, peak)
         big = [r["frac_of_peak"] for r in line["sweep"] if r.get("log2n", 0) >= 26 and "frac_of_peak" in r]
         line["sweep_worst_frac_of_peak_ge_2p26"] = min(big) if big else None
+        try:
+            line["code_export"] = code_export_bench(dev, min(args.log2n, 28), peak)
+        except Exception as e:
+            line["code_export"] = {"error": str(e)[:120]}
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.cpu_log2n)
     print(json.dumps(line), flush=True)

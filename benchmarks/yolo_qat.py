@@ -347,6 +347,8 @@ def run(args) -> dict:
            # copies / scalar instantiations the wrappers fell back to while the step was executed eagerly (warm-up, graph
            # capture, and -- without a graph -- the timed steps): all zero means every tensor took a fast path
            "slow_paths": _ops.slow_path_counters()}
+    if graphed is not None and getattr(graphed, "_marks", None):
+        res["step_timeline_ms"] = graphed.step_timeline_ms()
     peak = 6531.9
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])

@@ -28,6 +28,7 @@ import os as _os
 
 # measurement knob only (benchmarks: what does the step cost without its collective?) -- training without it is wrong
 _SKIP_ALLREDUCE = _os.environ.get("VSIQ_DEBUG_SKIP_ALLREDUCE", "0") not in ("", "0")
+_STEP_EVENTS = _os.environ.get("VSIQ_DEBUG_STEP_EVENTS", "0") not in ("", "0")
 
 
 class GraphedQATStep:
@@ -43,6 +44,7 @@ class GraphedQATStep:
             raise ValueError("GraphedQATStep reduces the gradients itself: pass the bare model, not a DDP wrapper")
         self.static_input = example_input.clone()
         self.post_backward = post_backward
+        self._marks = {}
         # timing events recorded INSIDE the captured graph (external event-record nodes): each replay re-records them, so
         # after a replay ``allreduce_ms()`` is the device time of that step's captured gradient all-reduce
         self._ar_events = None
@@ -65,14 +67,29 @@ class GraphedQATStep:
             self.static_loss = self._fwd_bwd_step()
         torch.cuda.synchronize()
 
+    def _mark(self, name):
+        """Debug timeline (VSIQ_DEBUG_STEP_EVENTS=1): external timing events captured into the graph."""
+        if _STEP_EVENTS:
+            ev = self._marks.setdefault(name, torch.cuda.Event(enable_timing=True, external=True))
+            ev.record()
+
+    def step_timeline_ms(self):
+        """{phase: ms} of the last replayed step when VSIQ_DEBUG_STEP_EVENTS=1 (call after a synchronisation)."""
+        names = [n for n in ("start", "forward", "backward", "packed", "reduced", "unpacked", "optimizer") if n in self._marks]
+        return {b: float(self._marks[a].elapsed_time(self._marks[b])) for a, b in zip(names, names[1:])}
+
     def _fwd_bwd_step(self):
+        self._mark("start")
         loss = self.loss_fn(self.model(self.static_input))
+        self._mark("forward")
         loss.backward()
+        self._mark("backward")
         if self.world > 1 and not _SKIP_ALLREDUCE:
             self._all_reduce_grads()
         if self.post_backward is not None:
             self.post_backward()
         self.optimizer.step()
+        self._mark("optimizer")
         return loss.detach()
 
     def _all_reduce_grads(self) -> None:
@@ -84,6 +101,8 @@ class GraphedQATStep:
                 by_dtype.setdefault(p.grad.dtype, []).append(p)
         self.allreduce_bytes = sum(p.grad.numel() * p.grad.element_size() for ps in by_dtype.values() for p in ps)
         flats = [(ps, torch.cat([p.grad.reshape(-1) for p in ps])) for ps in by_dtype.values()]
+        if hasattr(self, "_marks"):
+            self._mark("packed")
         ev = getattr(self, "_ar_events", None)
         if ev is not None:
             ev[0].record()
@@ -91,6 +110,8 @@ class GraphedQATStep:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         if ev is not None:
             ev[1].record()
+        if hasattr(self, "_marks"):
+            self._mark("reduced")
         for ps, flat in flats:
             if self.average:
                 flat.div_(self.world)
@@ -99,6 +120,8 @@ class GraphedQATStep:
                 n = p.numel()
                 p.grad = flat[off:off + n].view(p.shape)
                 off += n
+        if hasattr(self, "_marks"):
+            self._mark("unpacked")
 
     def allreduce_ms(self):
         """Device time of the captured NCCL gradient all-reduce(s) in the last replayed step, or
