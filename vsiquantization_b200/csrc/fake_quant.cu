@@ -135,31 +135,42 @@ __global__ void __launch_bounds__(kThreads)
             else
                 code_store1<BITS>(codes, off + i0, q2[0]);
         }
-        // ---- vector body
-        for (int v = tid; v < nvec; v += kThreads) {
-            const int64_t i = off + head + (int64_t)v * kVec;
-            const Vec<kVec> vin = ld_stream(x + i, (Vec<kVec>*)nullptr);
-            float q[kVec];
-            FastGuard guard;
-            guard_reset(guard, guard_seed(p.fast));
+        // ---- vector body: kCodeUnroll 256-bit loads in flight per thread before any arithmetic
+        constexpr int kCodeUnroll = 4;
+        for (int v0 = tid; v0 < nvec; v0 += kThreads * kCodeUnroll) {
+            Vec<kVec> vin[kCodeUnroll];
 #pragma unroll
-            for (int e = 0; e < kVec; ++e) {
-                guard_note(guard, vin.v[e]);
-                q[e] = elem_fast(vin.v[e], p).q;
+            for (int j = 0; j < kCodeUnroll; ++j) {
+                const int v = v0 + j * kThreads;
+                if (v < nvec) vin[j] = ld_stream(x + off + head + (int64_t)v * kVec, (Vec<kVec>*)nullptr);
             }
-            if (guard_bad(guard)) {
 #pragma unroll
-                for (int e = 0; e < kVec; ++e) q[e] = elem_slow(vin.v[e], p).q;
-            }
-            int qi[kVec];
-            Vec<kVec> vy;
+            for (int j = 0; j < kCodeUnroll; ++j) {
+                const int v = v0 + j * kThreads;
+                if (v >= nvec) continue;
+                const int64_t i = off + head + (int64_t)v * kVec;
+                float q[kVec];
+                FastGuard guard;
+                guard_reset(guard, guard_seed(p.fast));
 #pragma unroll
-            for (int e = 0; e < kVec; ++e) {
-                qi[e] = code_of(q[e]);
-                if (WANT_Y) vy.v[e] = dequant(q[e], p);
+                for (int e = 0; e < kVec; ++e) {
+                    guard_note(guard, vin[j].v[e]);
+                    q[e] = elem_fast(vin[j].v[e], p).q;
+                }
+                if (guard_bad(guard)) {
+#pragma unroll
+                    for (int e = 0; e < kVec; ++e) q[e] = elem_slow(vin[j].v[e], p).q;
+                }
+                int qi[kVec];
+                Vec<kVec> vy;
+#pragma unroll
+                for (int e = 0; e < kVec; ++e) {
+                    qi[e] = code_of(q[e]);
+                    if (WANT_Y) vy.v[e] = dequant(q[e], p);
+                }
+                CodePack<BITS>::store8(codes, i, qi);
+                if (WANT_Y) st_stream(y + i, vy);
             }
-            CodePack<BITS>::store8(codes, i, qi);
-            if (WANT_Y) st_stream(y + i, vy);
         }
     }
 }

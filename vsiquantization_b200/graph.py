@@ -93,33 +93,52 @@ class GraphedQATStep:
         return loss.detach()
 
     def _all_reduce_grads(self) -> None:
-        """One flat all-reduce per dtype over every gradient; the parameters' .grad become views of the flat buffer."""
+        """One flat all-reduce per dtype over every gradient; the parameters' .grad become views of the flat buffer.
+
+        The flat buffer is persistent and every gradient starts on a 32-byte boundary: the pack is ONE multi-tensor copy
+        (torch._foreach_copy_) instead of torch.cat over 228 tensors (measured inside the graph: 0.38 ms -> the copy's
+        bandwidth time), and the optimizer's multi-tensor kernels keep their vectorised path on the views (unaligned views
+        of a cat'ed buffer cost the SGD step 0.33 -> 0.65 ms)."""
         import torch.distributed as dist
         by_dtype = {}
         for p in self.model.parameters():
             if p.grad is not None:
                 by_dtype.setdefault(p.grad.dtype, []).append(p)
         self.allreduce_bytes = sum(p.grad.numel() * p.grad.element_size() for ps in by_dtype.values() for p in ps)
-        flats = [(ps, torch.cat([p.grad.reshape(-1) for p in ps])) for ps in by_dtype.values()]
+        if not hasattr(self, "_flat"):
+            self._flat = {}
+        packed = []
+        for dtype, ps in by_dtype.items():
+            align = max(1, 32 // ps[0].grad.element_size())
+            sig = tuple(p.numel() for p in ps)
+            ent = self._flat.get(dtype)
+            if ent is None or ent[0] != sig or ent[1].device != ps[0].grad.device:
+                offs, off = [], 0
+                for p in ps:
+                    offs.append(off)
+                    off += (p.numel() + align - 1) // align * align
+                ent = (sig, torch.zeros(off, dtype=dtype, device=ps[0].grad.device), offs)  # pads stay zero
+                self._flat[dtype] = ent
+            _, flat, offs = ent
+            views = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, ps)]
+            torch._foreach_copy_(views, [p.grad for p in ps])
+            packed.append((ps, flat, views))
         if hasattr(self, "_marks"):
             self._mark("packed")
         ev = getattr(self, "_ar_events", None)
         if ev is not None:
             ev[0].record()
-        for _, flat in flats:
+        for _, flat, _ in packed:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         if ev is not None:
             ev[1].record()
         if hasattr(self, "_marks"):
             self._mark("reduced")
-        for ps, flat in flats:
+        for ps, flat, views in packed:
             if self.average:
                 flat.div_(self.world)
-            off = 0
-            for p in ps:
-                n = p.numel()
-                p.grad = flat[off:off + n].view(p.shape)
-                off += n
+            for p, v in zip(ps, views):
+                p.grad = v
         if hasattr(self, "_marks"):
             self._mark("unpacked")
 
