@@ -139,14 +139,24 @@ def _flat_grad_case(rank, world):
     model = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)).double()
     model.register_parameter("scale64", torch.nn.Parameter(torch.tensor(0.5, dtype=torch.float64)))
     model.register_parameter("zp32", torch.nn.Parameter(torch.tensor([1.0, 2.0], dtype=torch.float32)))
+    # a channels_last 4-D weight: its gradient keeps channels_last strides, and so must the flat view handed back
+    wcl = torch.arange(2 * 3 * 2 * 2, dtype=torch.float32).reshape(2, 3, 2, 2).contiguous(memory_format=torch.channels_last)
+    model.register_parameter("wcl", torch.nn.Parameter(wcl))
     x = torch.full((2, 5), float(rank + 1), dtype=torch.float64)
-    loss = (model(x) ** 2).sum() * model.scale64 + (model.zp32 ** 2).sum() * (rank + 1)
+    loss = (model(x) ** 2).sum() * model.scale64 + (model.zp32 ** 2).sum() * (rank + 1) + (model.wcl ** 2).sum() * (rank + 2)
     loss.backward()
+    assert model.wcl.grad.stride() == model.wcl.stride()
     local = [p.grad.clone() for p in model.parameters()]
     step = GraphedQATStep.__new__(GraphedQATStep)  # the exchange only: no CUDA, no capture
     step.model, step.group, step.average, step.world = model, None, False, world
     step._all_reduce_grads()
-    return [g.numpy() for g in local], [p.grad.numpy().copy() for p in model.parameters()]
+    assert model.wcl.grad.stride() == model.wcl.stride()          # strides preserved: the optimizer's fast path
+    flat32 = step._flat[torch.float32][1]
+    assert all(p.grad.data_ptr() % 32 == 0 for p in model.parameters())  # every view starts on a 32-byte boundary
+    assert model.wcl.grad.untyped_storage().data_ptr() == flat32.untyped_storage().data_ptr()
+    step._all_reduce_grads()                                       # second call reuses the persistent buffers
+    assert step._flat[torch.float32][1] is flat32
+    return [g.numpy() for g in local], [p.grad.numpy().copy() / world for p in model.parameters()]
 
 
 def test_graphed_step_flat_gradient_all_reduce_is_a_sum_over_ranks():
