@@ -1009,3 +1009,33 @@ def test_fused_silu_epilogue_matches_aten_silu_then_quant(learn, monkeypatch):
     for n in g0:
         tol = 2e-5 if n.endswith(("scale", "zero_point", "bias")) else 1e-6
         assert float((g1[n].double() - g0[n].double()).abs().max()) <= tol * float(g0[n].abs().max() + 1e-12), n
+
+
+def test_unfused_layer_eval_bn_relu_is_one_pass_under_no_grad():
+    """A ConvBnReLU that kept its BN (is_fuse_bn=False), in eval mode under no_grad (calibration, evaluation): BN with the
+    running moments + ReLU run as ONE NHWC kernel pass and agree with ATen's batch_norm -> relu to 2 ulp-scale tolerance;
+    with autograd on, the ATen path (which has a backward) runs."""
+    from vsiquantization_b200 import _lib
+    from vsiquantization_b200.modules.fused import ConvBnReLU
+    torch.manual_seed(3)
+    cv, bn = torch.nn.Conv2d(8, 16, 3, padding=1, bias=False), torch.nn.BatchNorm2d(16, eps=1e-3)
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.2)
+    layer = ConvBnReLU(cv, bn, torch.nn.ReLU(), "MinMaxObserver", "UniformQuantizer", "MinMaxObserver", "UniformQuantizer",
+                       True, True, False, 8, 8).cuda().to(memory_format=torch.channels_last).eval()
+    for q in (layer.weight_quantizer, layer.activation_quantizer):
+        q.is_quantize = False
+        q.is_observer_qparam = False
+    x = torch.randn(4, 8, 24, 24, device="cuda").contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        n0 = _lib.launch_count
+        y = layer(x)
+        assert _lib.launch_count - n0 == 1            # the normalise + ReLU kernel (quantisers are switched off)
+        ref = torch.relu(layer.bn(layer._conv(x, layer.conv_fuse.weight, layer.conv_fuse.bias)))
+    assert torch.allclose(y, ref, rtol=2e-6, atol=2e-6)
+    n0 = _lib.launch_count
+    y2 = layer(x.clone().requires_grad_(True))       # autograd on: ATen's differentiable path
+    assert _lib.launch_count == n0 and torch.equal(y2.detach(), ref)

@@ -88,10 +88,21 @@ class ConvBnReLU(_ConvBase):
             x = self._bn(x)
         return x
 
+    fuse_eval_bn = True  # inference-mode BN + ReLU of a layer that kept its BN as ONE NHWC pass (no autograd: no_grad only)
+
     def run_forward_core(self, x, weights, bias):
         if not self.is_fuse_bn and self._bn_reestimate is not None:
             # BN re-estimation: the hook normalises with the batch moments and applies the activation in the same pass
             return self._bn_reestimate(self, self._conv(x, weights, bias), act="relu" if self.is_relu else "silu")
+        if (self.fuse_eval_bn and not self.is_fuse_bn and self.is_relu and not torch.is_grad_enabled()
+                and not self.bn.training and self.bn.running_mean is not None):
+            # calibration / evaluation of an unfused layer (fused.py:131-134: bn, then relu): ATen spends two read + write
+            # passes on it, vsiq_ci_bn_normalize one (x * a[c] + b[c] from the running moments, ReLU folded in)
+            y = self._conv(x, weights, bias)
+            if ops.ci_supported(y):
+                return ops.ci_bn_normalize(y, self.bn.running_mean, self.bn.running_var, self.bn.weight, self.bn.bias,
+                                           self.bn.eps, relu=True)
+            return F.relu(self.bn(y))
         x = self._pre_activation(x, weights, bias)
         # the reference applies SiLU when relu is not an nn.ReLU -- including relu=None (ConvBn overrides this)
         return F.relu(x) if self.is_relu else F.silu(x)

@@ -241,7 +241,8 @@ def code_bits_for(spec: QSpec) -> int:
     raise ValueError(f"integer range [{spec.qmin}, {spec.qmax}] does not fit 16-bit codes")
 
 
-def quantize_codes(x: torch.Tensor, scale, zero_point, spec: QSpec, code_bits: Optional[int] = None, want_y: bool = True):
+def quantize_codes(x: torch.Tensor, scale, zero_point, spec: QSpec, code_bits: Optional[int] = None, want_y: bool = True,
+                   codes_out: Optional[torch.Tensor] = None):
     """(y or None, integer codes) in one pass: codes = clamp(rint(x/s + z), qmin, qmax)  [uniform.py:54,95 keeps them as
     floats].  code_bits 8 / 16 -> int8 / uint8 / int16 / uint16 tensors shaped like x; 4 -> uint8 tensor with HALF the last
     dimension, two codes per byte (element 2k in the low nibble, two's complement when qmin < 0)."""
@@ -262,11 +263,18 @@ def quantize_codes(x: torch.Tensor, scale, zero_point, spec: QSpec, code_bits: O
         if bits == 4:
             if x.dim() == 0 or x.shape[-1] % 2:
                 raise ValueError("int4 packing needs an even last dimension")
-            codes = torch.empty(x.shape[:-1] + (x.shape[-1] // 2,), dtype=torch.uint8, device=x.device)
+            c_shape, dt = x.shape[:-1] + (x.shape[-1] // 2,), torch.uint8
         else:
             signed = spec.qmin < 0
+            c_shape = x.shape
             dt = {(8, True): torch.int8, (8, False): torch.uint8, (16, True): torch.int16, (16, False): torch.uint16}[(bits, signed)]
-            codes = torch.empty(x.shape, dtype=dt, device=x.device)
+        if codes_out is not None:
+            if tuple(codes_out.shape) != tuple(c_shape) or codes_out.dtype != dt or codes_out.device != x.device \
+                    or not codes_out.is_contiguous():
+                raise ValueError(f"codes_out must be a contiguous {dt} tensor of shape {tuple(c_shape)} on {x.device}")
+            codes = codes_out
+        else:
+            codes = torch.empty(c_shape, dtype=dt, device=x.device)
         check(lib.vsiq_quantize_codes(x.data_ptr(), y.data_ptr() if want_y else None, codes.data_ptr(), bits,
                                       ctypes.byref(lay), ctypes.byref(qp), _stream_ptr()), "vsiq_quantize_codes")
         _count_launch()
