@@ -244,6 +244,15 @@ size_t vsiq_ci_workspace_bytes(int64_t rows, int64_t channels);
 int vsiq_ci_fake_quant_fwd(const float *x, const float *bias, float *y, int64_t rows, int64_t channels,
                            const vsiq_qparams *qp, int64_t qp_channels, void *workspace, size_t workspace_bytes,
                            vsiq_stream_t stream);
+/* Two outputs from one pass over the conv output: y = fq(act(x + bias[c])) with qp, and y2 = fq2(y) with qp2 -- the
+ * tensor the NEXT layer's `quantize_inp` step (quantizers/fake_quantize.py:44-45: x = self.quantize_activation(x))
+ * would compute from y with its own activation quantiser.  y2 is bit-identical to vsiq_fake_quant_fwd(y, qp2); the pass
+ * costs 12 bytes per element instead of 8 + 8 for the two launches it replaces.  qp2->pre_op must be VSIQ_PRE_NONE;
+ * qp2_channels = 1 or channels.  The backward is the composition of the existing entry points (vsiq_lsq_bwd /
+ * vsiq_fake_quant_bwd_ste at y for the second quantiser, vsiq_ci_lsq_bwd at x for the first). */
+int vsiq_ci_fake_quant_fwd2(const float *x, const float *bias, float *y, float *y2, int64_t rows, int64_t channels,
+                            const vsiq_qparams *qp, int64_t qp_channels, const vsiq_qparams *qp2,
+                            int64_t qp2_channels, void *workspace, size_t workspace_bytes, vsiq_stream_t stream);
 int vsiq_ci_lsq_bwd(const float *x, const float *bias, const float *g, float *dx, void *dscale, int dscale_dtype,
                     void *dzp, int dzp_dtype, float *dbias, int64_t rows, int64_t channels, const vsiq_qparams *qp,
                     int64_t qp_channels, double grad_scale_host, const float *grad_scale_dev, int64_t g_row_pitch,

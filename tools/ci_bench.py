@@ -23,6 +23,7 @@ for shp in shapes:
         ("flat fwd pt", 8, lambda: ops.fake_quant_forward(x, s_t, 0, pt, out=y)),
         ("ci fwd pt+b", 8, lambda: ops.ci_forward(x, b, s_t, 0, pt, out=y)),
         ("ci fwd pc+b", 8, lambda: ops.ci_forward(x, b, sc, zc, pc, out=y)),
+        ("ci fwd2 (y + next layer's quantize_inp)", 12, lambda: ops.ci_forward(x, b, sc, zc, pc, out=y, second=(s_t, 0, ops.QSpec(-8, 7)))),
         ("flat lsq pt", 12, lambda: ops.lsq_backward(x, g, s_t, 0, pt, 1e-3)),
         ("ci lsq pt+b", 12, lambda: ops.ci_backward(x, b, g, s_t, 0, pt, 1e-3)),
         ("ci lsq pc+b", 12, lambda: ops.ci_backward(x, b, g, sc, zc, pc, 1e-3, None, True, True, True)),

@@ -87,6 +87,8 @@ _SIGNATURES = {
     "vsiq_ci_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "vsiq_ci_fake_quant_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, ctypes.POINTER(QParams), c_int64,
                                        c_void_p, c_size_t, c_void_p]),
+    "vsiq_ci_fake_quant_fwd2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, ctypes.POINTER(QParams),
+                                        c_int64, ctypes.POINTER(QParams), c_int64, c_void_p, c_size_t, c_void_p]),
     "vsiq_ci_lsq_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                 c_int64, c_int64, ctypes.POINTER(QParams), c_int64, c_double, c_void_p, c_int64, c_void_p,
                                 c_size_t, c_void_p]),

@@ -207,6 +207,84 @@ __global__ void __launch_bounds__(kThreads, 3)  // 80 registers, 3 CTAs per SM: 
     if (geo.sched == kCiDynamic) ci_leave(ws);
 }
 
+// Two outputs from one pass: y = fq1(act(x + bias[c])) (this layer's quantised output) and y2 = fq2(y), the SAME tensor
+// as the next layer's `quantize_inp` step would produce from y with ITS activation quantiser (fake_quantize.py:44-45:
+// `if self.quantize_inp: x = self.quantize_activation(x)`).  The second stage quantises the value that is about to be
+// stored, so it is bit-identical to a separate fake-quant launch over y, for 4 more bytes per element instead of 8
+// and one launch less.  Two CTAs per SM: the second set of qparams lives in registers next to the first.
+template <bool PCQ, bool BIAS, int ACT, bool PCQ2>
+__global__ void __launch_bounds__(kThreads, 2)
+    ci_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y,
+                   float* __restrict__ y2, CiGeom geo, QPDev qpd, QPDev qpd2, void* ws) {
+    const int t = threadIdx.x;
+    const bool active = t < geo.threads;
+    const int c0 = (t % geo.groups) * kCiVec;
+    constexpr int kU = 2 * kCiUnroll;
+    __shared__ uint32_t s_tile[2];
+    CiSched sc;
+    CiRange r = ci_sched_first(geo, sc, ws, s_tile, t);
+    QP p[kCiVec], p2[kCiVec];
+    float bv[kCiVec];
+    bool all_fast = true, all_fast2 = true;
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        p[e] = load_qp(qpd, PCQ ? c0 + e : 0);
+        p2[e] = load_qp(qpd2, PCQ2 ? c0 + e : 0);
+        all_fast = all_fast && p[e].fast;
+        all_fast2 = all_fast2 && p2[e].fast;
+        bv[e] = (BIAS && active) ? __ldg(bias + c0 + e) : 0.0f;
+    }
+    const uint32_t seed = guard_seed(all_fast), seed2 = guard_seed(all_fast2);
+    const int64_t stride = (int64_t)geo.threads * kCiVec;
+    const int64_t dy = y - x, dy2 = y2 - x;
+    for (;;) {
+        if (active) {
+            const float* xp = x + ((int64_t)r.s0 * geo.threads + t) * kCiVec;
+#pragma unroll 1
+            for (uint32_t s = r.s0; s < r.s1; s += kU, xp += kU * stride) {
+                Vec4 vin[kU];
+#pragma unroll
+                for (int j = 0; j < kU; ++j)
+                    if (s + j < r.s1) vin[j] = ld4(xp + j * stride);
+#pragma unroll
+                for (int j = 0; j < kU; ++j) {
+                    if (s + j >= r.s1) continue;
+                    Vec4 out, out2;
+                    FastGuard guard, guard2;
+                    guard_reset(guard, seed);
+                    guard_reset(guard2, seed2);
+#pragma unroll
+                    for (int e = 0; e < kCiVec; ++e) {
+                        const float xe = act_fwd<ACT>(BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e]);
+                        guard_note(guard, xe);
+                        out.v[e] = dequant(elem_fast(xe, p[e]).q, p[e]);
+                    }
+                    if (guard_bad(guard)) {
+#pragma unroll
+                        for (int e = 0; e < kCiVec; ++e) {
+                            const float xe = act_fwd<ACT>(BIAS ? __fadd_rn(vin[j].v[e], bv[e]) : vin[j].v[e]);
+                            out.v[e] = dequant(elem_slow(xe, p[e]).q, p[e]);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < kCiVec; ++e) {
+                        guard_note(guard2, out.v[e]);
+                        out2.v[e] = dequant(elem_fast(out.v[e], p2[e]).q, p2[e]);
+                    }
+                    if (guard_bad(guard2)) {
+#pragma unroll
+                        for (int e = 0; e < kCiVec; ++e) out2.v[e] = dequant(elem_slow(out.v[e], p2[e]).q, p2[e]);
+                    }
+                    st4(const_cast<float*>(xp) + j * stride + dy, out);
+                    st4(const_cast<float*>(xp) + j * stride + dy2, out2);
+                }
+            }
+        }
+        if (!ci_sched_next(geo, sc, s_tile, t, r)) break;
+    }
+    if (geo.sched == kCiDynamic) ci_leave(ws);
+}
+
 // ------------------------------------------------------------------------------ BatchNorm normalise (+ ReLU)
 // y = act(x * a[c] + b[c]),  a = gamma / sqrt(var + eps),  b = beta - mean * a: what training-mode BatchNorm computes for
 // a layer that kept its BN (is_fuse_bn=False) once the batch moments are known -- the second half of every layer of
@@ -743,6 +821,40 @@ extern "C" int vsiq_ci_fake_quant_fwd(const float* x, const float* bias, float* 
 #define F2(P, B) { if (act == kActRelu) F(P, B, kActRelu); else if (act == kActSilu) F(P, B, kActSilu); else F(P, B, kActNone); }
     if (pcq) { if (hb) F2(true, true) else F2(true, false) } else { if (hb) F2(false, true) else F2(false, false) }
 #undef F2
+#undef F
+    return (int)cudaGetLastError();
+}
+
+extern "C" int vsiq_ci_fake_quant_fwd2(const float* x, const float* bias, float* y, float* y2, int64_t rows,
+                                       int64_t channels, const vsiq_qparams* qp, int64_t qp_channels,
+                                       const vsiq_qparams* qp2, int64_t qp2_channels, void* workspace,
+                                       size_t workspace_bytes, vsiq_stream_t stream) {
+    QPDev qpd, qpd2;
+    if (int e = fill_qp(qp, &qpd)) return e;
+    if (int e = fill_qp(qp2, &qpd2)) return e;
+    if (qp2->pre_op != VSIQ_PRE_NONE) return VSIQ_ERR_INVALID_ARG;  // the second stage quantises y as it is
+    if (rows == 0) return VSIQ_OK;
+    if (!x || !y || !y2 || y == y2) return VSIQ_ERR_INVALID_ARG;
+    if (qp_channels != 1 && qp_channels != channels) return VSIQ_ERR_INVALID_ARG;
+    if (qp2_channels != 1 && qp2_channels != channels) return VSIQ_ERR_INVALID_ARG;
+    CiGeom geo;
+    if (!make_ci_geom(rows, channels, &geo)) return VSIQ_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(y2)) & 15u)
+        return VSIQ_ERR_UNSUPPORTED;
+    DeviceProps dp;
+    if (int e = get_device_props(&dp)) return e;
+    const int grid = ci_pick_grid(&geo, dp.sm_count, 2, 2 * kCiUnroll);
+    if (geo.sched == kCiDynamic && (!workspace || workspace_bytes < kWsHeader)) return VSIQ_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool pcq = qp_channels == channels && channels > 1, pcq2 = qp2_channels == channels && channels > 1;
+    const bool hb = bias != nullptr;
+    const int act = qp->pre_op;
+#define F(P, B, A, Q) ci_fwd2_kernel<P, B, A, Q><<<grid, kThreads, 0, st>>>(x, bias, y, y2, geo, qpd, qpd2, workspace)
+#define F1(P, B, A) { if (pcq2) F(P, B, A, true); else F(P, B, A, false); }
+#define F2(P, B) { if (act == kActRelu) F1(P, B, kActRelu) else if (act == kActSilu) F1(P, B, kActSilu) else F1(P, B, kActNone) }
+    if (pcq) { if (hb) F2(true, true) else F2(true, false) } else { if (hb) F2(false, true) else F2(false, false) }
+#undef F2
+#undef F1
 #undef F
     return (int)cudaGetLastError();
 }

@@ -118,16 +118,34 @@ class ConvBnReLU(_ConvBase):
                 and not (self._bn_reestimate is not None and not self.is_fuse_bn)):
             return super().forward(x)
         if self.quantize_inp:
-            x = self.quantize_activation(x)
+            x = self.quantize_input(x)
         weights, bias = self.get_weight_bias()
         weights = self.quantize_weights(weights)
+        consumer = self.__dict__.get("_inp_consumer")
+        if consumer is not None and not consumer.quantize_inp:
+            consumer = None
         if (self.fuse_bias_into_quant and bias is not None and self.is_fuse_bn and x.dim() == 4 and not x.is_contiguous()
                 and x.is_contiguous(memory_format=torch.channels_last)):
             pre = self._conv(x, weights, None)  # bias-free conv; the epilogue adds the bias and returns its gradient
             if ops.ci_supported(pre):
-                return self.activation_quantizer.quantize(pre, pre_act=act, bias=bias)
+                return self._quantize_out(pre, act, bias, consumer)
             return self.activation_quantizer.quantize(pre + bias.view(1, -1, 1, 1), pre_act=act)
-        return self.activation_quantizer.quantize(self._pre_activation(x, weights, bias), pre_act=act)
+        pre = self._pre_activation(x, weights, bias)
+        if consumer is not None and ops.ci_supported(pre):
+            return self._quantize_out(pre, act, None, consumer)
+        return self.activation_quantizer.quantize(pre, pre_act=act)
+
+    def _quantize_out(self, pre, act, bias, consumer):
+        """Output epilogue over a channels_last conv result; with a linked ``quantize_inp`` consumer
+        (feed_input_quantizer_of) the same pass also writes that layer's input quantisation."""
+        plan = consumer.activation_quantizer.prequant_plan(pre) if consumer is not None else None
+        if plan is None or not self.activation_quantizer.can_emit_second(act, pre):
+            return self.activation_quantizer.quantize(pre, pre_act=act, bias=bias)
+        sink: list = []
+        y = self.activation_quantizer.quantize(pre, pre_act=act, bias=bias, second=plan + (sink,))
+        if sink:
+            self._offer_prequant(y, sink[0], consumer)
+        return y
 
 
 class ConvBn(ConvBnReLU):

@@ -396,8 +396,11 @@ def _ci_qparams(spec: QSpec, scale, zero_point, C: int, device, keep: list):
 
 
 def ci_forward(x: torch.Tensor, bias: Optional[torch.Tensor], scale, zero_point, spec: QSpec,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = fq(act(x + bias[c])) on a channels_last tensor, in place of layout conversions (vsiq_ci_fake_quant_fwd)."""
+               out: Optional[torch.Tensor] = None, second: Optional[tuple] = None):
+    """y = fq(act(x + bias[c])) on a channels_last tensor, in place of layout conversions (vsiq_ci_fake_quant_fwd).
+
+    second = (scale2, zero_point2, spec2): also y2 = fq2(y), the next layer's ``quantize_inp`` result
+    (fake_quantize.py:44-45), written by the same pass (vsiq_ci_fake_quant_fwd2); returns (y, y2)."""
     if not ci_supported(x):
         raise ValueError("ci_forward needs a float32 CUDA channels_last tensor with C % 4 == 0 and C <= 1024")
     N, C, H, W = x.shape
@@ -412,6 +415,17 @@ def ci_forward(x: torch.Tensor, bias: Optional[torch.Tensor], scale, zero_point,
                 raise ValueError("bias must have one entry per channel")
         y = _out_like(x, out, "out")
         ws = _workspace(lib.vsiq_ci_workspace_bytes(rows, C), x.device)
+        if second is not None:
+            s2, z2, spec2 = second
+            if spec2.pre_relu or spec2.pre_silu:
+                raise ValueError("the second quantiser of a two-output pass has no activation of its own")
+            qp2, qpc2 = _ci_qparams(spec2, s2, z2, C, x.device, keep)
+            y2 = torch.empty_like(x)
+            check(lib.vsiq_ci_fake_quant_fwd2(x.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
+                                              y2.data_ptr(), rows, C, ctypes.byref(qp), qpc, ctypes.byref(qp2), qpc2,
+                                              ws.data_ptr(), ws.numel(), _stream_ptr()), "vsiq_ci_fake_quant_fwd2")
+            _count_launch()
+            return y, y2
         check(lib.vsiq_ci_fake_quant_fwd(x.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(), rows, C,
                                          ctypes.byref(qp), qpc, ws.data_ptr(), ws.numel(), _stream_ptr()),
               "vsiq_ci_fake_quant_fwd")
@@ -685,20 +699,35 @@ class HostPipeline:
 # ----------------------------------------------------------------------------------------------
 # autograd
 # ----------------------------------------------------------------------------------------------
+class Precomputed:
+    """Holder for a forward result some other kernel already produced (the two-output epilogue): handed to
+    FakeQuantFixed / FakeQuantLearned in place of a launch.  Not a tensor argument, so autograd sees a fresh output."""
+    __slots__ = ("tensor",)
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+
+    def take(self, x: torch.Tensor) -> torch.Tensor:
+        t, self.tensor = self.tensor, None
+        if t is None or t.shape != x.shape or t.dtype != x.dtype or t.device != x.device:
+            raise ValueError("precomputed fake-quant result does not match the tensor it stands for")
+        return t
+
+
 class FakeQuantFixed(torch.autograd.Function):
     """Fake-quant with constant qparams; STE backward.  (uniform.py:54-55 with is_learning_scale=False)"""
 
     @staticmethod
-    def forward(ctx, x, scale, zero_point, spec: QSpec):
+    def forward(ctx, x, scale, zero_point, spec: QSpec, pre: Optional[Precomputed] = None):
         ctx.spec, ctx.scale, ctx.zero_point = spec, scale, zero_point
         ctx.save_for_backward(x)
-        return fake_quant_forward(x, scale, zero_point, spec)
+        return pre.take(x) if pre is not None else fake_quant_forward(x, scale, zero_point, spec)
 
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
         dx = fake_quant_backward_ste(x, g, ctx.scale, ctx.zero_point, ctx.spec) if ctx.needs_input_grad[0] else None
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
 class FakeQuantLearned(torch.autograd.Function):
@@ -708,7 +737,8 @@ class FakeQuantLearned(torch.autograd.Function):
     path, [1,C,1,1] fp32 in lsq_module.py); zero_point: same-shaped float tensor, or a Python number."""
 
     @staticmethod
-    def forward(ctx, x, scale, zero_point, spec: QSpec, grad_scale: float, grad_scale_dev):
+    def forward(ctx, x, scale, zero_point, spec: QSpec, grad_scale: float, grad_scale_dev,
+                pre: Optional[Precomputed] = None):
         ctx.spec, ctx.grad_scale, ctx.grad_scale_dev = spec, grad_scale, grad_scale_dev
         ctx.zp_is_tensor = isinstance(zero_point, torch.Tensor)
         ctx.zp_const = None if ctx.zp_is_tensor else zero_point
@@ -716,7 +746,7 @@ class FakeQuantLearned(torch.autograd.Function):
             ctx.save_for_backward(x, scale, zero_point)
         else:
             ctx.save_for_backward(x, scale)
-        return fake_quant_forward(x, scale, zero_point, spec)
+        return pre.take(x) if pre is not None else fake_quant_forward(x, scale, zero_point, spec)
 
     @staticmethod
     def backward(ctx, g):
@@ -730,7 +760,7 @@ class FakeQuantLearned(torch.autograd.Function):
                                   ds_dtype=scale.dtype, dz_dtype=zp.dtype if ctx.zp_is_tensor else torch.float32)
         ds = ds.view(scale.shape).to(scale.device) if ctx.needs_input_grad[1] else None
         dz = dz.view(zp.shape).to(zp.device) if want_dz else None
-        return (dx if ctx.needs_input_grad[0] else None), ds, dz, None, None, None
+        return (dx if ctx.needs_input_grad[0] else None), ds, dz, None, None, None, None
 
 
 class FakeQuantEpilogue(torch.autograd.Function):
@@ -738,7 +768,10 @@ class FakeQuantEpilogue(torch.autograd.Function):
     quantiser as one forward pass, and dx, dbias (the conv's bias gradient), dscale, dzero_point as one backward pass."""
 
     @staticmethod
-    def forward(ctx, x, bias, scale, zero_point, spec: QSpec, grad_scale: float, grad_scale_dev):
+    def forward(ctx, x, bias, scale, zero_point, spec: QSpec, grad_scale: float, grad_scale_dev, second=None):
+        """second = (scale2, zero_point2, spec2, sink): the pass also writes y2 = fq2(y) -- the next layer's
+        quantize_inp result -- and appends it to the list ``sink`` (a plain buffer; its autograd node is the second
+        quantiser's own Function, fed through ops.Precomputed)."""
         ctx.spec, ctx.grad_scale, ctx.grad_scale_dev = spec, grad_scale, grad_scale_dev
         ctx.scale_is_tensor = isinstance(scale, torch.Tensor)
         ctx.zp_is_tensor = isinstance(zero_point, torch.Tensor)
@@ -748,6 +781,11 @@ class FakeQuantEpilogue(torch.autograd.Function):
         saved = [x] + ([bias] if ctx.has_bias else []) + ([scale] if ctx.scale_is_tensor else []) + \
             ([zero_point] if ctx.zp_is_tensor else [])
         ctx.save_for_backward(*saved)
+        if second is not None:
+            s2, z2, spec2, sink = second
+            y, y2 = ci_forward(x, bias, scale, zero_point, spec, second=(s2, z2, spec2))
+            sink.append(y2)
+            return y
         return ci_forward(x, bias, scale, zero_point, spec)
 
     @staticmethod
@@ -767,7 +805,7 @@ class FakeQuantEpilogue(torch.autograd.Function):
         ds = ds.view(scale.shape).to(scale.device) if want_ds else None
         dz = dz.view(zp.shape).to(zp.device) if want_dz else None
         db = db.view(bias.shape) if db is not None else None
-        return (dx if ctx.needs_input_grad[0] else None), db, ds, dz, None, None, None
+        return (dx if ctx.needs_input_grad[0] else None), db, ds, dz, None, None, None, None
 
 
 def lsq_grad_scale(qmax: int, numel: int, channels: int = 1) -> float:

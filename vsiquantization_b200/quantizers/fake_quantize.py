@@ -29,13 +29,39 @@ class FakeQuantize(nn.Module):
 
     def forward(self, x):
         if self.quantize_inp:
-            x = self.quantize_activation(x)
+            x = self.quantize_input(x)
         weights, bias = self.get_weight_bias()
         weights = self.quantize_weights(weights)
         out = self.run_forward_core(x, weights, bias)
         if self.quantize_out:
             out = self.quantize_activation(out)
         return out
+
+    def quantize_input(self, x):
+        """The ``quantize_inp`` step (fake_quantize.py:44-45).  When the layer that produced x was linked to this one
+        (feed_input_quantizer_of) its epilogue has already written this result in the same pass as its own output; the
+        tensor is picked up here instead of launching a fake-quant over x."""
+        pre = self.__dict__.get("_prequant")
+        if pre is not None:
+            self.__dict__["_prequant"] = None
+            if pre[0]() is x:
+                return pre[1]
+        return self.quantize_activation(x)
+
+    def feed_input_quantizer_of(self, consumer: Optional["FakeQuantize"]) -> None:
+        """Link this layer to the (unique or not) layer that consumes its output with ``quantize_inp=True``: this
+        layer's output epilogue then also writes the consumer's input quantisation (two outputs from one pass over the
+        conv result: 12 bytes per element instead of 8 + 8, one launch less).  None removes the link.  Results and
+        gradients are those of the unlinked model bit for bit; whenever the fused form does not apply (observing,
+        quantisers off, NCHW tensors) both layers fall back to their own launches."""
+        if consumer is not None and not hasattr(consumer, "activation_quantizer"):
+            raise TypeError("the consumer must be a fused QAT layer")
+        self.__dict__["_inp_consumer"] = consumer
+
+    def _offer_prequant(self, y, y2_raw, consumer) -> None:
+        import weakref
+        y2 = consumer.activation_quantizer.quantize_precomputed(y, y2_raw)
+        consumer.__dict__["_prequant"] = (weakref.ref(y), y2)
 
     def run_forward_core(self, x, weights, bias):
         raise NotImplementedError

@@ -237,7 +237,40 @@ class QuantizationManager(nn.Module):
                         and x is not None and ops.ci_supported(x))
         return False
 
-    def quantize(self, x, pre_relu: bool = False, bias=None, pre_act=None):
+    def _current_qparams(self):
+        """(scale, zero_point) as quantize() hands them to the plugin: learned Parameters, never-calibrated defaults or
+        host-set values as they are, calibrated fixed qparams from the observer state on the device (no sync)."""
+        if "scale" in self._parameters or "zero_point" in self._parameters or not self._calibrated \
+                or "scale" in self.__dict__:
+            return self.scale, self.zero_point
+        return self.observer.device_qparams()
+
+    def can_emit_second(self, act, x) -> bool:
+        """True when quantize(x, pre_act=act, second=...) will run as the two-output channels_last epilogue."""
+        from .. import ops
+        q = self.quantizer
+        return bool(act is not None and self.can_fuse_act(act, x) and ops.ci_supported(x) and hasattr(q, "kernel_args")
+                    and getattr(q, "mask_mode", "rounded") == "rounded" and self.__dict__.get("_banked") is None)
+
+    def prequant_plan(self, x):
+        """(scale, zero_point, QSpec) for running THIS manager's quantise step as the second stage of another layer's
+        epilogue over the channels_last tensor x (the producer of a ``quantize_inp`` layer's input), or None when it
+        must run on its own: still observing, quantisation switched off, or a plugin / layout without that form."""
+        collecting = (not self.is_learning_scale) and self.is_observer_qparam
+        plan = getattr(self.quantizer, "kernel_args", None)
+        if collecting or not self.is_quantize or plan is None or self.__dict__.get("_banked") is not None:
+            return None
+        s, z = self._current_qparams()
+        return plan(x, s, z, self.is_learning_scale)
+
+    def quantize_precomputed(self, x, y_pre):
+        """quantize(x) whose forward result ``y_pre`` was already written by the producer's two-output epilogue: same
+        autograd node (STE / LSQ backward at x), no forward launch."""
+        from .. import ops
+        s, z = self._current_qparams()
+        return self.quantizer.quantize(x, s, z, self.is_learning_scale, precomputed=ops.Precomputed(y_pre))
+
+    def quantize(self, x, pre_relu: bool = False, bias=None, pre_act=None, second=None):
         """collect (if calibrating) then fake-quantise (if enabled) -- :73-90.  ``pre_act`` ("relu" / "silu"; ``pre_relu``
         is the older spelling of "relu"): x is the pre-activation and the activation is applied here -- fused into the
         quantiser kernels when quantising, as a plain F.relu / F.silu otherwise.  ``bias`` (with an activation,
@@ -257,6 +290,8 @@ class QuantizationManager(nn.Module):
             kw = {"pre_act": act}
             if bias is not None:
                 kw["bias"] = bias
+            if second is not None:
+                kw["second"] = second
             if "scale" in self._parameters or "zero_point" in self._parameters or not self._calibrated \
                     or "scale" in self.__dict__:
                 return self.quantizer.quantize(x, self.scale, self.zero_point, self.is_learning_scale, **kw)

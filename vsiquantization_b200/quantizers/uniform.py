@@ -74,7 +74,22 @@ class UniformQuantizer(BaseQuantizer):
                          pre_relu=pre_relu, pre_silu=pre_silu)
 
     # -- the plugin entry point ------------------------------------------------------------------------
-    def quantize(self, x, scale, zero_point, is_learning_scale=False, pre_relu=False, bias=None, pre_act=None):
+    def kernel_args(self, x, scale, zero_point, is_learning_scale=False):
+        """(scale, zero_point, QSpec) exactly as quantize() hands them to the forward kernel, or None when this
+        quantiser cannot ride along as the SECOND stage of a two-output epilogue over the channels_last tensor x."""
+        if not ops.ci_supported(x):
+            return None
+        ch_axis = self._resolve_axis(x, scale)
+        if ch_axis not in (None, 1):
+            return None
+        zp_tensor = isinstance(zero_point, torch.Tensor)
+        zp_round = zp_tensor and is_learning_scale and not self.symmetric and zero_point.is_floating_point()
+        s = scale.detach() if isinstance(scale, torch.Tensor) else scale
+        z = zero_point.detach() if zp_tensor else zero_point
+        return s, z, self._spec(ch_axis, zp_learned=zp_round)
+
+    def quantize(self, x, scale, zero_point, is_learning_scale=False, pre_relu=False, bias=None, pre_act=None,
+                 second=None, precomputed=None):
         """Fake-quantise x (uniform.py:34-56); with ``pre_relu`` quantise relu(x) in the same pass (the fused layer's
         F.relu, modules/fused.py:133, folded into the kernel; gradients include relu's mask).
 
@@ -87,13 +102,19 @@ class UniformQuantizer(BaseQuantizer):
         pre_relu = bool(pre_relu) or pre_act == "relu"
         pre_silu = pre_act == "silu"
         if not x.is_cuda:
+            if second is not None or precomputed is not None:
+                raise ValueError("two-output epilogue / precomputed results are for CUDA tensors")
             y = self.quantize(_as_cuda(x), scale, zero_point, is_learning_scale, pre_relu, bias, "silu" if pre_silu else None)
             return y.to(x.device)
         ch_axis = self._resolve_axis(x, scale)
-        if bias is not None or pre_silu:
+        if bias is not None or pre_silu or second is not None:
             # SiLU (x / (1 + exp(-x)), the fused layer's F.silu of modules/fused.py:133) exists in the channels_last
-            # epilogue kernels only
-            return self._quantize_epilogue(x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis, pre_silu)
+            # epilogue kernels only; ``second`` = (scale2, zero_point2, spec2, sink): the same pass also writes the next
+            # layer's quantize_inp result (fake_quantize.py:44-45) into sink
+            if precomputed is not None:
+                raise ValueError("a precomputed result replaces a plain fake-quant launch, not an epilogue")
+            return self._quantize_epilogue(x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis, pre_silu,
+                                           second=second)
         scale_learn = isinstance(scale, torch.Tensor) and scale.requires_grad and torch.is_grad_enabled()
         zp_tensor = isinstance(zero_point, torch.Tensor)
         # the reference rounds / clamps a tensor zero-point only on the asymmetric learning path (uniform.py:50-52)
@@ -102,7 +123,8 @@ class UniformQuantizer(BaseQuantizer):
         if not (scale_learn or zp_learn):
             s = scale.detach() if isinstance(scale, torch.Tensor) else scale
             z = zero_point.detach() if zp_tensor else zero_point
-            return ops.FakeQuantFixed.apply(x, s, z, self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu))
+            return ops.FakeQuantFixed.apply(x, s, z, self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu),
+                                            precomputed)
         if not isinstance(scale, torch.Tensor):
             raise TypeError("a learnable zero_point needs a tensor scale")
         C = scale.numel()
@@ -117,9 +139,10 @@ class UniformQuantizer(BaseQuantizer):
                 gs_host *= float(cgs)
         zp_arg = zero_point if zp_learn else (zero_point.detach() if zp_tensor else zero_point)
         return ops.FakeQuantLearned.apply(x, scale, zp_arg, self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu),
-                                          gs_host, gs_dev)
+                                          gs_host, gs_dev, precomputed)
 
-    def _quantize_epilogue(self, x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis, pre_silu=False):
+    def _quantize_epilogue(self, x, bias, scale, zero_point, is_learning_scale, pre_relu, ch_axis, pre_silu=False,
+                           second=None):
         """fq(act(x + bias)) on a channels_last conv output (ops.FakeQuantEpilogue); bias gradient from the same pass."""
         if not ops.ci_supported(x):
             raise ValueError("bias / SiLU fusion needs a channels_last float32 CUDA tensor with C % 4 == 0 and C <= 1024")
@@ -141,7 +164,7 @@ class UniformQuantizer(BaseQuantizer):
         s_arg = scale if scale_learn else (scale.detach() if isinstance(scale, torch.Tensor) else scale)
         z_arg = zero_point if zp_learn else (zero_point.detach() if zp_tensor else zero_point)
         spec = self._spec(ch_axis, zp_learned=zp_round, pre_relu=pre_relu, pre_silu=pre_silu)
-        return ops.FakeQuantEpilogue.apply(x, bias, s_arg, z_arg, spec, gs_host, gs_dev)
+        return ops.FakeQuantEpilogue.apply(x, bias, s_arg, z_arg, spec, gs_host, gs_dev, second)
 
     def quantize_codes(self, x, scale, zero_point, code_bits: Optional[int] = None):
         """(fake-quantised tensor, integer codes) -- the reference keeps codes as floats (uniform.py:54).  int8 / uint8
