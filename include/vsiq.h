@@ -171,6 +171,18 @@ size_t vsiq_observe_workspace_bytes(const vsiq_layout *layout);
 int vsiq_observe(const float *x, const vsiq_layout *layout, double *stats, double *state, int bits,
                  int symmetric, double eps, void *workspace, size_t workspace_bytes, vsiq_stream_t stream);
 
+/* Calibration epilogue of a fused layer on a channel-innermost tensor: y = act(pre(x)) written AND observed (per tensor)
+ * in one pass -- the fused layer's bias add / inference-mode BatchNorm + ReLU / SiLU (modules/fused.py:124-134) followed by
+ * quantize_activation -> collect_qparameter -> observer.observe(y) (quantizers/quantization_manager.py:55-71,
+ * observers/minmax.py:32-47).  pre: `bias` (x + bias[c]) or `mean`/`var`/`gamma`/`beta`/`bn_eps`
+ * (x * a[c] + b[c], a = gamma / sqrt(var + eps), b = beta - mean * a, as vsiq_ci_bn_normalize), or neither; never both.
+ * act: VSIQ_PRE_NONE / _RELU / _SILU.  stats / state / bits / symmetric / eps as vsiq_observe with a per-tensor layout.
+ * 8 bytes per element instead of 8 + 4 (or ATen's 8 + 8 + 4).  Workspace: vsiq_ci_observe_workspace_bytes(). */
+int vsiq_ci_epilogue_observe(const float *x, const float *bias, const float *mean, const float *var, const float *gamma,
+                             const float *beta, float bn_eps, int act, float *y, int64_t rows, int64_t channels,
+                             double *stats, double *state, int bits, int symmetric, double eps, void *workspace,
+                             size_t workspace_bytes, vsiq_stream_t stream);
+
 /* scale / zero-point for n observers at once from their running extrema (after an all-reduce MIN/MAX
  * of the packed state, see parallel.py): state is [n][VSIQ_STATE_WIDTH]; columns 2,3 are rewritten.
  * bits / symmetric: one entry per observer (device int32 arrays) -- observers/minmax.py:67-74. */

@@ -96,6 +96,8 @@ _SIGNATURES = {
     "vsiq_ci_observe_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "vsiq_ci_observe": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_size_t,
                                 c_void_p]),
+    "vsiq_ci_epilogue_observe": (c_int, [c_void_p] * 6 + [c_float, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                         c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
     "vsiq_selftest_division": (c_int, [c_float, c_int, c_void_p, c_void_p]),
     "vsiq_mt_plan": (c_int, [ctypes.POINTER(MtEntry), c_int, ctypes.POINTER(ctypes.c_uint32)]),
     "vsiq_mt_fake_quant_fwd": (c_int, [ctypes.POINTER(MtEntry), c_void_p, c_int, c_void_p, c_void_p]),

@@ -490,6 +490,100 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// Calibration epilogue of a fused layer on channels_last memory: y = act(pre(x)) written AND observed in the same pass
+// (per-tensor observer of the layer's output: running min / max, scale / zero-point, the LSQ-init statistics).
+//   PRE 0: y = act(x)
+//   PRE 1: y = act(x + bias[c])                the BN-folded layer's conv bias (modules/fused.py:124-130)
+//   PRE 2: y = act(x * a[c] + b[c])            inference-mode BatchNorm of a layer that kept its BN (fused.py:131-134),
+//                                              a = gamma / sqrt(var + eps), b = beta - mean * a  (as ci_affine_kernel)
+// then quantize_activation -> collect_qparameter -> observer.observe(y) (quantization_manager.py:55-71,
+// observers/minmax.py:32-47).  ATen + a separate observer launch move 8 + 8 + 4 (bias form: relu pass; BN form:
+// batch_norm + relu) or, with vsiq_ci_bn_normalize, 8 + 4 bytes per element; this kernel moves 8.  The values of y are
+// those of the separate passes bit for bit, min / max are exact, the three sums are fp64 sums of 8-element fp32
+// partials like every other observer kernel here (a different summation order, same error class).
+template <int PRE, int ACT>
+__global__ void __launch_bounds__(kThreads, 3)
+    ci_epilogue_observe_kernel(const float* __restrict__ x, const float* __restrict__ p0, const float* __restrict__ var,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                               float* __restrict__ y, CiGeom geo, void* ws, ObserveOut o) {
+    __shared__ double s_red[kWarps][kPartialWidth];
+    __shared__ uint32_t s_tile[2];
+    const int t = threadIdx.x;
+    const bool active = t < geo.threads;
+    const int c0 = (t % geo.groups) * kCiVec;
+    constexpr int kU = 2 * kCiUnroll;
+    CiSched sc;
+    CiRange r = ci_sched_first(geo, sc, ws, s_tile, t);
+    float a[kCiVec], b[kCiVec];
+#pragma unroll
+    for (int e = 0; e < kCiVec; ++e) {
+        const int c = active ? c0 + e : 0;
+        a[e] = 1.0f;
+        b[e] = 0.0f;
+        if (PRE == 1) b[e] = __ldg(p0 + c);
+        if (PRE == 2) {
+            const float g = gamma ? __ldg(gamma + c) : 1.0f;
+            a[e] = __fdiv_rn(g, __fsqrt_rn(__fadd_rn(__ldg(var + c), eps)));
+            b[e] = __fsub_rn(beta ? __ldg(beta + c) : 0.0f, __fmul_rn(__ldg(p0 + c), a[e]));
+        }
+    }
+    StatsOp op;
+    op.reset();
+    const int64_t stride = (int64_t)geo.threads * kCiVec;
+    const int64_t dy = y - x;
+    for (;;) {
+        if (active) {
+            const float* xp = x + ((int64_t)r.s0 * geo.threads + t) * kCiVec;
+#pragma unroll 1
+            for (uint32_t s = r.s0; s < r.s1; s += kU, xp += kU * stride) {
+                Vec4 vin[kU];
+#pragma unroll
+                for (int j = 0; j < kU; ++j)
+                    if (s + j < r.s1) vin[j] = ld4(xp + j * stride);
+#pragma unroll
+                for (int j = 0; j < kU; ++j) {
+                    if (s + j < r.s1) {
+                        Vec4 out;
+#pragma unroll
+                        for (int e = 0; e < kCiVec; ++e) {
+                            float v = vin[j].v[e];
+                            if (PRE == 1) v = __fadd_rn(v, b[e]);
+                            if (PRE == 2) v = __fmaf_rn(v, a[e], b[e]);
+                            v = act_fwd<ACT>(v);
+                            out.v[e] = v;
+                            op.mn = min_nan(op.mn, v);
+                            op.mx = max_nan(op.mx, v);
+                            op.fa += fabsf(v);
+                            op.f1 += v;
+                            op.f2 = fmaf(v, v, op.f2);
+                        }
+                        st4(const_cast<float*>(xp) + j * stride + dy, out);
+                    }
+                    if (j & 1) op.vec_done();  // fp32 partials of 8 elements, then fp64
+                }
+            }
+        }
+        if (!ci_sched_next(geo, sc, s_tile, t, r)) break;
+    }
+    double rec[kPartialWidth];
+    stats_group_reduce<kThreads>(op, rec, s_red);
+    double* partials = ws_partials(ws);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < kPartialWidth; ++k) partials[(size_t)blockIdx.x * kPartialWidth + k] = rec[k];
+    }
+    if (!last_cta_ticket((unsigned int*)ws, threadIdx.x == 0)) return;
+    if (threadIdx.x == 0) *((unsigned int*)ws + 1) = 0;  // tile counter of the dynamic schedule
+    Tiles recs;
+    recs.rows = 1;
+    recs.channels = 1;
+    recs.inner = 0;
+    recs.chunks = gridDim.x;
+    recs.n_tiles = gridDim.x;
+    recs.tile = 0;
+    observe_combine<kThreads>(partials, recs, 1, 0, o, s_red);
+}
+
 // MODE 0: thread per channel, 1: warp per channel, 2: CTA per channel
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
@@ -717,6 +811,41 @@ extern "C" int vsiq_ci_observe(const float* x, int64_t rows, int64_t channels, d
     const int fgrid = (int)((channels + kCombineEntries - 1) / kCombineEntries);
     return (int)launch_pdl(ci_observe_finalize_kernel, dim3(fgrid), dim3(kThreads), 0, st, (const void*)workspace,
                            (int)channels, grid, oo);
+}
+
+extern "C" int vsiq_ci_epilogue_observe(const float* x, const float* bias, const float* mean, const float* var,
+                                        const float* gamma, const float* beta, float bn_eps, int act, float* y,
+                                        int64_t rows, int64_t channels, double* stats, double* state, int bits,
+                                        int symmetric, double eps, void* workspace, size_t workspace_bytes,
+                                        vsiq_stream_t stream) {
+    if (!x || !y || (!stats && !state) || rows <= 0) return VSIQ_ERR_INVALID_ARG;
+    if (state && (bits < 2 || bits > 8)) return VSIQ_ERR_INVALID_ARG;
+    if (bias && (mean || var)) return VSIQ_ERR_INVALID_ARG;  // one pre-op: bias add OR BatchNorm
+    if ((mean == nullptr) != (var == nullptr)) return VSIQ_ERR_INVALID_ARG;
+    if (act != VSIQ_PRE_NONE && act != VSIQ_PRE_RELU && act != VSIQ_PRE_SILU) return VSIQ_ERR_INVALID_ARG;
+    CiGeom geo;
+    if (!make_ci_geom(rows, channels, &geo)) return VSIQ_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return VSIQ_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < vsiq_ci_observe_workspace_bytes(rows, channels)) return VSIQ_ERR_WORKSPACE;
+    DeviceProps dp;
+    if (int e = get_device_props(&dp)) return e;
+    const uint32_t grid = (uint32_t)ci_pick_grid(&geo, dp.sm_count, 3, 2 * kCiUnroll);
+    cudaStream_t st = (cudaStream_t)stream;
+    ObserveOut oo;
+    oo.stats = stats;
+    oo.state = state;
+    oo.bits = bits;
+    oo.symmetric = symmetric;
+    oo.eps = eps;
+    oo.count = (double)rows * (double)channels;  // per-tensor statistics
+    const int pre = mean ? 2 : (bias ? 1 : 0);
+    const float* p0 = mean ? mean : bias;
+#define K(P, A) ci_epilogue_observe_kernel<P, A><<<grid, kThreads, 0, st>>>(x, p0, var, gamma, beta, bn_eps, y, geo, workspace, oo)
+#define KA(P) { if (act == VSIQ_PRE_RELU) K(P, kActRelu); else if (act == VSIQ_PRE_SILU) K(P, kActSilu); else K(P, kActNone); }
+    if (pre == 2) KA(2) else if (pre == 1) KA(1) else KA(0)
+#undef KA
+#undef K
+    return (int)cudaGetLastError();
 }
 
 extern "C" int vsiq_qparams_from_minmax(double* state, int64_t n, const int32_t* bits, const int32_t* symmetric,

@@ -107,11 +107,51 @@ class ConvBnReLU(_ConvBase):
         # the reference applies SiLU when relu is not an nn.ReLU -- including relu=None (ConvBn overrides this)
         return F.relu(x) if self.is_relu else F.silu(x)
 
+    fuse_observer_into_epilogue = True  # calibration: bias / BN + activation + output observer as ONE NHWC pass
+
+    def _calibration_forward(self, x, act):
+        """The calibration forward (calibrate_qat_model: observers on, quantisation off, no autograd) of a layer on
+        channels_last memory: conv, then ONE pass that adds the bias (or applies the inference-mode BN the layer kept),
+        applies the activation, writes the result and feeds the output observer -- instead of bias / BN + activation
+        passes followed by an observer pass (fused.py:124-134, quantization_manager.py:55-71).  None = not applicable
+        (nothing has been touched yet): the caller runs the ordinary forward."""
+        aq = self.activation_quantizer
+        collecting = (not aq.is_learning_scale) and aq.is_observer_qparam
+        obs = aq.observer
+        if (not collecting or aq.is_quantize or torch.is_grad_enabled() or not hasattr(obs, "observe_epilogue")
+                or getattr(obs, "ch_axis", None) is not None or x.dim() != 4 or not x.is_cuda or x.is_contiguous()
+                or not x.is_contiguous(memory_format=torch.channels_last)):
+            return None
+        if not self.is_fuse_bn and (self.bn.training or self.bn.running_mean is None):
+            return None
+        if self.quantize_inp:
+            x = self.quantize_input(x)
+        weights, bias = self.get_weight_bias()
+        weights = self.quantize_weights(weights)
+        fn = F.relu if act == "relu" else F.silu
+        if self.is_fuse_bn:
+            pre = self._conv(x, weights, None)  # the epilogue adds the bias, as in the training step
+            y = aq.collect_epilogue(pre, act, bias=bias)
+            if y is None:
+                y = aq.quantize(fn(pre if bias is None else pre + bias.view(1, -1, 1, 1)))
+            return y
+        pre = self._conv(x, weights, bias)
+        bn = self.bn
+        y = aq.collect_epilogue(pre, act, bn=(bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.eps))
+        if y is None:
+            y = aq.quantize(fn(bn(pre)))
+        return y
+
     def forward(self, x):
         """fake_quantize.py:43-51 with the activation folded into the output quantiser when that is possible: ReLU in
         every layout, SiLU (what the reference applies whenever ``relu`` is not an nn.ReLU, fused.py:81,133) on
         channels_last tensors."""
         act = "relu" if self.is_relu else "silu"
+        if (self.fuse_observer_into_epilogue and self._has_act and self.quantize_out and self._bn_reestimate is None
+                and type(self).run_forward_core is ConvBnReLU.run_forward_core):
+            y = self._calibration_forward(x, act)
+            if y is not None:
+                return y
         if not (self.fuse_relu_into_quant and self._has_act and self.quantize_out
                 and type(self).run_forward_core is ConvBnReLU.run_forward_core
                 and self.activation_quantizer.can_fuse_relu()

@@ -131,6 +131,18 @@ class MinMaxObserver(BaseObserver):
         self.last_count = x.numel() // st.shape[0]
         self._host = None
 
+    def observe_epilogue(self, pre, act=None, bias=None, bn=None):
+        """observe(act(pre + bias)) / observe(act(BatchNorm_eval(pre))) with the activated tensor written by the SAME
+        pass (ops.ci_epilogue_observe): returns it, or None when this observer / tensor has no such form (per-channel
+        statistics, NCHW memory) and the caller must run its separate passes."""
+        if self.ch_axis is not None or not ops.ci_supported(pre) or pre.requires_grad:
+            return None
+        st = self._ensure_state(pre)
+        y, self.last_stats = ops.ci_epilogue_observe(pre, st, self.num_bits, self.symmetric, self.eps, act, bias, bn)
+        self.last_count = pre.numel()
+        self._host = None
+        return y
+
     def get_scale_zero_point(self):
         """(scale, zero_point) as Python float / int like observers/minmax.py:49-74 (per tensor), or two
         [C] tensors (per channel).  Before anything was observed the state is min = max = 0."""

@@ -524,6 +524,47 @@ def _ci_observe(x, state, bits, symmetric, eps, want_stats):
     return stats
 
 
+def ci_epilogue_observe(x: torch.Tensor, state: torch.Tensor, bits: int = 8, symmetric: bool = True, eps: float = 1e-8,
+                        act: Optional[str] = None, bias: Optional[torch.Tensor] = None, bn: Optional[tuple] = None,
+                        want_stats: bool = True):
+    """(y, stats): y = act(x + bias[c]) or act(BatchNorm_eval(x)) or act(x) on a channels_last conv output, written and
+    observed PER TENSOR in the same pass (vsiq_ci_epilogue_observe): the calibration forward of a fused layer
+    (modules/fused.py:124-134 then quantization_manager.py:55-71) at 8 bytes per element.
+    bn = (running_mean, running_var, weight, bias, eps); act = None / "relu" / "silu"."""
+    if not ci_supported(x):
+        raise ValueError("ci_epilogue_observe needs a float32 CUDA channels_last tensor with C % 4 == 0 and C <= 1024")
+    if bias is not None and bn is not None:
+        raise ValueError("one pre-op: a bias add or a BatchNorm, not both")
+    N, C, H, W = x.shape
+    rows = N * H * W
+    code = {None: _lib.PRE_NONE, "relu": _lib.PRE_RELU, "silu": _lib.PRE_SILU}[act]
+    f32 = lambda t: None if t is None else t.detach().to(device=x.device, dtype=torch.float32).contiguous()  # noqa: E731
+    ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    with torch.cuda.device(x.device):
+        if state.dtype != torch.float64 or not state.is_cuda or state.numel() != _lib.STATE_WIDTH or not state.is_contiguous():
+            raise ValueError("a per-tensor observer state is a contiguous CUDA float64 tensor [1, 8]")
+        stats = torch.empty(1, _lib.STATS_WIDTH, dtype=torch.float64, device=x.device) if want_stats else None
+        b = f32(bias)
+        mean = var = gamma = beta = None
+        bn_eps = 0.0
+        if bn is not None:
+            mean, var, gamma, beta = (f32(t) for t in bn[:4])
+            bn_eps = float(bn[4])
+            if mean is None or var is None:
+                raise ValueError("BatchNorm pre-op needs running_mean and running_var")
+        for t in (b, mean, var, gamma, beta):
+            if t is not None and t.numel() != C:
+                raise ValueError("per-channel operands need one entry per channel")
+        y = torch.empty_like(x)
+        ws = _workspace(lib.vsiq_ci_observe_workspace_bytes(rows, C), x.device)
+        check(lib.vsiq_ci_epilogue_observe(x.data_ptr(), ptr(b), ptr(mean), ptr(var), ptr(gamma), ptr(beta), bn_eps, code,
+                                           y.data_ptr(), rows, C, ptr(stats), state.data_ptr(), int(bits),
+                                           int(bool(symmetric)), float(eps), ws.data_ptr(), ws.numel(), _stream_ptr()),
+              "vsiq_ci_epilogue_observe")
+        _count_launch()
+    return y, stats
+
+
 def qparams_from_minmax(states: torch.Tensor, bits: torch.Tensor, symmetric: torch.Tensor, eps: float = 1e-8) -> None:
     """Recompute scale / zero-point of n observers in place from their running extrema [minmax.py:67-74]."""
     n = states.numel() // _lib.STATE_WIDTH

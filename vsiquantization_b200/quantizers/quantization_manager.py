@@ -222,6 +222,22 @@ class QuantizationManager(nn.Module):
             self._calibrated = True
             self._invalidate()
 
+    def collect_epilogue(self, pre, act=None, bias=None, bn=None):
+        """Calibration form of quantize(act(pre + bias)): while this manager only observes (no quantisation yet) the
+        activation and the observer run as one pass over the conv output.  Returns the activated tensor, or None when
+        the separate passes must run (quantising, not observing, a plugin observer without the fused form)."""
+        collecting = (not self.is_learning_scale) and self.is_observer_qparam
+        fused = getattr(self.observer, "observe_epilogue", None)
+        if not collecting or self.is_quantize or fused is None:
+            return None
+        y = fused(pre, act, bias, bn)
+        if y is None:
+            return None
+        self._call_stats.append((self.observer.last_stats, self.observer.last_count))
+        self._calibrated = True
+        self._invalidate()
+        return y
+
     def can_fuse_relu(self) -> bool:
         """True when quantize(x, pre_relu=True) will run relu + fake-quant as ONE kernel pass."""
         collecting = (not self.is_learning_scale) and self.is_observer_qparam
