@@ -138,3 +138,37 @@ def test_calibrating_layer_is_one_epilogue_pass_and_matches_the_separate_passes(
     n0 = _lib.launch_count
     calibrate_qat_model(twin, batches[:1], lambda m, loader, dev: [m(b) for b in loader])
     assert _lib.launch_count - n0 >= 2
+
+
+def test_bn_reestimation_while_observing_folds_the_observer_into_the_normalise_pass(monkeypatch):
+    """reestimate_BN_stats right after calibrate_qat_model (observers still collecting, utils/estimate_bn.py:79-91): per
+    layer and batch the moments pass, then normalise + ReLU + output observer as ONE pass -- same running statistics and
+    observer state as the separate passes, one launch less."""
+    import copy
+    from vsiquantization_b200 import _lib
+    from vsiquantization_b200.utils.estimate_bn import reestimate_BN_stats
+    from vsiquantization_b200.utils.quantize_manager import calibrate_qat_model
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    torch.manual_seed(4)
+    fused = _layer(False, torch.nn.ReLU)
+    plain = copy.deepcopy(fused)
+    plain.fuse_observer_into_epilogue = False
+    imgs = [(torch.randint(0, 256, (4, 8, 12, 12), dtype=torch.uint8, device="cuda")
+             .contiguous(memory_format=torch.channels_last),) for _ in range(3)]
+
+    def calib(m, loader, dev):
+        with torch.no_grad():
+            return [m(_cl(b[0].float() / 255.0)) for b in loader]
+
+    counts = []
+    for m in (fused, plain):
+        calibrate_qat_model(m, imgs, calib)
+        n0 = _lib.launch_count
+        reestimate_BN_stats(m, imgs, num_batches=3, sync=False)
+        counts.append(_lib.launch_count - n0)
+    assert counts[1] - counts[0] == 3, counts          # the separate output-observer launch of every batch is gone
+    assert torch.equal(fused.bn.running_mean, plain.bn.running_mean)
+    assert torch.equal(fused.bn.running_var, plain.bn.running_var)
+    sf, sp = fused.activation_quantizer.observer.state, plain.activation_quantizer.observer.state
+    assert torch.equal(sf[:, :5], sp[:, :5]) and _close(sf[:, 5:], sp[:, 5:], 2e-6)

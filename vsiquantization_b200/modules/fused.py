@@ -122,12 +122,19 @@ class ConvBnReLU(_ConvBase):
                 or getattr(obs, "ch_axis", None) is not None or x.dim() != 4 or not x.is_cuda or x.is_contiguous()
                 or not x.is_contiguous(memory_format=torch.channels_last)):
             return None
-        if not self.is_fuse_bn and (self.bn.training or self.bn.running_mean is None):
+        reestimating = self._bn_reestimate is not None and not self.is_fuse_bn
+        if self._bn_reestimate is not None and self.is_fuse_bn:
+            return None
+        if not self.is_fuse_bn and not reestimating and (self.bn.training or self.bn.running_mean is None):
             return None
         if self.quantize_inp:
             x = self.quantize_input(x)
         weights, bias = self.get_weight_bias()
         weights = self.quantize_weights(weights)
+        if reestimating:
+            # reestimate_BN_stats while the output observer is still collecting: batch moments (one read), then
+            # normalise + activation + observer as one pass (utils/estimate_bn.py hook)
+            return self._bn_reestimate(self, self._conv(x, weights, bias), act=act, collect=aq)
         fn = F.relu if act == "relu" else F.silu
         if self.is_fuse_bn:
             pre = self._conv(x, weights, None)  # the epilogue adds the bias, as in the training step
@@ -147,7 +154,7 @@ class ConvBnReLU(_ConvBase):
         every layout, SiLU (what the reference applies whenever ``relu`` is not an nn.ReLU, fused.py:81,133) on
         channels_last tensors."""
         act = "relu" if self.is_relu else "silu"
-        if (self.fuse_observer_into_epilogue and self._has_act and self.quantize_out and self._bn_reestimate is None
+        if (self.fuse_observer_into_epilogue and self._has_act and self.quantize_out
                 and type(self).run_forward_core is ConvBnReLU.run_forward_core):
             y = self._calibration_forward(x, act)
             if y is not None:

@@ -42,9 +42,11 @@ def _make_hook(ctx: dict):
     """ctx carries the per-iteration facts the hook needs: ``sync`` (all-reduce the sums), ``weight`` (0.0 when this rank
     only replays a batch to keep the collectives aligned), ``local_images`` / ``global_images`` (this rank's and all
     ranks' image count of the iteration -- the global per-channel element count follows without a per-layer sync)."""
-    def hook(module: ConvBnReLU, x: torch.Tensor, act=None) -> torch.Tensor:
+    def hook(module: ConvBnReLU, x: torch.Tensor, act=None, collect=None) -> torch.Tensor:
         """Moments of this batch -> running sums; returns training-mode BN of x, with ``act`` ("relu" / "silu" / None)
-        applied (the layer hands its activation over so that normalise + ReLU are one pass on channels_last tensors)."""
+        applied (the layer hands its activation over so that normalise + ReLU are one pass on channels_last tensors).
+        ``collect``: the layer's output QuantizationManager while it is only observing -- normalise + activation + its
+        observer then run as ONE pass (vsiq_ci_epilogue_observe) and the returned tensor is the layer's final output."""
         bn = module.bn
         stats = ops.observe(x, ch_axis=1)                      # [C,5]: .., sum x, sum x^2  -- one read of x
         count = float(x.numel() // x.shape[1])
@@ -59,13 +61,20 @@ def _make_hook(ctx: dict):
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         # training-mode BN normalises with the batch mean and the BIASED batch variance
-        if act in (None, "relu") and ops.ci_supported(x):
-            return ops.ci_bn_normalize(x, mean, var_b, bn.weight, bn.bias, bn.eps, relu=act == "relu")
-        y = F.batch_norm(x, mean, var_b, bn.weight, bn.bias, False, 0.0, bn.eps)
-        if act == "relu":
-            return F.relu(y)
-        return F.silu(y) if act == "silu" else y
+        if collect is not None:
+            y = collect.collect_epilogue(x, act, bn=(mean, var_b, bn.weight, bn.bias, bn.eps))
+            return y if y is not None else collect.quantize(_normalise(x, mean, var_b, bn, act))
+        return _normalise(x, mean, var_b, bn, act)
     return hook
+
+
+def _normalise(x, mean, var_b, bn, act):
+    if act in (None, "relu") and ops.ci_supported(x):
+        return ops.ci_bn_normalize(x, mean, var_b, bn.weight, bn.bias, bn.eps, relu=act == "relu")
+    y = F.batch_norm(x, mean, var_b, bn.weight, bn.bias, False, 0.0, bn.eps)
+    if act == "relu":
+        return F.relu(y)
+    return F.silu(y) if act == "silu" else y
 
 
 def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=False, sync=True):
