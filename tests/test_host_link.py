@@ -65,3 +65,14 @@ def test_link_rejects_non_layers():
     import pytest
     with pytest.raises(TypeError):
         _Stub().feed_input_quantizer_of(torch.nn.ReLU())
+
+
+def test_observers_with_their_own_update_rule_keep_their_separate_pass():
+    """The calibration epilogue folds MinMaxObserver.observe into the activation pass; a subclass that overrides observe()
+    (the moving-average observers) must not inherit that shortcut."""
+    from vsiquantization_b200.observers.minmax import LSQObserver, MinMaxObserver
+    from vsiquantization_b200.observers.moving_average import MovingAverageMinMaxObserver
+    x = torch.zeros(1, 4, 2, 2)
+    assert MovingAverageMinMaxObserver().observe_epilogue(x) is None
+    assert type(LSQObserver(True)).observe is MinMaxObserver.observe
+    assert MinMaxObserver(True).observe_epilogue(x) is None      # a CPU / NCHW tensor: not applicable either, no launch

@@ -22,6 +22,7 @@ sc = torch.full((1, C, 1, 1), 0.02, device="cuda")
 zc = torch.full((1, C, 1, 1), 3.3, device="cuda")
 pc = ops.QSpec(0, 255, ch_axis=1, zp_learned=True, pre_relu=True)
 flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+st = ops.new_observer_state(1, x.device)
 for _ in range(reps):
     flush.fill_(1.0)
     y.copy_(x)
@@ -33,5 +34,9 @@ for _ in range(reps):
     ops.ci_backward(x, b, gp, sc, zc, pc, 1e-3, None, True, True, True)
     flush.fill_(1.0)
     ops.observe(x, ch_axis=1)
+    flush.fill_(1.0)
+    ops.ci_forward(x, b, sc, zc, pc, out=y, second=(0.02, 0, ops.QSpec(-8, 7)))   # y + the next layer's quantize_inp
+    flush.fill_(1.0)
+    ops.ci_epilogue_observe(x, st, 8, True, 1e-8, "relu", bias=b)                  # calibration epilogue
 torch.cuda.synchronize()
 print("ok")

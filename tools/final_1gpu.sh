@@ -20,7 +20,7 @@ for s in "512 20" "256 40" "128 80"; do
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches_ci_${s// /x}.csv \
       python tools/ci_ncu_driver.py $s > /dev/null 2>&1
 done
-ncu --set full --clock-control none --import-source on -k regex:"ci_bwd_tma|ci_fwd|ci_observe_kernel" -s 3 -c 3 \
+ncu --set full --clock-control none --import-source on -k regex:"ci_bwd_tma|ci_fwd|ci_observe_kernel|ci_epilogue_observe" -s 6 -c 6 \
     -o $O/${TAG}_full_ci_256x40 python tools/ci_ncu_driver.py 256 40 2 > /dev/null 2>&1
 ncu -i $O/${TAG}_full_ci_256x40.ncu-rep --page raw --csv > $O/${TAG}_ncu_full_ci_256x40_raw.csv 2>/dev/null
 python tools/microbench.py --log2n 22 24 26 28 --iters 10 --per-channel > $O/${TAG}_microbench.log 2>&1

@@ -135,6 +135,8 @@ class MinMaxObserver(BaseObserver):
         """observe(act(pre + bias)) / observe(act(BatchNorm_eval(pre))) with the activated tensor written by the SAME
         pass (ops.ci_epilogue_observe): returns it, or None when this observer / tensor has no such form (per-channel
         statistics, NCHW memory) and the caller must run its separate passes."""
+        if type(self).observe is not MinMaxObserver.observe:
+            return None  # a subclass with its own update rule (moving averages): its observe() must see the tensor
         if self.ch_axis is not None or not ops.ci_supported(pre) or pre.requires_grad:
             return None
         st = self._ensure_state(pre)
