@@ -133,11 +133,29 @@ def test_calibrating_layer_is_one_epilogue_pass_and_matches_the_separate_passes(
     activate_learning_qparam(fused, use_init=True)
     activate_learning_qparam(plain, use_init=True)
     assert _close(fused.activation_quantizer.scale.detach(), plain.activation_quantizer.scale.detach(), 1e-5)
-    # with autograd on (a data_calib callback without no_grad) the ordinary forward runs
+    # with autograd on (the reference's data_calib, yolov8_qat.py:42-52, has no no_grad) the same pass runs behind an
+    # autograd node; a backward through it -- nobody's hot path -- gives the ATen composition's gradients
     twin = _layer(is_fuse_bn, act_cls)
-    n0 = _lib.launch_count
-    calibrate_qat_model(twin, batches[:1], lambda m, loader, dev: [m(b) for b in loader])
-    assert _lib.launch_count - n0 >= 2
+    ref = copy.deepcopy(twin)
+    ref.fuse_observer_into_epilogue = False
+    grads = []
+    for m in (twin, ref):
+        outs = []
+        n0 = _lib.launch_count
+        calibrate_qat_model(m, batches[:1], lambda mm, loader, dev: outs.extend(mm(b) for b in loader))
+        if m is twin:
+            assert _lib.launch_count - n0 == 2
+        assert outs[0].requires_grad
+        (outs[0] * torch.linspace(-1, 1, outs[0].numel(), device="cuda").view_as(outs[0])).sum().backward()
+        grads.append({n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None})
+    assert set(grads[0]) == set(grads[1]) and len(grads[0]) >= 2
+    for n in grads[1]:
+        assert torch.allclose(grads[0][n], grads[1][n], rtol=1e-5, atol=1e-6 * float(grads[1][n].abs().max())), n
+    st_t, st_r = twin.activation_quantizer.observer.state, ref.activation_quantizer.observer.state
+    if is_fuse_bn:
+        assert torch.equal(st_t[:, :4], st_r[:, :4])
+    else:   # with autograd on the separate passes use ATen's batch_norm, an ulp away from x * a[c] + b[c]
+        assert _close(st_t[:, :4], st_r[:, :4], 1e-5)
 
 
 def test_bn_reestimation_while_observing_folds_the_observer_into_the_normalise_pass(monkeypatch):

@@ -110,7 +110,7 @@ class ConvBnReLU(_ConvBase):
     fuse_observer_into_epilogue = True  # calibration: bias / BN + activation + output observer as ONE NHWC pass
 
     def _calibration_forward(self, x, act):
-        """The calibration forward (calibrate_qat_model: observers on, quantisation off, no autograd) of a layer on
+        """The calibration forward (calibrate_qat_model: observers on, quantisation off) of a layer on
         channels_last memory: conv, then ONE pass that adds the bias (or applies the inference-mode BN the layer kept),
         applies the activation, writes the result and feeds the output observer -- instead of bias / BN + activation
         passes followed by an observer pass (fused.py:124-134, quantization_manager.py:55-71).  None = not applicable
@@ -118,7 +118,7 @@ class ConvBnReLU(_ConvBase):
         aq = self.activation_quantizer
         collecting = (not aq.is_learning_scale) and aq.is_observer_qparam
         obs = aq.observer
-        if (not collecting or aq.is_quantize or torch.is_grad_enabled() or not hasattr(obs, "observe_epilogue")
+        if (not collecting or aq.is_quantize or not hasattr(obs, "observe_epilogue")
                 or getattr(obs, "ch_axis", None) is not None or x.dim() != 4 or not x.is_cuda or x.is_contiguous()
                 or not x.is_contiguous(memory_format=torch.channels_last)):
             return None

@@ -137,10 +137,20 @@ class MinMaxObserver(BaseObserver):
         statistics, NCHW memory) and the caller must run its separate passes."""
         if type(self).observe is not MinMaxObserver.observe:
             return None  # a subclass with its own update rule (moving averages): its observe() must see the tensor
-        if self.ch_axis is not None or not ops.ci_supported(pre) or pre.requires_grad:
+        if self.ch_axis is not None or not ops.ci_supported(pre):
             return None
         st = self._ensure_state(pre)
-        y, self.last_stats = ops.ci_epilogue_observe(pre, st, self.num_bits, self.symmetric, self.eps, act, bias, bn)
+        operands = (pre, bias) + (tuple(bn[:4]) if bn is not None else ())
+        if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in operands):
+            # a calibration loop with autograd on (the reference's data_calib): same kernel behind an autograd node
+            sink: list = []
+            m, v, w, b, e = bn if bn is not None else (None, None, None, None, 0.0)
+            y = ops.EpilogueObserve.apply(pre, bias, m, v, w, b, float(e), act, st, self.num_bits, self.symmetric,
+                                          self.eps, sink)
+            self.last_stats = sink[0]
+        else:
+            y, self.last_stats = ops.ci_epilogue_observe(pre.detach(), st, self.num_bits, self.symmetric, self.eps, act,
+                                                         bias, bn)
         self.last_count = pre.numel()
         self._host = None
         return y

@@ -849,6 +849,41 @@ class FakeQuantEpilogue(torch.autograd.Function):
         return (dx if ctx.needs_input_grad[0] else None), db, ds, dz, None, None, None, None
 
 
+class EpilogueObserve(torch.autograd.Function):
+    """ci_epilogue_observe with an autograd node, for calibration loops that do not switch autograd off (the reference's
+    data_calib, yolov8_qat.py:42-52, runs model(imgs) with grad mode on).  Nobody back-propagates through a calibration
+    pass; if someone does, the backward re-runs the ATen composition the kernel stands for (bias add or inference-mode
+    batch_norm, then relu / silu) under autograd -- correct, and never on a hot path."""
+
+    @staticmethod
+    def forward(ctx, pre, bias, bn_mean, bn_var, bn_weight, bn_bias, bn_eps, act, state, bits, symmetric, eps, sink):
+        bn = None if bn_mean is None else (bn_mean, bn_var, bn_weight, bn_bias, bn_eps)
+        y, stats = ci_epilogue_observe(pre, state, bits, symmetric, eps, act, bias, bn)
+        sink.append(stats)
+        ctx.act, ctx.bn_eps, ctx.has_bn = act, bn_eps, bn is not None
+        ctx.save_for_backward(pre, bias, bn_mean, bn_var, bn_weight, bn_bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        pre, bias, mean, var, w, b = ctx.saved_tensors
+        F = torch.nn.functional
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(True) if (t is not None and need) else t
+                      for t, need in zip((pre, bias, w, b), (ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                                             ctx.needs_input_grad[4], ctx.needs_input_grad[5]))]
+            p_, bias_, w_, b_ = leaves
+            if ctx.has_bn:
+                y = F.batch_norm(p_, mean, var, w_, b_, False, 0.0, ctx.bn_eps)
+            else:
+                y = p_ if bias_ is None else p_ + bias_.view(1, -1, 1, 1)
+            y = F.relu(y) if ctx.act == "relu" else (F.silu(y) if ctx.act == "silu" else y)
+            wanted = [t for t in leaves if t is not None and t.requires_grad]
+            got = iter(torch.autograd.grad(y, wanted, g, allow_unused=True)) if wanted else iter(())
+        out = [next(got) if (t is not None and t.requires_grad) else None for t in leaves]
+        return (out[0], out[1], None, None, out[2], out[3]) + (None,) * 7
+
+
 def lsq_grad_scale(qmax: int, numel: int, channels: int = 1) -> float:
     """(qmax * numel / channels) ** -0.5  [uniform.py:69-71; lsq_module.py:327-340]."""
     return float((qmax * (numel / channels)) ** -0.5) if channels > 1 else float((qmax * numel) ** -0.5)
