@@ -1,6 +1,7 @@
 # Round-end evidence on ONE B200: tests, contract bench (both arms), ncu launch lists + full captures, microbenchmarks.
 # Everything lands in gpurun_out/ with the tag given as $1 (default r02); tools/collect_profiles.sh copies the summaries
-# into profiles/.  Nothing printed under ncu is ever used as a benchmark number.
+# into profiles/.  Nothing printed under ncu is ever used as a benchmark number.  The .ncu-rep files stay in /tmp on the
+# box (gpurun brings back at most 64 MiB); only their raw CSV exports travel.
 TAG=${1:-r02}
 O=gpurun_out
 mkdir -p $O
@@ -12,17 +13,17 @@ python bench.py $MICRO > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/${TAG}_launches_bench.csv \
     python bench.py $MICRO > $O/${TAG}_ncu_list.log 2>&1
 python tools/ncu_driver.py 28 2 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"fq_|lsq_|observe|ci_|mt_" -s 19 -c 19 -o $O/${TAG}_full \
+ncu --set full --clock-control none --import-source on -k regex:"fq_|lsq_|observe|ci_|mt_" -s 19 -c 19 -o /tmp/${TAG}_full \
     python tools/ncu_driver.py 28 2 > $O/${TAG}_ncu_full.log 2>&1
-ncu -i $O/${TAG}_full.ncu-rep --page raw --csv > $O/${TAG}_ncu_full_raw.csv 2>/dev/null
+ncu -i /tmp/${TAG}_full.ncu-rep --page raw --csv > $O/${TAG}_ncu_full_raw.csv 2>/dev/null
 for s in "512 20" "256 40" "128 80"; do
   python tools/ci_ncu_driver.py $s > /dev/null 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches_ci_${s// /x}.csv \
       python tools/ci_ncu_driver.py $s > /dev/null 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:"ci_bwd_tma|ci_fwd|ci_observe_kernel|ci_epilogue_observe" -s 6 -c 6 \
-    -o $O/${TAG}_full_ci_256x40 python tools/ci_ncu_driver.py 256 40 2 > /dev/null 2>&1
-ncu -i $O/${TAG}_full_ci_256x40.ncu-rep --page raw --csv > $O/${TAG}_ncu_full_ci_256x40_raw.csv 2>/dev/null
+    -o /tmp/${TAG}_full_ci_256x40 python tools/ci_ncu_driver.py 256 40 2 > /dev/null 2>&1
+ncu -i /tmp/${TAG}_full_ci_256x40.ncu-rep --page raw --csv > $O/${TAG}_ncu_full_ci_256x40_raw.csv 2>/dev/null
 python tools/microbench.py --log2n 22 24 26 28 --iters 10 --per-channel > $O/${TAG}_microbench.log 2>&1
 python tools/ci_bench.py 64 > $O/${TAG}_ci_bench.log 2>&1
 python tools/shapes_bench.py 64 > $O/${TAG}_shapes_bench.log 2>&1

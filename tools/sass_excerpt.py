@@ -23,6 +23,8 @@ HOT = [  # (substring of the demangled name, why it is listed)
     ("ci_finalize_kernel", "combine kernel, a programmatic dependent of the streaming kernel"),
     ("ci_observe_kernel", "NHWC per-channel observer"),
     ("fq_codes_kernel<4, false>", "packed int4 code export"),
+    ("ci_fwd2_kernel<true, true, 1, false>", "two-output epilogue: y and the next layer's quantize_inp tensor"),
+    ("ci_epilogue_observe_kernel<1, 1>", "calibration epilogue: bias + ReLU + per-tensor observer in one pass"),
 ]
 KEEP = re.compile(r"\b(LDG\S*|STG\S*|LDL\S*|STL\S*|UBLKCP\S*|SYNCS\S*|ACQBULK|PREEXIT|LDS\.128|ATOMG\S*|RED\S*|BAR\S*)\b")
 
