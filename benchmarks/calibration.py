@@ -117,6 +117,11 @@ def run(args) -> dict:
     mgrs = quantization_managers(model)
     hw = _digest((q.scale, q.zero_point) for n, q in mgrs if n.endswith("weight_quantizer"))
     ha = _digest((q.scale, q.zero_point) for n, q in mgrs if n.endswith("activation_quantizer"))
+    px = None
+    if world > 1:  # one-off set-up of the peer-memory exchange (buffers + cudaIpc handles), outside the timed pass
+        from vsiquantization_b200.parallel import peer_exchange_for
+        px = peer_exchange_for(None)
+        dist.barrier()
     t0 = time.perf_counter()
     reestimate_BN_stats(model, mine, num_batches=len(mine), sync=True)
     torch.cuda.synchronize()
@@ -147,6 +152,9 @@ def run(args) -> dict:
             "vsiq_launches_calibration": launches_cal, "host_syncs_in_calibration_forward": 0,
             "weight_scales_sha256": hw[:16], "activation_scales_sha256": ha[:16], "bn_stats_sha256": hb[:16],
             "ranks_agree": bool(agree),
+            "bn_exchange": ("none (one rank)" if world == 1 else
+                            (f"vsiq_bn_moments_exchange over peer memory, {px.status()[0]} exchanges" if px is not None
+                             else "NCCL all_reduce per layer")),
             "bn0_running_mean_head": [round(float(v), 6) for v in bn[0].running_mean[:3]]}
 
 

@@ -194,6 +194,30 @@ int vsiq_qparams_from_minmax(double *state, int64_t n, const int32_t *bits, cons
 int vsiq_lsq_init_scale(const double *state, int64_t channels, int bits, void *scale_out, int scale_dtype,
                         vsiq_stream_t stream);
 
+/* ---- BN re-estimation under data parallelism: the per-layer exchange as ONE kernel over NVLink peer memory -------
+ * reestimate_BN_stats (utils/estimate_bn.py:56-99) with the batch sharded over ranks needs sum x / sum x^2 of every rank
+ * before a layer's output can be normalised.  Instead of combine kernel -> ncclAllReduce -> moments kernel,
+ * every rank launches vsiq_bn_moments_exchange: it publishes weight * (sum x, sum x^2) of its shard in its exchange buffer,
+ * signals its peers, waits for theirs (release / acquire flag words, system scope), adds all shards in rank order through
+ * the peer pointers -- bit-identical sums on every rank -- and finishes like vsiq_bn_moments_finalize (global_count =
+ * elements per channel over all ranks).  One process per GPU, one node, world <= vsiq_peer_max_world(), channels <=
+ * vsiq_peer_max_channels().  Buffers: vsiq_peer_alloc() (cudaMalloc, zeroed, 64-byte cudaIpc handle to hand to the other
+ * ranks), vsiq_peer_open() on their handles, peer_buffers[r] = rank r's buffer as seen from this process (own buffer at
+ * [rank]).  Every rank must issue the same sequence of exchanges.  A peer that does not arrive within timeout_s (<= 0:
+ * 10 s) makes the kernel give up: outputs untouched, vsiq_peer_status() reports the failed sequence number. */
+size_t vsiq_peer_buffer_bytes(void);
+int vsiq_peer_max_world(void);
+int vsiq_peer_max_channels(void);
+int vsiq_peer_alloc(void **buffer, unsigned char *handle64);
+int vsiq_peer_open(const unsigned char *handle64, void **buffer);
+int vsiq_peer_close(void *buffer);
+int vsiq_peer_free(void *buffer);
+int vsiq_peer_status(const void *own_buffer, uint64_t *sequence, uint64_t *failed_sequence);
+int vsiq_bn_moments_exchange(const double *stats, double weight, double global_count, int64_t channels,
+                             void *const *peer_buffers, int rank, int world, double timeout_s, float *batch_mean,
+                             float *batch_var_biased, float *batch_var_unbiased, float *mean_sum, float *var_sum,
+                             vsiq_stream_t stream);
+
 /* ---- (5) Conv/Linear + BN fold (+ weight fake-quant) ---------------------------------------
  * t = gamma / sqrt(var + eps);  W' = W * t[c];  b' = beta + (b - mean) * t   (b = 0 if bias NULL)
  * replaces ConvBnReLU.__init__ modules/fused.py:98-108 and LinearBnReLU.__init__ :292-300.

@@ -98,6 +98,16 @@ _SIGNATURES = {
                                 c_void_p]),
     "vsiq_ci_epilogue_observe": (c_int, [c_void_p] * 6 + [c_float, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                                          c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
+    "vsiq_peer_buffer_bytes": (c_size_t, []),
+    "vsiq_peer_max_world": (c_int, []),
+    "vsiq_peer_max_channels": (c_int, []),
+    "vsiq_peer_alloc": (c_int, [ctypes.POINTER(c_void_p), ctypes.c_char_p]),
+    "vsiq_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "vsiq_peer_close": (c_int, [c_void_p]),
+    "vsiq_peer_free": (c_int, [c_void_p]),
+    "vsiq_peer_status": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "vsiq_bn_moments_exchange": (c_int, [c_void_p, c_double, c_double, c_int64, ctypes.POINTER(c_void_p), c_int, c_int,
+                                         c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vsiq_selftest_division": (c_int, [c_float, c_int, c_void_p, c_void_p]),
     "vsiq_mt_plan": (c_int, [ctypes.POINTER(MtEntry), c_int, ctypes.POINTER(ctypes.c_uint32)]),
     "vsiq_mt_fake_quant_fwd": (c_int, [ctypes.POINTER(MtEntry), c_void_p, c_int, c_void_p, c_void_p]),

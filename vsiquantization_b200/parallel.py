@@ -163,3 +163,123 @@ class QParamGradBucket:
         """Tell DistributedDataParallel (call BEFORE wrapping) not to reduce these parameters itself."""
         from torch.nn.parallel import DistributedDataParallel as DDP
         DDP._set_params_and_buffers_to_ignore_for_model(model, list(self.names))
+
+
+class PeerExchange:
+    """The per-layer exchange of BN re-estimation as ONE kernel over NVLink peer memory (vsiq_bn_moments_exchange,
+    csrc/peer_exchange.cu) instead of combine kernel -> NCCL all_reduce -> moments kernel.
+
+    One process per GPU on one node, at most 8 ranks.  Every rank allocates an exchange buffer, the cudaIpc handles go
+    round once through torch.distributed, and from then on the ranks talk through peer pointers only: publish the shard's
+    sums, signal, wait, add all shards in rank order (every rank gets the same bits), finish the moments.  ``local_buffers``
+    (tests): run several "ranks" inside one process on buffers of one GPU -- the same kernel and protocol, no IPC."""
+
+    def __init__(self, group=None, device=None, local_buffers=None, rank: int = 0, timeout_s: float = 60.0):
+        import ctypes
+
+        from ._lib import check, lib
+        self._lib, self._check, self._ct = lib, check, ctypes
+        self.timeout_s = float(timeout_s)
+        self.group = group
+        self._opened: List[int] = []
+        self._own = None
+        if local_buffers is not None:
+            self.rank, self.world = int(rank), len(local_buffers)
+            self.device = torch.device(device if device is not None else "cuda")
+            self._ptrs = [int(p) for p in local_buffers]
+        else:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+            if self.world > lib.vsiq_peer_max_world():
+                raise RuntimeError(f"PeerExchange handles at most {lib.vsiq_peer_max_world()} ranks of one node")
+            import socket
+            handle = ctypes.create_string_buffer(64)
+            buf = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                rc0 = lib.vsiq_peer_alloc(ctypes.byref(buf), handle)
+            self._own = buf.value if rc0 == 0 else None
+            # from here to the all-reduced verdict every rank walks the same collectives, whatever failed locally
+            mine = (socket.gethostname(), self.device.index, bytes(handle.raw) if rc0 == 0 else None)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+            self._ptrs = []
+            ok = len({h for h, _, _ in everyone}) == 1 and all(hnd is not None for _, _, hnd in everyone)  # one node
+            for r, (_, _, hnd) in enumerate(everyone):
+                if r == self.rank:
+                    self._ptrs.append(self._own or 0)
+                    continue
+                p = ctypes.c_void_p()
+                rc = -1
+                if ok:
+                    with torch.cuda.device(self.device):
+                        rc = lib.vsiq_peer_open(hnd, ctypes.byref(p))
+                if rc != 0:
+                    ok = False
+                    self._ptrs.append(0)
+                else:
+                    self._opened.append(p.value)
+                    self._ptrs.append(p.value)
+            flag = torch.tensor([1.0 if ok else 0.0], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # everybody or nobody
+            if float(flag.item()) != 1.0:
+                self.close()
+                raise RuntimeError("peer memory is not available between all ranks (cudaIpc open failed or several nodes)")
+        self._arr = (ctypes.c_void_p * self.world)(*self._ptrs)
+
+    def bn_moments(self, stats: torch.Tensor, weight: float, global_count: float, mean_sum=None, var_sum=None):
+        """(batch mean, biased batch variance, unbiased batch variance) over ALL ranks' shards from this rank's [C,5]
+        statistics block (ops.observe(x, ch_axis=1)); running sums updated like ops.bn_moments_finalize."""
+        from . import _lib
+        from .ops import _stream_ptr
+        C = stats.shape[0]
+        if stats.dtype != torch.float64 or not stats.is_cuda or not stats.is_contiguous() or stats.shape[1] != _lib.STATS_WIDTH:
+            raise ValueError("stats must be a contiguous CUDA float64 [channels, 5] block")
+        dev = stats.device
+        with torch.cuda.device(dev):
+            m = torch.empty(C, dtype=torch.float32, device=dev)
+            vb = torch.empty(C, dtype=torch.float32, device=dev)
+            vu = torch.empty(C, dtype=torch.float32, device=dev)
+            self._check(self._lib.vsiq_bn_moments_exchange(
+                stats.data_ptr(), float(weight), float(global_count), C, self._arr, self.rank, self.world, self.timeout_s,
+                m.data_ptr(), vb.data_ptr(), vu.data_ptr(), mean_sum.data_ptr() if mean_sum is not None else None,
+                var_sum.data_ptr() if var_sum is not None else None, _stream_ptr()), "vsiq_bn_moments_exchange")
+            _lib.launch_count += 1
+        return m, vb, vu
+
+    def status(self) -> Tuple[int, int]:
+        """(exchanges completed, sequence number of a timed-out exchange or 0).  Synchronises."""
+        ct = self._ct
+        seq, bad = ct.c_uint64(), ct.c_uint64()
+        self._check(self._lib.vsiq_peer_status(self._ptrs[self.rank], ct.byref(seq), ct.byref(bad)), "vsiq_peer_status")
+        return int(seq.value), int(bad.value)
+
+    def close(self) -> None:
+        for p in self._opened:
+            self._lib.vsiq_peer_close(p)
+        self._opened = []
+        if self._own is not None:
+            self._lib.vsiq_peer_free(self._own)
+            self._own = None
+
+
+_peer_exchanges: Dict[object, object] = {}
+
+
+def peer_exchange_for(group=None):
+    """The process group's PeerExchange, created on first use; None when peer memory cannot be used (gloo / CPU tests,
+    more than 8 ranks, several nodes, VSIQ_PEER_EXCHANGE=0) -- callers then keep their NCCL collective."""
+    import os
+    if os.environ.get("VSIQ_PEER_EXCHANGE", "1") == "0" or not (dist.is_available() and dist.is_initialized()):
+        return None
+    key = group if group is not None else "world"
+    if key not in _peer_exchanges:
+        px = None
+        try:
+            if dist.get_backend(group) == "nccl" and torch.cuda.is_available() and dist.get_world_size(group) > 1:
+                px = PeerExchange(group)
+        except Exception:  # no peer access between some pair of ranks: every rank raises (all-reduced flag) and falls back
+            px = None
+        _peer_exchanges[key] = px
+    return _peer_exchanges[key]

@@ -50,6 +50,18 @@ def _make_hook(ctx: dict):
         bn = module.bn
         stats = ops.observe(x, ch_axis=1)                      # [C,5]: .., sum x, sum x^2  -- one read of x
         count = float(x.numel() // x.shape[1])
+        if ctx["sync"] and ctx.get("peer") is not None and x.shape[1] <= ctx["peer_max_channels"]:
+            # one kernel per rank over NVLink peer memory: publish this shard's sums, wait for the peers', add them in
+            # rank order, finish the moments (csrc/peer_exchange.cu) -- no NCCL call, no separate moments launch
+            count = count / ctx["local_images"] * ctx["global_images"]
+            mean, var_b, _ = ctx["peer"].bn_moments(stats, ctx["weight"], count, module.running_mean_sum,
+                                                    module.running_var_sum)
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            if collect is not None:
+                y = collect.collect_epilogue(x, act, bn=(mean, var_b, bn.weight, bn.bias, bn.eps))
+                return y if y is not None else collect.quantize(_normalise(x, mean, var_b, bn, act))
+            return _normalise(x, mean, var_b, bn, act)
         if ctx["sync"]:
             if ctx["weight"] != 1.0:
                 stats.mul_(ctx["weight"])
@@ -88,7 +100,12 @@ def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=Fals
     when no rank has data left."""
     model.eval()
     layers = [(n, m) for n, m in model.named_modules() if isinstance(m, ConvBnReLU) and hasattr(m, "bn")]
-    ctx = {"sync": _dist_on(sync), "weight": 1.0, "local_images": 1, "global_images": 1}
+    ctx = {"sync": _dist_on(sync), "weight": 1.0, "local_images": 1, "global_images": 1, "peer": None}
+    if ctx["sync"]:
+        from .. import _lib
+        from ..parallel import peer_exchange_for
+        ctx["peer"] = peer_exchange_for(None)
+        ctx["peer_max_channels"] = _lib.lib.vsiq_peer_max_channels()
     hook = _make_hook(ctx)
     for _, m in layers:
         m.running_mean_sum = torch.zeros_like(m.bn.running_mean)
@@ -132,6 +149,11 @@ def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=Fals
     finally:
         for _, m in layers:
             m._bn_reestimate = None
+    if ctx["peer"] is not None:
+        done, failed = ctx["peer"].status()
+        if failed:
+            raise RuntimeError(f"reestimate_BN_stats: peer exchange {failed} timed out (a rank did not arrive); "
+                               "set VSIQ_PEER_EXCHANGE=0 to use the NCCL collective")
     if batch_count:
         for _, m in layers:
             ops.bn_reestimate_finish(m.running_mean_sum, m.running_var_sum, batch_count, m.bn.running_mean,
