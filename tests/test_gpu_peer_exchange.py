@@ -59,6 +59,11 @@ def test_a_missing_peer_times_out_instead_of_hanging():
     torch.cuda.synchronize()
     assert lonely.status() == (0, 1)      # nothing completed, exchange 1 reported as failed
     del mean
+    import time
+    t0 = time.perf_counter()
+    lonely.bn_moments(stats, 1.0, 144.0)  # after a failure every later exchange returns at once (no second wait)
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 0.1 and lonely.status() == (0, 1)
 
 
 def _worker(rank, world, port, results):

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kPeerThreads)
     const unsigned long long seq = my_words[8] + 1ull;  // written by thread 0 at the very end of the previous exchange
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
     const size_t area = kPeerHeader + (size_t)(seq & 1ull) * kPeerAreaBytes;
+    if (my_words[9] != 0ull) return;  // an earlier exchange timed out: fail fast (the peers' kernels time out once, then do the same)
     if (threadIdx.x == 0) s_failed = 0;
     __syncthreads();
     const int c = threadIdx.x;

@@ -174,7 +174,7 @@ class PeerExchange:
     sums, signal, wait, add all shards in rank order (every rank gets the same bits), finish the moments.  ``local_buffers``
     (tests): run several "ranks" inside one process on buffers of one GPU -- the same kernel and protocol, no IPC."""
 
-    def __init__(self, group=None, device=None, local_buffers=None, rank: int = 0, timeout_s: float = 60.0):
+    def __init__(self, group=None, device=None, local_buffers=None, rank: int = 0, timeout_s: float = 30.0):
         import ctypes
 
         from ._lib import check, lib
@@ -283,3 +283,12 @@ def peer_exchange_for(group=None):
             px = None
         _peer_exchanges[key] = px
     return _peer_exchanges[key]
+
+
+def drop_peer_exchange(group=None) -> None:
+    """Forget the group's PeerExchange after a failed exchange: peer_exchange_for() then answers None (NCCL fallback)."""
+    key = group if group is not None else "world"
+    px = _peer_exchanges.get(key)
+    if px is not None:
+        px.close()
+    _peer_exchanges[key] = None

@@ -151,9 +151,14 @@ def reestimate_BN_stats(model, data_loader, num_batches=50, store_ema_stats=Fals
             m._bn_reestimate = None
     if ctx["peer"] is not None:
         done, failed = ctx["peer"].status()
-        if failed:
-            raise RuntimeError(f"reestimate_BN_stats: peer exchange {failed} timed out (a rank did not arrive); "
-                               "set VSIQ_PEER_EXCHANGE=0 to use the NCCL collective")
+        bad = torch.tensor([1.0 if failed else 0.0], device=device)
+        torch.distributed.all_reduce(bad, op=torch.distributed.ReduceOp.MAX)  # every rank raises, or none does
+        if float(bad.item()):
+            from ..parallel import drop_peer_exchange
+            drop_peer_exchange(None)  # later calls use the NCCL collective
+            raise RuntimeError(f"reestimate_BN_stats: a peer-memory exchange timed out (this rank: exchange {failed or '-'} "
+                               f"after {done} completed); the running statistics were not updated. Later calls use the "
+                               "NCCL collective; VSIQ_PEER_EXCHANGE=0 selects it from the start")
     if batch_count:
         for _, m in layers:
             ops.bn_reestimate_finish(m.running_mean_sum, m.running_var_sum, batch_count, m.bn.running_mean,
