@@ -13,7 +13,8 @@
  *   - plain pointers and sizes only; every tensor pointer is DEVICE memory
  *     (fp32 unless stated) owned by the caller, except in the *_host entry.
  *   - every call is asynchronous on the given stream (a cudaStream_t passed as
- *     void*), allocates nothing (scratch comes in as `workspace`), keeps no
+ *     void*), allocates nothing (scratch comes in as `workspace`; the exceptions say so: the host pipeline's
+ *     handle and vsiq_peer_alloc, whose buffer must be cudaMalloc memory to be exported to other processes), keeps no
  *     global mutable state (beyond mutex-guarded, write-once per-device caches of
  *     device attributes and kernel attributes) and is re-entrant across streams and devices.
  *     Workspaces must not be shared by calls running concurrently on
@@ -252,7 +253,7 @@ int vsiq_bn_reestimate_finish(const float *mean_sum, const float *var_sum, int64
  * cut into chunks that flow H2D -> fused kernel -> D2H on `n_slots` streams so the three stages
  * overlap.  Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory);
  * pageable memory works but serialises.  The handle owns its device staging buffers and streams
- * (the only entry points that allocate).  fwd_bwd returns after everything has landed in y / dx. */
+ * (these and vsiq_peer_alloc are the only entry points that allocate).  fwd_bwd returns after everything has landed in y / dx. */
 typedef struct vsiq_host_pipeline vsiq_host_pipeline;
 int vsiq_host_pipeline_create(vsiq_host_pipeline **out, int64_t chunk_elems, int n_slots);
 int vsiq_host_pipeline_destroy(vsiq_host_pipeline *p);

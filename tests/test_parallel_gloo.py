@@ -212,3 +212,20 @@ def test_sync_observers_averages_moving_average_observers():
     assert np.array_equal(a0[0][:, :2], want) and np.array_equal(a0[0][:, 4], b0[0][:, 4] + b1[0][:, 4])
     # activations: only rank 0 has data -> its extrema survive unchanged
     assert np.array_equal(a0[1][:, :2], b0[1][:, :2]) and a0[1][0, 4] == 3
+
+
+def _peer_case(rank, world):
+    """Under gloo (no CUDA peers) the per-layer exchange of BN re-estimation must keep its collective: peer_exchange_for
+    answers None on every rank, and VSIQ_PEER_EXCHANGE=0 switches it off wherever it would apply."""
+    from vsiquantization_b200 import parallel
+    parallel._peer_exchanges.clear()
+    first = parallel.peer_exchange_for(None)
+    os.environ["VSIQ_PEER_EXCHANGE"] = "0"
+    second = parallel.peer_exchange_for(None)
+    os.environ.pop("VSIQ_PEER_EXCHANGE")
+    parallel.drop_peer_exchange(None)
+    return first is None and second is None and parallel.peer_exchange_for(None) is None
+
+
+def test_peer_exchange_declines_without_cuda_peers():
+    assert _run(_peer_case) == [True, True]
