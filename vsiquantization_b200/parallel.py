@@ -267,13 +267,20 @@ class PeerExchange:
 _peer_exchanges: Dict[object, object] = {}
 
 
+def _group_key(group):
+    """The process-group OBJECT (a re-initialised default group is a new object: its ranks need new buffers)."""
+    if group is not None:
+        return group
+    return dist.group.WORLD if dist.is_available() and dist.is_initialized() else "world"
+
+
 def peer_exchange_for(group=None):
     """The process group's PeerExchange, created on first use; None when peer memory cannot be used (gloo / CPU tests,
     more than 8 ranks, several nodes, VSIQ_PEER_EXCHANGE=0) -- callers then keep their NCCL collective."""
     import os
     if os.environ.get("VSIQ_PEER_EXCHANGE", "1") == "0" or not (dist.is_available() and dist.is_initialized()):
         return None
-    key = group if group is not None else "world"
+    key = _group_key(group)
     if key not in _peer_exchanges:
         px = None
         try:
@@ -287,7 +294,7 @@ def peer_exchange_for(group=None):
 
 def drop_peer_exchange(group=None) -> None:
     """Forget the group's PeerExchange after a failed exchange: peer_exchange_for() then answers None (NCCL fallback)."""
-    key = group if group is not None else "world"
+    key = _group_key(group)
     px = _peer_exchanges.get(key)
     if px is not None:
         px.close()
