@@ -513,6 +513,39 @@ def test_ci_observe_matches_nchw_observer(shape):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("bits,qmin,qmax,z", [(8, -128, 127, 0.0), (4, 0, 15, 8.0), (16, -32768, 32767, 0.0)])
+def test_integer_code_export_long_tiles(ops, bits, qmin, qmax, z):
+    """Large tensors walk tiles of up to 8 batches (reduce_tile_mult) and take the code straight from the mantissa of
+    t + 1.5 * 2^23: every code in the range, ties, specials and a ragged tail against the oracle, codes only and with y."""
+    rng = np.random.default_rng(bits)
+    n = (1 << 24) + 40
+    s = np.float32(6.0 / (qmax - qmin))
+    x = (rng.standard_normal(n) * 2).astype(np.float32)
+    k = np.arange(qmin - 3, qmax + 4, dtype=np.float64)
+    ties = np.concatenate([(k - z) * s, (k + 0.5 - z) * s]).astype(np.float32)  # exact codes and half-way points
+    x[1000:1000 + ties.size] = ties
+    x[::9973] = np.nan
+    x[1::9967] = np.inf
+    x[2::9949] = -1e30
+    x[3::9941] = 1e-42
+    x[4::9931] = -0.0
+    y_o, c_o = oracle.fake_quant_fwd(x, s, z, qmin, qmax, want_codes=True)
+    want = np.where(np.isnan(c_o), 0, c_o).astype(np.int64)
+    spec = ops.QSpec(qmin, qmax)
+    xt = dev(x)
+    for want_y in (False, True):
+        y, codes = ops.quantize_codes(xt, float(s), float(z), spec, bits, want_y=want_y)
+        c = codes.cpu().numpy()
+        if bits == 4:
+            got = np.stack([(c & 0xf), (c >> 4)], axis=-1).reshape(-1).astype(np.int64)
+        else:
+            got = c.astype(np.int64)
+        assert np.array_equal(got, want), (bits, want_y, np.flatnonzero(got != want)[:5])
+        if want_y:
+            assert bits_equal(y.cpu().numpy(), y_o)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("bits,sym", [(8, True), (8, False), (4, True), (4, False), (16, True), (12, False), (3, True)])
 @pytest.mark.parametrize("shape,ch_axis", [(((1 << 16) + 24,), None), ((37, 1030), 0), ((3, 6, 50, 38), 1), ((5, 8), None)])
 def test_integer_code_export(ops, bits, sym, shape, ch_axis):
@@ -547,6 +580,9 @@ def test_integer_code_export(ops, bits, sym, shape, ch_axis):
             got = c.astype(np.int64)
             assert c.shape == shape and c.dtype.itemsize * 8 == code_bits and (c.dtype.kind == "i") == sym
         assert np.array_equal(got, want), code_bits
+        # the codes-only instantiation (no y written: its own kernel) emits the same bytes
+        none, codes_only = ops.quantize_codes(xt, st, zt, spec, code_bits, want_y=False)
+        assert none is None and np.array_equal(codes_only.cpu().numpy(), c), code_bits
     # the default width never wraps: 8 bits when the range fits, else 16
     y2, c2 = ops.fake_quant_forward(xt, st, zt, spec, want_codes=True)
     assert c2.dtype.itemsize == (1 if bits <= 8 else 2) and np.array_equal(c2.cpu().numpy().astype(np.int64), want)

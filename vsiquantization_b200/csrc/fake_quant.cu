@@ -101,16 +101,63 @@ __device__ __forceinline__ void code_store1(void* codes, int64_t i, int q) {
     if (BITS == 16) ((uint16_t*)codes)[i] = (uint16_t)(q & 0xffff);
 }
 
+// One 256-bit vector -> 8 codes.  On the fast path (every |x| in [2^-60, 2^61) or 0, |s| in [2^-40, 2^40]: no NaN can
+// appear) the pre-rounding clamp leaves t in [qmin - 0.5, qmax + 0.5], so ONE add of 1.5 * 2^23 both rounds to nearest
+// even and leaves the two's-complement code in the low mantissa bits: no F2I on the conversion pipe.
+constexpr float kCodeMagic = 12582912.0f;  // 0x4B400000: low 22 bits of (t + magic) == rint(t) mod 2^22
 template <int BITS, bool WANT_Y>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void codes_vec(const Vec<kVec>& in, int64_t i, const QP& p, uint32_t seed, float* y,
+                                          void* codes) {
+    FastGuard guard;
+    guard_reset(guard, seed);
+    float t[kVec];
+#pragma unroll
+    for (int e = 0; e < kVec; ++e) {
+        guard_note(guard, in.v[e]);
+        t[e] = clamp_t(__fadd_rn(div_fast(in.v[e], p), p.z), p);
+    }
+    int qi[kVec];
+    Vec<kVec> vy;
+    if (guard_bad(guard)) {
+#pragma unroll
+        for (int e = 0; e < kVec; ++e) {
+            const float q = elem_slow(in.v[e], p).q;
+            qi[e] = code_of(q);
+            if (WANT_Y) vy.v[e] = dequant(q, p);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < kVec; ++e) {
+            if (WANT_Y) {
+                const float q = rintf(t[e]);  // keeps the sign of a negative zero for y
+                vy.v[e] = dequant(q, p);
+                qi[e] = __float_as_int(__fadd_rn(q, kCodeMagic));
+            } else {
+                qi[e] = __float_as_int(__fadd_rn(t[e], kCodeMagic));
+            }
+        }
+    }
+    CodePack<BITS>::store8(codes, i, qi);
+    if (WANT_Y) st_stream(y + i, vy);
+}
+
+// Tiles are up to 8 batches long for large tensors (reduce_tile_mult): the kernel moves only 4.5-5 bytes per element, so
+// with one 8192-element batch per CTA the launch / drain of a CTA is not covered by its own traffic.  Measured on B200 at
+// 2^28 elements (profiles/r02_ab_code_export.log): int8 236 -> 205 us, packed int4 256 -> 205 us; a register
+// double buffer (loads of batch k+1 issued before batch k is converted) and 5 CTAs/SM were measured too and add nothing.
+template <int BITS, bool WANT_Y>
+__global__ void __launch_bounds__(kThreads, 4)
     fq_codes_kernel(const float* __restrict__ x, float* __restrict__ y, void* __restrict__ codes, Tiles tiles, QPDev qpd) {
     const int tid = threadIdx.x;
     int64_t cur_channel = -1;
     QP p;
+    uint32_t seed = 0;
+    constexpr int kCodeUnroll = 4;
     for (uint32_t t = blockIdx.x; t < tiles.n_tiles; t += gridDim.x) {
         const TileCursor<kThreads> c = tile_at<kThreads>(tiles, t);
         if (c.channel != cur_channel) {
             p = load_qp(qpd, c.channel);
+            seed = guard_seed(p.fast);
             cur_channel = c.channel;
         }
         const int64_t off = c.offset;
@@ -118,6 +165,7 @@ __global__ void __launch_bounds__(kThreads)
         head = head < c.len ? head : c.len;
         const int nvec = (c.len - head) / kVec;
         const int tail0 = head + nvec * kVec;
+        const float* xb = x + off + head;
         // ---- ragged head and tail: IEEE sequence, one element (int4: one byte = two elements) per thread
         const int ragged = head + (c.len - tail0);
         const int per = BITS == 4 ? 2 : 1;
@@ -136,40 +184,17 @@ __global__ void __launch_bounds__(kThreads)
                 code_store1<BITS>(codes, off + i0, q2[0]);
         }
         // ---- vector body: kCodeUnroll 256-bit loads in flight per thread before any arithmetic
-        constexpr int kCodeUnroll = 4;
         for (int v0 = tid; v0 < nvec; v0 += kThreads * kCodeUnroll) {
             Vec<kVec> vin[kCodeUnroll];
 #pragma unroll
             for (int j = 0; j < kCodeUnroll; ++j) {
                 const int v = v0 + j * kThreads;
-                if (v < nvec) vin[j] = ld_stream(x + off + head + (int64_t)v * kVec, (Vec<kVec>*)nullptr);
+                if (v < nvec) vin[j] = ld_stream(xb + (int64_t)v * kVec, (Vec<kVec>*)nullptr);
             }
 #pragma unroll
             for (int j = 0; j < kCodeUnroll; ++j) {
                 const int v = v0 + j * kThreads;
-                if (v >= nvec) continue;
-                const int64_t i = off + head + (int64_t)v * kVec;
-                float q[kVec];
-                FastGuard guard;
-                guard_reset(guard, guard_seed(p.fast));
-#pragma unroll
-                for (int e = 0; e < kVec; ++e) {
-                    guard_note(guard, vin[j].v[e]);
-                    q[e] = elem_fast(vin[j].v[e], p).q;
-                }
-                if (guard_bad(guard)) {
-#pragma unroll
-                    for (int e = 0; e < kVec; ++e) q[e] = elem_slow(vin[j].v[e], p).q;
-                }
-                int qi[kVec];
-                Vec<kVec> vy;
-#pragma unroll
-                for (int e = 0; e < kVec; ++e) {
-                    qi[e] = code_of(q[e]);
-                    if (WANT_Y) vy.v[e] = dequant(q[e], p);
-                }
-                CodePack<BITS>::store8(codes, i, qi);
-                if (WANT_Y) st_stream(y + i, vy);
+                if (v < nvec) codes_vec<BITS, WANT_Y>(vin[j], off + head + (int64_t)v * kVec, p, seed, y, codes);
             }
         }
     }
@@ -544,7 +569,8 @@ extern "C" int vsiq_quantize_codes(const float* x, float* y, void* codes, int co
     const uintptr_t amask = reinterpret_cast<uintptr_t>(x) | (y ? reinterpret_cast<uintptr_t>(y) : 0);
     if ((amask & 31u) || (reinterpret_cast<uintptr_t>(codes) & 15u)) return VSIQ_ERR_UNSUPPORTED;
     Tiles tiles;
-    if (!make_tiles<kThreads>(layout->outer, layout->channels, layout->inner, &tiles)) return VSIQ_ERR_INVALID_ARG;
+    const int mult = reduce_tile_mult<kThreads>(layout->outer, layout->channels, layout->inner);
+    if (!make_tiles<kThreads>(layout->outer, layout->channels, layout->inner, &tiles, mult)) return VSIQ_ERR_INVALID_ARG;
     const int grid = launch_grid(tiles.n_tiles);
     if (grid < 0) return -grid;
     cudaStream_t st = (cudaStream_t)stream;
