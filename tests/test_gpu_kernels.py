@@ -383,6 +383,46 @@ def test_full_size_properties(ops, log2n):
     assert st[4] == pytest.approx(float((x.double() ** 2).sum()), rel=1e-6)
 
 
+def test_maximum_size_2p30_windows(ops):
+    """BASELINE configs[1] tops out at 2^30 elements (4 GiB per tensor: byte offsets cross 2^32).  Windows at the head,
+    across the 2^31- and 2^32-byte marks and at the tail against the oracle, bit for bit (y, codes, STE dx, LSQ dx), plus
+    whole-tensor properties: y == codes * s, extrema equal torch's, ds linear in g."""
+    n = 1 << 30
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30 * (1 << 30):
+        pytest.skip("needs 30 GiB of free device memory")
+    torch.manual_seed(30)
+    x = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda")
+    s, qmin, qmax = 3.0 / 127, -128, 127
+    spec = ops.QSpec(qmin, qmax)
+    y, codes = ops.fake_quant_forward(x, s, 0, spec, want_codes=True)
+    _, codes_only = ops.quantize_codes(x, s, 0, spec, 8, want_y=False)
+    assert torch.equal(codes, codes_only)
+    assert torch.equal(codes.float() * torch.tensor(s, device="cuda", dtype=torch.float32), y)
+    del codes_only
+    dx = ops.fake_quant_backward_ste(x, g, s, 0, spec)
+    s_t = torch.tensor(s, dtype=torch.float64, device="cuda")
+    gs = ops.lsq_grad_scale(qmax, n)
+    dx_l, ds1, _ = ops.lsq_backward(x, g, s_t, 0, spec, gs, ds_dtype=torch.float64)
+    k = 1 << 18
+    for start in (0, (1 << 29) - k // 2, (1 << 30) - k):  # element 2^29 = byte 2^31; the tail ends at byte 2^32
+        xo, go = x[start:start + k].cpu().numpy(), g[start:start + k].cpu().numpy()
+        y_o, c_o = oracle.fake_quant_fwd(xo, s, 0, qmin, qmax, want_codes=True)
+        assert bits_equal(y[start:start + k].cpu().numpy(), y_o), start
+        assert np.array_equal(codes[start:start + k].cpu().numpy().astype(np.float32), c_o), start
+        dx_o = oracle.fake_quant_bwd(xo, go, s, 0, qmin, qmax, want_ds=False)[0]
+        assert bits_equal(dx[start:start + k].cpu().numpy(), dx_o), start
+        assert bits_equal(dx_l[start:start + k].cpu().numpy(), dx_o), start
+    del y, codes, dx, dx_l
+    g.mul_(2)
+    _, ds2, _ = ops.lsq_backward(x, g, s_t, 0, spec, gs, ds_dtype=torch.float64)
+    assert ds2.item() == pytest.approx(2 * ds1.item(), rel=1e-12)
+    st = ops.observe(x).cpu().numpy()[0]
+    assert st[0] == float(x.min()) and st[1] == float(x.max())
+    assert st[4] == pytest.approx(float((x.double() ** 2).sum()), rel=1e-6)
+
+
 # ---------------------------------------------------------- channel-innermost (NHWC / channels_last) kernels
 @pytest.mark.parametrize("shape", [(2, 16, 9, 7), (3, 64, 20, 20), (1, 48, 33, 5), (2, 512, 6, 5), (2, 1024, 3, 3), (5, 4, 40, 40),
                                    (64, 32, 64, 64)])
