@@ -331,6 +331,111 @@ def test_empty_and_errors(ops):
         ops.fake_quant_forward(torch.zeros(4, device="cuda"), 0.1, 0, ops.QSpec(7, 7))  # qmin >= qmax
 
 
+# --------------------------------------------------------------- red zones: nothing is written outside the outputs
+_SENT32 = 0x7FC0DEAD  # a NaN with a payload no kernel produces
+_PAD = 4096           # elements of sentinel on each side of an output
+
+
+class _RedZone:
+    """An output carved out of a sentinel-filled buffer at an element offset (so every alignment class of the stores is
+    visited); untouched() is true when every word outside the carved range still holds the sentinel."""
+
+    def __init__(self, n, off, dtype=torch.float32):
+        self.n, self.off, self.dtype = n, off, dtype
+        if dtype == torch.float32:
+            self.raw = torch.full((2 * _PAD + n + 16,), _SENT32, dtype=torch.int32, device="cuda")
+            self.buf = self.raw.view(torch.float32)
+        else:
+            self.raw = torch.full((2 * _PAD + n + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+            self.buf = self.raw.view(dtype)
+        self.out = self.buf[_PAD + off:_PAD + off + n]
+
+    def untouched(self):
+        sent = _SENT32 if self.dtype == torch.float32 else 0xA5
+        lo, hi = self.raw[:_PAD + self.off], self.raw[_PAD + self.off + self.n:]
+        return bool((lo == sent).all()) and bool((hi == sent).all())
+
+
+def _same_bits(a, b):
+    return torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
+
+
+@pytest.mark.parametrize("off", [0, 1, 5, 8])
+@pytest.mark.parametrize("shape,ch_axis", [((1,), None), ((7,), None), ((31,), None), ((255,), None), ((1027,), None),
+                                           ((8191,), None), ((8200,), None), ((65536 + 24,), None), ((300007,), None),
+                                           ((5, 37), 0), ((64, 1030), 0), ((3, 70001), 0), ((300, 9), 0),
+                                           ((3, 6, 50, 38), 1)])
+def test_no_write_outside_the_outputs(ops, shape, ch_axis, off):
+    """Forward, STE backward and the fused sweep write exactly their outputs: y / dx live inside sentinel-filled
+    buffers at element offsets 0, 1, 5, 8 (32-byte aligned, unaligned, 32-byte aligned again), the input is offset the
+    same way, and the result equals the one computed into a fresh, aligned allocation bit for bit."""
+    rng = np.random.default_rng(len(shape) * 131 + shape[-1] + off)
+    n = int(np.prod(shape))
+    C = 1 if ch_axis is None else shape[ch_axis]
+    xs, gs_ = _RedZone(n, off), _RedZone(n, off)
+    xs.out.copy_(dev((rng.standard_normal(n) * 3).astype(np.float32)))
+    gs_.out.copy_(dev(rng.standard_normal(n).astype(np.float32)))
+    x, g = xs.out.view(shape), gs_.out.view(shape)
+    spec = ops.QSpec(-8, 7, ch_axis=ch_axis)
+    s = 0.4 if ch_axis is None else dev((rng.uniform(0.5, 2.0, C) * 0.4).astype(np.float32))
+    z = 0 if ch_axis is None else torch.zeros(C, device="cuda")
+    y_ref = ops.fake_quant_forward(x.clone(), s, z, spec)
+    dx_ref = ops.fake_quant_backward_ste(x.clone(), g.clone(), s, z, spec)
+    yz, dz = _RedZone(n, off), _RedZone(n, off)
+    y = ops.fake_quant_forward(x, s, z, spec, out=yz.out.view(shape))
+    dx = ops.fake_quant_backward_ste(x, g, s, z, spec, out=dz.out.view(shape))
+    assert yz.untouched() and dz.untouched() and xs.untouched() and gs_.untouched()
+    assert _same_bits(y, y_ref) and _same_bits(dx, dx_ref)
+    if ch_axis is None:
+        y2z, dx2z = _RedZone(n, off), _RedZone(n, off)
+        y2, dx2 = ops.fake_quant_forward_backward(x, g, s, z, spec, y_out=y2z.out.view(shape), dx_out=dx2z.out.view(shape))
+        assert y2z.untouched() and dx2z.untouched()
+        assert _same_bits(y2, y_ref) and _same_bits(dx2, dx_ref)
+
+
+@pytest.mark.parametrize("bits", [4, 8, 16])
+@pytest.mark.parametrize("shape,ch_axis", [((2,), None), ((30,), None), ((8190,), None), ((8194,), None), ((70002,), None),
+                                           (((1 << 21) + 6,), None), ((5, 38), 0), ((3, 70002), 0), ((3, 6, 50, 38), 1)])
+def test_code_export_writes_only_its_codes(ops, bits, shape, ch_axis):
+    """Packed codes (two per byte, one per byte, one per 16 bits) inside a 0xA5-filled byte buffer: ragged heads and
+    tails, per-channel rows and multi-batch tiles leave every byte outside the codes alone."""
+    rng = np.random.default_rng(bits + shape[-1])
+    n = int(np.prod(shape))
+    C = 1 if ch_axis is None else shape[ch_axis]
+    x = dev((rng.standard_normal(shape) * 3).astype(np.float32))
+    qmin, qmax = (0, 15) if bits == 4 else (-(1 << (bits - 1)), (1 << (bits - 1)) - 1)
+    spec = ops.QSpec(qmin, qmax, ch_axis=ch_axis)
+    s = 6.0 / (qmax - qmin) if ch_axis is None else dev((rng.uniform(0.5, 2.0, C) * 6.0 / (qmax - qmin)).astype(np.float32))
+    z = (8 if bits == 4 else 0) if ch_axis is None else torch.full((C,), 8.0 if bits == 4 else 0.0, device="cuda")
+    _, ref = ops.quantize_codes(x, s, z, spec, bits, want_y=False)
+    nbytes = n // 2 if bits == 4 else n * (bits // 8)
+    rz = _RedZone(nbytes, 16, torch.uint8)
+    c_shape = shape[:-1] + (shape[-1] // 2,) if bits == 4 else shape
+    out = rz.out.view(ref.dtype).view(c_shape)
+    _, codes = ops.quantize_codes(x, s, z, spec, bits, want_y=False, codes_out=out)
+    assert rz.untouched()
+    assert torch.equal(codes, ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 9, 7), (1, 48, 33, 5), (2, 512, 6, 5), (5, 4, 41, 40)])
+def test_channels_last_epilogue_writes_only_its_output(ops, shape):
+    """The NHWC epilogue forward (bias + ReLU + per-channel fake-quant) into a sentinel-padded channels_last output."""
+    rng = np.random.default_rng(sum(shape))
+    N, C, H, W = shape
+    n = N * C * H * W
+    x = dev((rng.standard_normal(shape) * 2).astype(np.float32)).contiguous(memory_format=torch.channels_last)
+    b = dev(rng.standard_normal(C).astype(np.float32))
+    s = dev((rng.uniform(0.5, 2.0, C) * 0.02).astype(np.float32))
+    z = torch.zeros(C, device="cuda")
+    spec = ops.QSpec(-128, 127, ch_axis=1, pre_relu=True)
+    ref = ops.ci_forward(x, b, s, z, spec)
+    rz = _RedZone(n, 4)
+    out = rz.out.view(N, H, W, C).permute(0, 3, 1, 2)
+    y = ops.ci_forward(x, b, s, z, spec, out=out)
+    assert rz.untouched()
+    assert _same_bits(y.permute(0, 2, 3, 1), ref.permute(0, 2, 3, 1))
+
+
 # --------------------------------------------------------------- full-size, size-independent properties
 @pytest.mark.parametrize("log2n", [26, 28])
 def test_full_size_properties(ops, log2n):
