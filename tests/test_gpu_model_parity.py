@@ -208,3 +208,67 @@ def test_native_equals_eager_composition_at_model_scale(per_channel_lsq, monkeyp
         assert float(l1.detach()) == float(l2), "graphed and eagerly launched steps diverge"
     for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         assert np.array_equal(_bits(p1), _bits(p2)), n1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("phase", ["train", "calibrate"])
+def test_channel_slice_input_keeps_the_channels_last_epilogue(phase, monkeypatch):
+    """C2f blocks feed a fused layer ``chunk(2, dim=1)[1]`` of a channels_last tensor: stride(1) == 1 but pitched rows.
+    The layer densifies that view once and stays on the NHWC epilogue (bias add, ReLU, quantiser -- or observer while
+    calibrating -- in one pass; dx + dbias + dscale in one backward pass) instead of falling back to a convolution with
+    its own bias-add / bias-gradient passes and an input copy in each direction.  Outputs and every gradient equal those
+    of the same layer fed a dense copy of the slice, bit for bit, with the same number of native launches."""
+    from vsiquantization_b200 import _lib
+    from vsiquantization_b200.modules.fused import ConvBnReLU
+    from vsiquantization_b200.utils.quantize_manager import activate_learning_qparam, activate_quantizer, calibrate_qat_model
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    torch.manual_seed(3)
+    cv, bn = torch.nn.Conv2d(16, 32, 3, padding=1, bias=False), torch.nn.BatchNorm2d(32)
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.1)
+        bn.running_var.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.2)
+    layer = ConvBnReLU(cv, bn, torch.nn.ReLU(), "LSQObserver", "LSQQuantizer", "LSQObserver", "LSQQuantizer", True, False,
+                       True, 4, 8).cuda().to(memory_format=torch.channels_last)
+    wide = torch.randn(4, 32, 20, 20, device="cuda").contiguous(memory_format=torch.channels_last)
+    calib = lambda m, loader, dev: [m(b) for b in loader]  # noqa: E731
+    if phase == "calibrate":
+        import copy
+        twin = copy.deepcopy(layer)
+        n0 = _lib.launch_count
+        calibrate_qat_model(layer, [wide.chunk(2, 1)[1]], calib)
+        n_slice = _lib.launch_count - n0
+        n0 = _lib.launch_count
+        calibrate_qat_model(twin, [wide.chunk(2, 1)[1].contiguous(memory_format=torch.channels_last)], calib)
+        assert _lib.launch_count - n0 == n_slice
+        a, b = layer.activation_quantizer, twin.activation_quantizer
+        assert a.observer.get_scale_zero_point() == b.observer.get_scale_zero_point()
+        return
+    calibrate_qat_model(layer, [wide.chunk(2, 1)[1].contiguous(memory_format=torch.channels_last)], calib)
+    activate_learning_qparam(layer, use_init=True)
+    activate_quantizer(layer)
+    layer.train()
+
+    def run(dense):
+        layer.zero_grad(set_to_none=True)
+        w = wide.clone().requires_grad_(True)
+        x = w.chunk(2, 1)[1]
+        assert x.stride(1) == 1 and not x.is_contiguous(memory_format=torch.channels_last)
+        if dense:
+            x = x.contiguous(memory_format=torch.channels_last)
+        n0 = _lib.launch_count
+        y = layer(x)
+        (y * torch.linspace(-1, 1, y.numel(), device="cuda").view_as(y)).sum().backward()
+        grads = {n: p.grad.detach().clone() for n, p in layer.named_parameters() if p.grad is not None}
+        return y.detach().clone(), w.grad.detach().clone(), grads, _lib.launch_count - n0
+
+    y0, dw0, g0, n_dense = run(True)
+    y1, dw1, g1, n_slice = run(False)
+    assert n_slice == n_dense
+    assert y1.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y1, y0) and torch.equal(dw1, dw0)
+    assert bool((dw1[:, :16] == 0).all())  # the other half of the chunk gets no gradient
+    assert set(g1) == set(g0) and any(n.endswith("conv_fuse.bias") for n in g0)
+    for n in g0:
+        assert torch.equal(g1[n], g0[n]), n

@@ -55,6 +55,18 @@ class _ConvBase(FakeQuantize):
         c = self.conv_fuse
         return F.conv2d(x, weights, bias, stride=c.stride, padding=c.padding, dilation=c.dilation, groups=c.groups)
 
+    @staticmethod
+    def _dense_input(x):
+        """A channel slice of a channels_last tensor (``chunk`` / ``split`` along dim 1, as in C2f blocks: stride(1) == 1
+        but pitched rows) is made dense ONCE, here.  cuDNN needs a dense tensor, so ATen would copy it inside the
+        convolution anyway -- in the forward and AGAIN in the backward, because autograd saves the view -- and the layer
+        would fall off the channels_last epilogue (separate bias-add pass, separate bias-gradient reduction, separate
+        observer pass while calibrating).  Same values, so every result is unchanged."""
+        if (x.dim() == 4 and x.is_cuda and x.shape[1] > 1 and x.stride(1) == 1 and not x.is_contiguous()
+                and not x.is_contiguous(memory_format=torch.channels_last)):
+            return x.contiguous(memory_format=torch.channels_last)
+        return x
+
 
 class ConvBnReLU(_ConvBase):
     """Conv2d + BatchNorm2d + ReLU/SiLU (fused.py:32-134).  ``relu`` may be nn.ReLU or nn.SiLU."""
@@ -154,6 +166,7 @@ class ConvBnReLU(_ConvBase):
         every layout, SiLU (what the reference applies whenever ``relu`` is not an nn.ReLU, fused.py:81,133) on
         channels_last tensors."""
         act = "relu" if self.is_relu else "silu"
+        x = self._dense_input(x)
         if (self.fuse_observer_into_epilogue and self._has_act and self.quantize_out
                 and type(self).run_forward_core is ConvBnReLU.run_forward_core):
             y = self._calibration_forward(x, act)
