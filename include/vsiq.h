@@ -250,8 +250,8 @@ int vsiq_bn_reestimate_finish(const float *mean_sum, const float *var_sum, int64
 
 /* ---- host-buffer pipeline (end-to-end entry) ----------------------------------------------
  * Forward + STE backward of one per-tensor quantiser over HOST buffers: x, g -> y, dx.  The range is
- * cut into chunks that flow H2D -> fused kernel -> D2H on `n_slots` streams so the three stages
- * overlap.  Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory);
+ * cut into chunks that flow H2D -> fused kernel -> D2H through `n_slots` sets of device staging buffers on
+ * three event-linked streams (one per engine), so the two copy directions and the kernel overlap.  Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory);
  * pageable memory works but serialises.  The handle owns its device staging buffers and streams
  * (these and vsiq_peer_alloc are the only entry points that allocate).  fwd_bwd returns after everything has landed in y / dx. */
 typedef struct vsiq_host_pipeline vsiq_host_pipeline;
@@ -261,6 +261,8 @@ int vsiq_host_pipeline_fwd_bwd(vsiq_host_pipeline *p, const float *x_host, const
                                float *dx_host, int64_t n, float scale, float zero_point, int qmin, int qmax);
 /* number of kernels the last fwd_bwd call launched (for launch accounting) */
 int64_t vsiq_host_pipeline_last_launches(const vsiq_host_pipeline *p);
+/* host time (ns) the last vsiq_host_pipeline_fwd_bwd call spent submitting its copies and launches, before waiting */
+int64_t vsiq_host_pipeline_last_enqueue_ns(const vsiq_host_pipeline *p);
 
 /* fused forward + STE backward on DEVICE buffers (what the pipeline launches per chunk):
  * one read of x and g, one write of y and dx -- 16 B/element instead of 20. */

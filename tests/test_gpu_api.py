@@ -1039,3 +1039,39 @@ def test_unfused_layer_eval_bn_relu_is_one_pass_under_no_grad():
     n0 = _lib.launch_count
     y2 = layer(x.clone().requires_grad_(True))       # autograd on: ATen's differentiable path
     assert _lib.launch_count == n0 and torch.equal(y2.detach(), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk,slots,n", [(1024, 1, 5000), (4096, 2, 4096 * 7 + 13), (1 << 16, 4, (1 << 20) + 999),
+                                          (1 << 16, 8, 3 * (1 << 16)), (1 << 20, 4, 777)])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_pipeline_matches_the_oracle(chunk, slots, n, pinned):
+    """The end-to-end entry (vsiq_host_pipeline_fwd_bwd: host x, g -> host y, dx through chunked H2D / fused kernel / D2H
+    on three event-linked streams) against the oracle, bit for bit: ragged last chunk, fewer chunks than slots, more
+    chunks than slots (staging buffers re-used behind the events), pinned and pageable buffers, repeated calls on one
+    handle, untouched bytes beyond n."""
+    from vsiquantization_b200 import ops
+    rng = np.random.default_rng(n + slots)
+    s, z, qmin, qmax = 3.0 / 127, 0.0, -128, 127
+    pipe = ops.HostPipeline(chunk, slots)
+    try:
+        for rep in range(3):
+            x = (rng.standard_normal(n) * 3).astype(np.float32)
+            g = rng.standard_normal(n).astype(np.float32)
+            x[::101] = np.nan
+            x[1::103] = np.inf
+            x[2::107] = 1e-42
+            xt, gt = torch.from_numpy(x), torch.from_numpy(g)
+            yt = torch.full((n + 64,), -7.0)
+            dt = torch.full((n + 64,), -7.0)
+            if pinned:
+                xt, gt, yt, dt = xt.pin_memory(), gt.pin_memory(), yt.pin_memory(), dt.pin_memory()
+            y, dx = pipe.fwd_bwd(xt, gt, s, z, qmin, qmax, yt[:n], dt[:n])
+            y_o = oracle.fake_quant_fwd(x, s, z, qmin, qmax)
+            dx_o = oracle.fake_quant_bwd(x, g, s, z, qmin, qmax, want_ds=False)[0]
+            assert bits_equal(y.numpy(), y_o), (rep, first_mismatch(y.numpy(), y_o))
+            assert bits_equal(dx.numpy(), dx_o), (rep, first_mismatch(dx.numpy(), dx_o))
+            assert bool((yt[n:] == -7.0).all()) and bool((dt[n:] == -7.0).all())
+            assert pipe.last_submit_ms >= 0.0
+    finally:
+        pipe.close()

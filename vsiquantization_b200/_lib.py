@@ -84,6 +84,7 @@ _SIGNATURES = {
     "vsiq_host_pipeline_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                            c_int, c_int]),
     "vsiq_host_pipeline_last_launches": (c_int64, [c_void_p]),
+    "vsiq_host_pipeline_last_enqueue_ns": (c_int64, [c_void_p]),
     "vsiq_ci_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "vsiq_ci_fake_quant_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, ctypes.POINTER(QParams), c_int64,
                                        c_void_p, c_size_t, c_void_p]),

@@ -702,9 +702,10 @@ def selftest_division(scale: float, mode: int = 0, device=None) -> int:
 
 
 class HostPipeline:
-    """Forward + STE backward over HOST (ideally pinned) buffers, chunked and overlapped on several streams."""
+    """Forward + STE backward over HOST (ideally pinned) buffers, chunked; H2D, kernel and D2H overlap on three
+    event-linked streams through ``n_slots`` sets of staging buffers (csrc/host_pipeline.cu)."""
 
-    def __init__(self, chunk_elems: int = 1 << 22, n_slots: int = 4, device=None):
+    def __init__(self, chunk_elems: int = 1 << 23, n_slots: int = 4, device=None):
         self._h = ctypes.c_void_p()
         self.device = torch.device(device or "cuda")
         with torch.cuda.device(self.device):
@@ -724,6 +725,11 @@ class HostPipeline:
                   "vsiq_host_pipeline_fwd_bwd")
         _count_launch(int(lib.vsiq_host_pipeline_last_launches(self._h)))
         return y, dx
+
+    @property
+    def last_submit_ms(self) -> float:
+        """Host time the last fwd_bwd call spent submitting copies and launches (before waiting for them)."""
+        return lib.vsiq_host_pipeline_last_enqueue_ns(self._h) / 1e6
 
     def close(self):
         if self._h:
