@@ -258,3 +258,14 @@ def proof_division(scale: float, mode: int = 0, first: int = 0, stride: int = 1)
     covered = ctypes.c_ulonglong(0)
     wrong = _proof.vsiq_proof_division(float(scale), int(mode), int(first), int(stride), ctypes.byref(covered))
     return int(wrong), int(covered.value)
+
+
+def proof_code_magic(lo: float, hi: float, bits: int):
+    """(mismatches, floats visited) of the code-export conversion -- low `bits` mantissa bits of RN(t + 1.5 * 2^23)
+    against (int)rint(t) -- over EVERY float32 in [lo, hi], emulated on the host (oracle/fastpath_proof.c)."""
+    proof_division(1.0, 0, 0, 1 << 31)  # loads (and if needed builds) the library
+    _proof.vsiq_proof_code_magic.restype = ctypes.c_ulonglong
+    _proof.vsiq_proof_code_magic.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
+    covered = ctypes.c_ulonglong(0)
+    wrong = _proof.vsiq_proof_code_magic(float(lo), float(hi), int(bits), ctypes.byref(covered))
+    return int(wrong), int(covered.value)

@@ -67,3 +67,25 @@ unsigned long long vsiq_proof_division(float s, int mode, uint32_t first, uint32
     if (covered) *covered = fast;
     return wrong;
 }
+
+/* Integer-code export (csrc/fake_quant.cu: codes_vec).  On the fast path the pre-rounding clamp leaves t in
+ * [qmin - 0.5, qmax + 0.5]; the kernel then takes the code from the low mantissa bits of RN(t + 1.5 * 2^23) instead of
+ * converting rint(t) (the reference's torch.round + clamp, quantizers/uniform.py:54,95).  vsiq_proof_code_magic walks
+ * EVERY float in [lo, hi] (both signs of zero and all denormals included) and counts the values whose two's-complement
+ * code of `bits` bits differs from (int)rintf(t); *covered receives how many floats were visited. */
+unsigned long long vsiq_proof_code_magic(float lo, float hi, int bits, unsigned long long *covered) {
+    const float magic = 12582912.0f; /* 0x4B400000 */
+    const uint32_t mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+    unsigned long long wrong = 0, seen = 0;
+#pragma omp parallel for reduction(+ : wrong, seen) schedule(static)
+    for (uint64_t u = 0; u < 0x100000000ull; ++u) {
+        const float t = bits_to_float((uint32_t)u);
+        if (!(t >= lo && t <= hi)) continue; /* NaN fails both compares */
+        ++seen;
+        const uint32_t got = float_to_bits(t + magic) & mask;
+        const uint32_t want = (uint32_t)(int32_t)rintf(t) & mask;
+        if (got != want) ++wrong;
+    }
+    if (covered) *covered = seen;
+    return wrong;
+}

@@ -91,3 +91,15 @@ def test_division_free_arithmetic_is_exact_for_every_input(scale):
 def test_division_free_arithmetic_declines_out_of_range_scales():
     for scale in (2.0 ** -41, 2.0 ** 41, 0.0, float("inf"), float("nan")):
         assert oracle.proof_division(scale, 0, 0, 65537) == (0, 0)  # such tiles always run the IEEE sequence
+
+
+@pytest.mark.parametrize("qmin,qmax,bits", [(-8, 7, 4), (0, 15, 4), (-128, 127, 8), (0, 255, 8), (-32768, 32767, 16),
+                                            (0, 65535, 16), (-2, 1, 4), (0, 3, 8)])
+def test_code_export_mantissa_conversion_is_exact_for_every_float(qmin, qmax, bits):
+    """The code-export kernel (csrc/fake_quant.cu: codes_vec) reads the integer code from the low mantissa bits of
+    RN(t + 1.5 * 2^23) instead of converting rint(t).  Emulated on the host over EVERY float32 t the pre-rounding clamp
+    can leave ([qmin - 0.5, qmax + 0.5]: both zeros, all denormals, every tie): identical to (int)rint(t) in two's
+    complement, for each code width and range the ABI admits."""
+    wrong, covered = oracle.proof_code_magic(qmin - 0.5, qmax + 0.5, bits)
+    assert wrong == 0, (qmin, qmax, bits, wrong)
+    assert covered > 2 ** 30  # more than a billion floats live in such an interval (denormals and tiny values included)
