@@ -521,12 +521,25 @@ def run_native(args):
 
     # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside the timed region)
     e2e = None
-    if not args.no_e2e:
+    e2e_ok, e2e_err = not args.no_e2e, None
+    if e2e_ok:
         e2e_n = n
-        xh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
-        gh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
-        yh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
-        dh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
+        xh = gh = yh = dh = None
+        try:  # 16 bytes of page-locked host memory per element and rank
+            xh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
+            gh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
+            yh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
+            dh = torch.empty(e2e_n, dtype=torch.float32, pin_memory=True)
+        except Exception as e:  # noqa: BLE001 -- reported in the line instead of losing it
+            e2e_ok, e2e_err = False, str(e)[:120]
+        if world > 1:  # every rank or none: the timed region below holds collectives
+            flag = torch.tensor([1.0 if e2e_ok else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            e2e_ok = bool(flag.item() == 1.0)
+        if not e2e_ok:
+            e2e = {"error": "pinned host buffers unavailable on some rank: " + (e2e_err or "another rank failed")}
+            del xh, gh, yh, dh
+    if e2e_ok:
         xh.copy_(x)
         gh.copy_(g)
         pipe = ops.HostPipeline(chunk_elems=1 << 23, n_slots=4, device=dev)
